@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+# Build libchessvision_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+mkdir -p build
+$NVCC $FLAGS -c csrc/conv_tc.cu -o build/conv_tc.o &
+$NVCC $FLAGS -c csrc/stem.cu -o build/stem.o &
+$NVCC $FLAGS -fmad=false -c csrc/geometry.cu -o build/geometry.o &
+$NVCC $FLAGS -c csrc/api.cu -o build/api.o &
+wait
+$NVCC -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/geometry.o build/api.o
+echo "built $(pwd)/libchessvision_b200.so"

@@ -1,0 +1,266 @@
+"""ctypes binding of ``libchessvision_b200.so`` (C ABI in ``include/chessvision_b200.h``).
+
+PyTorch is used here only as the owner of device memory and streams: tensors are allocated with torch and their
+``data_ptr()`` is handed to the library.  There is no CPU or PyTorch-eager fallback: if the shared library is missing or
+the device is not sm_100, construction fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent.parent / "libchessvision_b200.so"
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class _Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class _Outputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("logits", "mask", "quad", "found", "status", "board", "probs", "labels", "labels_valid", "fen")]
+
+
+OUTPUT_FIELDS = tuple(n for n, _ in _Outputs._fields_)
+
+# every symbol include/chessvision_b200.h declares: name -> (restype, argtypes)
+_P, _I, _F = C.c_void_p, C.c_int, C.c_float
+SYMBOLS = {
+    "cvb_version": (_I, []),
+    "cvb_create": (_P, [_I, _I]),
+    "cvb_destroy": (None, [_P]),
+    "cvb_last_error": (C.c_char_p, [_P]),
+    "cvb_max_batch": (_I, [_P]),
+    "cvb_load_unet": (_I, [_P, C.POINTER(_Tensor), _I]),
+    "cvb_load_resnet18": (_I, [_P, C.POINTER(_Tensor), _I]),
+    "cvb_resize_area_half": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "cvb_unet_forward": (_I, [_P, _P, _I, _F, _P, _P, _P]),
+    "cvb_mask_from_logits": (_I, [_P, _P, _I, _F, _P, _P]),
+    "cvb_mask_to_quad": (_I, [_P, _P, _I, _P, _P, _P, _P]),
+    "cvb_warp_squares": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "cvb_classify": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
+    "cvb_image_to_fen": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs), _P]),
+    "cvb_image_to_fen_host": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs)]),
+    "cvb_conv2d_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
+    "cvb_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P]),
+    "cvb_launch_count": (C.c_int64, [_P]),
+    "cvb_profile": (_I, [_P, _I]),
+    "cvb_profile_read": (_I, [_P, C.POINTER(C.c_float), _I]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the shared library and bind every declared symbol (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise NativeError(f"{_LIB_PATH} is missing: build it with chessvision-3lc_b200/build.sh "
+                              "(python -c 'import __graft_entry__ as g; g.build()'); there is no fallback path")
+        lib = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _state_dict_array(sd):
+    """torch state_dict -> (ctypes array of cvb_tensor, keep-alive list).  Only floating tensors are passed."""
+    keep, items = [], []
+    for k, v in sd.items():
+        if not torch.is_tensor(v) or not v.is_floating_point():
+            continue
+        a = np.ascontiguousarray(v.detach().cpu().float().numpy())
+        keep.append(a)
+        t = _Tensor()
+        t.name = k.encode()
+        t.data = a.ctypes.data
+        t.ndim = a.ndim
+        for i in range(4):
+            t.shape[i] = a.shape[i] if i < a.ndim else 1
+        items.append(t)
+    arr = (_Tensor * len(items))(*items)
+    return arr, keep
+
+
+class Engine:
+    """One context on one GPU.  All tensor arguments are torch CUDA tensors on that GPU (or host arrays for *_host)."""
+
+    def __init__(self, device: int = 0, max_batch: int = 64):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeError("no CUDA device: the B200 path has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        self.h = self.lib.cvb_create(device, max_batch)
+        if not self.h:
+            raise NativeError("cvb_create failed (see stderr): the library needs an sm_100 GPU and enough free memory")
+        self.max_batch = max_batch
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cvb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise NativeError(f"{what} failed ({rc}): {self.lib.cvb_last_error(self.h).decode()}")
+
+    # ---- weights
+    def load_unet(self, state_dict):
+        arr, keep = _state_dict_array(state_dict)
+        self._ck(self.lib.cvb_load_unet(self.h, arr, len(arr)), "cvb_load_unet")
+
+    def load_resnet18(self, state_dict):
+        arr, keep = _state_dict_array(state_dict)
+        self._ck(self.lib.cvb_load_resnet18(self.h, arr, len(arr)), "cvb_load_resnet18")
+
+    # ---- stages (device tensors)
+    def resize_area_half(self, img):
+        n, h2, w2, _ = img.shape
+        out = torch.empty((n, h2 // 2, w2 // 2, 3), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_resize_area_half(self.h, _ptr(img), n, h2 // 2, w2 // 2, _ptr(out), _stream()), "cvb_resize_area_half")
+        return out
+
+    def unet_forward(self, img, threshold=0.5):
+        n = img.shape[0]
+        assert img.dtype == torch.uint8 and tuple(img.shape[1:]) == (512, 512, 3) and img.is_contiguous()
+        logits = torch.empty((n, 256, 256), dtype=torch.float32, device=self.device)
+        mask = torch.empty((n, 256, 256), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_unet_forward(self.h, _ptr(img), n, threshold, _ptr(logits), _ptr(mask), _stream()), "cvb_unet_forward")
+        return logits, mask
+
+    def mask_from_logits(self, logits, threshold=0.5):
+        n = logits.shape[0]
+        mask = torch.empty((n, 256, 256), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_mask_from_logits(self.h, _ptr(logits), n, threshold, _ptr(mask), _stream()), "cvb_mask_from_logits")
+        return mask
+
+    def mask_to_quad(self, mask):
+        n = mask.shape[0]
+        assert mask.dtype == torch.uint8 and tuple(mask.shape[1:]) == (256, 256) and mask.is_contiguous()
+        quad = torch.empty((n, 4, 2), dtype=torch.int32, device=self.device)
+        found = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        status = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.cvb_mask_to_quad(self.h, _ptr(mask), n, _ptr(quad), _ptr(found), _ptr(status), _stream()), "cvb_mask_to_quad")
+        return quad, found, status
+
+    def warp_squares(self, img, quad, found):
+        n, H, W, _ = img.shape
+        board = torch.empty((n, 512, 512), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_warp_squares(self.h, _ptr(img), _ptr(quad), _ptr(found), n, H, W, _ptr(board), _stream()), "cvb_warp_squares")
+        return board
+
+    def classify(self, board, flip=False):
+        n = board.shape[0]
+        probs = torch.empty((n, 64, 13), dtype=torch.float32, device=self.device)
+        labels = torch.empty((n, 64), dtype=torch.uint8, device=self.device)
+        labels_valid = torch.empty((n, 64), dtype=torch.uint8, device=self.device)
+        fen = torch.empty((n, 2, 72), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_classify(self.h, _ptr(board), n, int(flip), _ptr(probs), _ptr(labels), _ptr(labels_valid), _ptr(fen),
+                                       _stream()), "cvb_classify")
+        return probs, labels, labels_valid, fen
+
+    def alloc_outputs(self, n, full=False, pinned_host=False):
+        """Allocate the cvb_outputs buffers (device, or pinned host when ``pinned_host``)."""
+        kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=self.device)
+        out = {
+            "quad": torch.empty((n, 4, 2), dtype=torch.int32, **kw),
+            "found": torch.empty((n,), dtype=torch.uint8, **kw),
+            "status": torch.empty((n,), dtype=torch.int32, **kw),
+            "probs": torch.empty((n, 64, 13), dtype=torch.float32, **kw),
+            "labels": torch.empty((n, 64), dtype=torch.uint8, **kw),
+            "labels_valid": torch.empty((n, 64), dtype=torch.uint8, **kw),
+            "fen": torch.empty((n, 2, 72), dtype=torch.uint8, **kw),
+        }
+        if full:
+            out["logits"] = torch.empty((n, 256, 256), dtype=torch.float32, **kw)
+            out["mask"] = torch.empty((n, 256, 256), dtype=torch.uint8, **kw)
+            out["board"] = torch.empty((n, 512, 512), dtype=torch.uint8, **kw)
+        return out
+
+    @staticmethod
+    def _outputs_struct(out):
+        o = _Outputs()
+        for name in OUTPUT_FIELDS:
+            t = out.get(name)
+            setattr(o, name, None if t is None else t.data_ptr())
+        return o
+
+    def image_to_fen(self, img, out, threshold=0.5, flip=False):
+        n = img.shape[0]
+        assert img.is_cuda and img.dtype == torch.uint8 and tuple(img.shape[1:]) == (512, 512, 3) and img.is_contiguous()
+        o = self._outputs_struct(out)
+        self._ck(self.lib.cvb_image_to_fen(self.h, _ptr(img), n, threshold, int(flip), C.byref(o), _stream()), "cvb_image_to_fen")
+        return out
+
+    def image_to_fen_host(self, img_host, out_host, threshold=0.5, flip=False):
+        """img_host: torch CPU uint8 [N,512,512,3] (pinned for overlap) ; out_host: dict of CPU tensors."""
+        n = img_host.shape[0]
+        assert not img_host.is_cuda and img_host.dtype == torch.uint8 and img_host.is_contiguous()
+        o = self._outputs_struct(out_host)
+        self._ck(self.lib.cvb_image_to_fen_host(self.h, C.c_void_p(img_host.data_ptr()), n, threshold, int(flip), C.byref(o)),
+                 "cvb_image_to_fen_host")
+        return out_host
+
+    # ---- building blocks for parity tests
+    def conv2d_f16(self, x, w_packed, bias, ksize, stride, relu, residual=None):
+        n, h, w, cin = x.shape
+        cout = w_packed.shape[0]
+        out = torch.empty((n, h // stride, w // stride, cout), dtype=torch.float16, device=self.device)
+        self._ck(self.lib.cvb_conv2d_f16(self.h, _ptr(x), n, h, w, cin, _ptr(w_packed), _ptr(bias), cout, ksize, stride, int(relu),
+                                         _ptr(residual), _ptr(out), _stream()), "cvb_conv2d_f16")
+        return out
+
+    def convt2x2_f16(self, x, w_packed, bias4, cout, out, out_c_off):
+        n, h, w, cin = x.shape
+        self._ck(self.lib.cvb_convt2x2_f16(self.h, _ptr(x), n, h, w, cin, _ptr(w_packed), _ptr(bias4), cout, _ptr(out), out.shape[3],
+                                           out_c_off, _stream()), "cvb_convt2x2_f16")
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.cvb_launch_count(self.h))
+
+    def profile(self, enable: bool):
+        self._ck(self.lib.cvb_profile(self.h, int(enable)), "cvb_profile")
+
+    def profile_read(self):
+        buf = (C.c_float * 7)()
+        self._ck(self.lib.cvb_profile_read(self.h, buf, 7), "cvb_profile_read")
+        names = ("unet_conv_tc", "unet_aux", "mask_to_quad", "warp", "resnet_stem", "resnet_conv_tc", "head")
+        return dict(zip(names, [float(v) for v in buf]))
+
+
+def fen_strings(fen_tensor):
+    """uint8 [N,2,72] -> list of (original_fen, fen)."""
+    a = fen_tensor.cpu().numpy()
+    out = []
+    for i in range(a.shape[0]):
+        out.append(tuple(bytes(a[i, j]).split(b"\0", 1)[0].decode() for j in range(2)))
+    return out

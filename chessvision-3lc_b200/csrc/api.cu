@@ -1,0 +1,812 @@
+// C ABI of the B200-native image->FEN path (include/chessvision_b200.h): context, weight folding/packing, the static
+// launch plan of both networks, the per-chunk pipeline and the host<->device streaming entry point.
+#include "../../include/chessvision_b200.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "conv_tc.h"
+#include "kernels.h"
+
+using namespace cvb;
+
+namespace {
+
+constexpr int kStages = 7;
+constexpr int kMaxProfileEvents = 8192;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct ConvWeights {
+    __half* w = nullptr;   // [rows][K]
+    float* bias = nullptr; // [rows]
+    int rows = 0, K = 0;
+};
+
+}  // namespace
+
+struct cvb_ctx {
+    int device = 0;
+    int max_batch = 0;
+    int sm_count = 148;
+    std::string err;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+
+    // ---- UNet
+    bool unet_loaded = false;
+    float *stem_w = nullptr, *stem_b = nullptr;        // inc.double_conv.0 folded, fp32 [27][64], [64]
+    float* outc_w = nullptr;                           // [64]
+    float outc_b = 0.f;
+    std::vector<ConvWeights> unet_w;                   // 17 conv3x3 + 4 convT, in plan order
+    __half *cat0, *t0, *p1, *t1, *cat1, *p2, *t2, *cat2, *p3, *t3, *cat3, *p4, *t4, *x5, *u1, *u2, *u3;
+    std::vector<ConvLaunch> unet_plan;                 // indices documented in build_unet_plan
+    float* ws_logits = nullptr;                        // [B,256,256]
+    uint8_t* ws_mask = nullptr;                        // [B,256,256]
+
+    // ---- geometry
+    int32_t *ws_quad = nullptr, *ws_status = nullptr, *ws_ncont = nullptr, *ws_owner = nullptr;
+    uint8_t* ws_found = nullptr;
+    double* ws_minv = nullptr;
+    uint8_t* ws_board = nullptr;                       // [B,512,512]
+
+    // ---- ResNet-18
+    bool resnet_loaded = false;
+    float *rstem_w = nullptr, *rstem_b = nullptr;      // conv1+bn1 folded fp32 [49][64], [64]
+    float *fc_w = nullptr, *fc_b = nullptr;            // [13][512], [13]
+    std::vector<ConvWeights> res_w;
+    __half* rbuf[12] = {nullptr};                      // 3 per resolution level
+    std::vector<ConvLaunch> res_plan;
+    float* ws_probs = nullptr;
+    uint8_t *ws_labels = nullptr, *ws_labels_valid = nullptr;
+    char* ws_fen = nullptr;
+
+    // ---- host streaming
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    uint8_t* slot_img[2] = {nullptr, nullptr};
+    // per-slot device outputs for the host path
+    cvb_outputs slot_out[2];
+
+    // ---- profiling
+    bool profile = false;
+    std::vector<cudaEvent_t> pev;
+    std::vector<int> pev_stage;
+    int pev_used = 0;
+    float stage_ms[kStages] = {0};
+};
+
+namespace {
+
+int fail(cvb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(ctx, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+int dalloc(cvb_ctx* ctx, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, -3, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    ctx->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+const cvb_tensor* find(const cvb_tensor* sd, int n, const std::string& name) {
+    for (int i = 0; i < n; ++i)
+        if (name == sd[i].name) return &sd[i];
+    return nullptr;
+}
+
+int64_t numel(const cvb_tensor* t) {
+    int64_t k = 1;
+    for (int i = 0; i < t->ndim; ++i) k *= t->shape[i];
+    return k;
+}
+
+struct Bn {
+    std::vector<float> scale, shift;
+};
+
+// BatchNorm2d(eval, eps 1e-5): y = x*scale + shift
+int load_bn(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& prefix, int C, Bn& bn) {
+    const cvb_tensor* g = find(sd, n, prefix + ".weight");
+    const cvb_tensor* b = find(sd, n, prefix + ".bias");
+    const cvb_tensor* m = find(sd, n, prefix + ".running_mean");
+    const cvb_tensor* v = find(sd, n, prefix + ".running_var");
+    if (!g || !b || !m || !v) return fail(ctx, -4, "state_dict lacks BatchNorm tensors '%s.*'", prefix.c_str());
+    if (numel(g) != C || numel(b) != C || numel(m) != C || numel(v) != C) return fail(ctx, -4, "bad BatchNorm shape at '%s'", prefix.c_str());
+    bn.scale.resize(C);
+    bn.shift.resize(C);
+    for (int c = 0; c < C; ++c) {
+        const double s = static_cast<double>(g->data[c]) / sqrt(static_cast<double>(v->data[c]) + 1e-5);
+        bn.scale[c] = static_cast<float>(s);
+        bn.shift[c] = static_cast<float>(static_cast<double>(b->data[c]) - static_cast<double>(m->data[c]) * s);
+    }
+    return 0;
+}
+
+int upload_conv(cvb_ctx* ctx, const std::vector<__half>& w, const std::vector<float>& bias, int rows, int K, ConvWeights& out) {
+    if (dalloc(ctx, &out.w, w.size())) return -3;
+    if (dalloc(ctx, &out.bias, bias.size())) return -3;
+    CK(cudaMemcpy(out.w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(out.bias, bias.data(), bias.size() * sizeof(float), cudaMemcpyHostToDevice));
+    out.rows = rows;
+    out.K = K;
+    return 0;
+}
+
+// Conv2d weight [Cout][Cin][k][k] (+BN) -> fp16 [Cout][(r*k+s)*Cin + ci], bias fp32 [Cout]
+int pack_conv(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv, const std::string& bn_prefix, int Cout,
+              int Cin, int k, ConvWeights& out) {
+    const cvb_tensor* w = find(sd, n, conv + ".weight");
+    if (!w) return fail(ctx, -4, "state_dict lacks '%s.weight'", conv.c_str());
+    if (numel(w) != 1LL * Cout * Cin * k * k) return fail(ctx, -4, "bad shape for '%s.weight'", conv.c_str());
+    Bn bn;
+    if (load_bn(ctx, sd, n, bn_prefix, Cout, bn)) return -4;
+    const int K = k * k * Cin;
+    std::vector<__half> pw(static_cast<size_t>(Cout) * K);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int r = 0; r < k; ++r)
+                for (int s = 0; s < k; ++s) {
+                    const float v = w->data[((static_cast<size_t>(co) * Cin + ci) * k + r) * k + s] * bn.scale[co];
+                    pw[static_cast<size_t>(co) * K + (r * k + s) * Cin + ci] = __float2half_rn(v);
+                }
+    return upload_conv(ctx, pw, bn.shift, Cout, K, out);
+}
+
+// ConvTranspose2d weight [Cin][Cout][2][2] + bias[Cout] -> fp16 [(dy*2+dx)*Cout + co][Cin], bias fp32 [4*Cout]
+int pack_convt(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& name, int Cin, int Cout, ConvWeights& out) {
+    const cvb_tensor* w = find(sd, n, name + ".weight");
+    const cvb_tensor* b = find(sd, n, name + ".bias");
+    if (!w || !b) return fail(ctx, -4, "state_dict lacks '%s.{weight,bias}'", name.c_str());
+    if (numel(w) != 4LL * Cin * Cout || numel(b) != Cout) return fail(ctx, -4, "bad shape for '%s'", name.c_str());
+    std::vector<__half> pw(static_cast<size_t>(4) * Cout * Cin);
+    std::vector<float> pb(static_cast<size_t>(4) * Cout);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx)
+                    pw[(static_cast<size_t>(dy * 2 + dx) * Cout + co) * Cin + ci] =
+                        __float2half_rn(w->data[((static_cast<size_t>(ci) * Cout + co) * 2 + dy) * 2 + dx]);
+    for (int q = 0; q < 4; ++q)
+        for (int co = 0; co < Cout; ++co) pb[static_cast<size_t>(q) * Cout + co] = b->data[co];
+    return upload_conv(ctx, pw, pb, 4 * Cout, Cin, out);
+}
+
+// tiny-K first layers stay fp32 on CUDA cores: [k*k*Cin][64] with BN folded
+int pack_stem(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv, const std::string& bn_prefix, int Cin, int k,
+              float** d_w, float** d_b) {
+    const cvb_tensor* w = find(sd, n, conv + ".weight");
+    if (!w || numel(w) != 64LL * Cin * k * k) return fail(ctx, -4, "missing/bad '%s.weight'", conv.c_str());
+    Bn bn;
+    if (load_bn(ctx, sd, n, bn_prefix, 64, bn)) return -4;
+    std::vector<float> pw(static_cast<size_t>(k) * k * Cin * 64);
+    for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int r = 0; r < k; ++r)
+                for (int s = 0; s < k; ++s)
+                    pw[(static_cast<size_t>(r * k + s) * Cin + ci) * 64 + co] =
+                        w->data[((static_cast<size_t>(co) * Cin + ci) * k + r) * k + s] * bn.scale[co];
+    if (dalloc(ctx, d_w, pw.size()) || dalloc(ctx, d_b, 64)) return -3;
+    CK(cudaMemcpy(*d_w, pw.data(), pw.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(*d_b, bn.shift.data(), 64 * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+void pick_tile(int Ho, int Wo, int& tn, int& th, int& tw) {
+    tw = Wo < 16 ? Wo : 16;
+    th = 128 / tw;
+    if (th > Ho) th = Ho;
+    tn = 128 / (tw * th);
+}
+
+// Describe one conv (ksize 1|3, stride 1|2, pad ksize/2) over an NHWC fp16 buffer whose pixel stride is in_c_stride.
+int build_conv(cvb_ctx* ctx, ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int in_c_stride, int in_c_off, int Cin,
+               const ConvWeights& cw, int ksize, int stride, int epilogue) {
+    memset(&L, 0, sizeof L);
+    ConvParams& p = L.p;
+    const int Ho = Hin / stride, Wo = Win / stride;
+    if (Cin % 64 || cw.K != ksize * ksize * Cin) return fail(ctx, -5, "conv: Cin=%d K=%d ksize=%d not supported", Cin, cw.K, ksize);
+    pick_tile(Ho, Wo, p.tn, p.th, p.tw);
+    if (Wo % p.tw || Ho % p.th || p.tn * p.th * p.tw != 128) return fail(ctx, -5, "conv: %dx%d output cannot be tiled", Ho, Wo);
+    p.H = Ho;
+    p.W = Wo;
+    p.tiles_w = Wo / p.tw;
+    p.tiles_h = Ho / p.th;
+    p.taps = ksize * ksize;
+    p.c_chunks = Cin / 64;
+    p.a_c_off = in_c_off;
+    const int64_t sW = in_c_stride, sH = static_cast<int64_t>(Win) * in_c_stride, sN = static_cast<int64_t>(Hin) * Win * in_c_stride;
+    int rc = 0;
+    if (stride == 1) {
+        rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, p.th, p.tn);
+        for (int r = 0; r < ksize; ++r)
+            for (int s = 0; s < ksize; ++s) {
+                p.tap_map[r * ksize + s] = 0;
+                p.tap_dy[r * ksize + s] = static_cast<int8_t>(r - ksize / 2);
+                p.tap_dx[r * ksize + s] = static_cast<int8_t>(s - ksize / 2);
+            }
+    } else {
+        // stride 2: four parity views (py,px) of the input, each with doubled strides; tap r reads parity (r+1)&1 at
+        // view offset -1 (r == 0) or 0, and the zero fill of the view at -1 is exactly the padding row/column.
+        for (int py = 0; py < 2 && !rc; ++py)
+            for (int px = 0; px < 2 && !rc; ++px)
+                rc = tmap_act(&p.a_map[py * 2 + px], in + (static_cast<int64_t>(py) * Win + px) * in_c_stride, in_c_stride,
+                              Win / 2, Hin / 2, Nmax, 2 * sW, 2 * sH, sN, p.tw, p.th, p.tn);
+        for (int r = 0; r < ksize; ++r)
+            for (int s = 0; s < ksize; ++s) {
+                const int rr = ksize == 1 ? 1 : r, ss = ksize == 1 ? 1 : s;  // 1x1: the centre tap
+                const int py = (rr + 1) & 1, px = (ss + 1) & 1;
+                p.tap_map[r * ksize + s] = static_cast<int8_t>(py * 2 + px);
+                p.tap_dy[r * ksize + s] = static_cast<int8_t>(rr == 0 ? -1 : 0);
+                p.tap_dx[r * ksize + s] = static_cast<int8_t>(ss == 0 ? -1 : 0);
+            }
+    }
+    if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (activations) failed: %d", rc);
+    L.block_n = cw.rows % 256 == 0 ? 256 : (cw.rows % 128 == 0 ? 128 : 64);
+    if (epilogue == EPI_OUTC) L.block_n = 64;
+    if (cw.rows % L.block_n) return fail(ctx, -5, "conv: Cout=%d not a multiple of %d", cw.rows, L.block_n);
+    p.n_tiles = cw.rows / L.block_n;
+    rc = tmap_weights(&p.b_map, cw.w, cw.K, cw.rows, L.block_n);
+    if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (weights) failed: %d", rc);
+    p.bias = cw.bias;
+    L.epilogue = epilogue;
+    return 0;
+}
+
+void set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride) {
+    L.p.out = out;
+    L.p.out_c_stride = out_c_stride;
+    L.p.out_c_off = out_c_off;
+    L.p.relu = relu;
+    L.p.res = res;
+    L.p.res_c_stride = res_c_stride;
+}
+
+// ------------------------------------------------------------------------------------------------------ profiling
+struct StageTimer {
+    cvb_ctx* c;
+    cudaStream_t s;
+    bool on;
+    StageTimer(cvb_ctx* ctx, int stage, cudaStream_t st) : c(ctx), s(st), on(false) {
+        if (!c->profile || c->pev_used + 2 > static_cast<int>(c->pev.size())) return;
+        on = true;
+        c->pev_stage[c->pev_used] = stage;
+        cudaEventRecord(c->pev[c->pev_used], s);
+    }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(c->pev[c->pev_used + 1], s);
+        c->pev_used += 2;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------ stages
+int run_conv(cvb_ctx* ctx, ConvLaunch& L, int n, cudaStream_t s) {
+    CK(conv_launch(L, n, ctx->sm_count, s));
+    ctx->launches++;
+    return 0;
+}
+
+int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logits, uint8_t* mask, cudaStream_t s) {
+    if (!ctx->unet_loaded) return fail(ctx, -7, "UNet weights not loaded (call cvb_load_unet)");
+    auto& P = ctx->unet_plan;
+    auto aux = [&](cudaError_t e) { ctx->launches++; return e; };
+    {
+        StageTimer t(ctx, 1, s);
+        CK(aux(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, ctx->t0, n, 256, 256, 64, s)));
+    }
+    { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[0], n, s)) return -2; }                       // inc.3      t0 -> cat0[0:64)
+    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat0, ctx->p1, n, 256, 256, 64, 128, s))); }
+    { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[1], n, s) || run_conv(ctx, P[2], n, s)) return -2; }   // down1
+    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat1, ctx->p2, n, 128, 128, 128, 256, s))); }
+    { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[3], n, s) || run_conv(ctx, P[4], n, s)) return -2; }   // down2
+    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat2, ctx->p3, n, 64, 64, 256, 512, s))); }
+    { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[5], n, s) || run_conv(ctx, P[6], n, s)) return -2; }   // down3
+    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat3, ctx->p4, n, 32, 32, 512, 1024, s))); }
+    {
+        StageTimer t(ctx, 0, s);
+        for (int i = 7; i <= 19; ++i)                                                             // down4, up1..up4.conv0
+            if (run_conv(ctx, P[i], n, s)) return -2;
+        ConvLaunch& last = P[20];                                                                 // up4.conv3 + outc
+        last.p.logits = logits ? logits : ctx->ws_logits;
+        last.p.mask = mask ? mask : ctx->ws_mask;
+        last.p.thr = thr;
+        if (run_conv(ctx, last, n, s)) return -2;
+    }
+    return 0;
+}
+
+int classify(cvb_ctx* ctx, const uint8_t* board, int n, int flip, float* probs, uint8_t* labels, uint8_t* labels_valid, char* fen,
+             cudaStream_t s) {
+    if (!ctx->resnet_loaded) return fail(ctx, -7, "classifier weights not loaded (call cvb_load_resnet18)");
+    {
+        StageTimer t(ctx, 4, s);
+        CK(launch_resnet_stem(board, ctx->rstem_w, ctx->rstem_b, ctx->rbuf[0], n, s));
+        ctx->launches++;
+    }
+    {
+        StageTimer t(ctx, 5, s);
+        for (auto& L : ctx->res_plan)
+            if (run_conv(ctx, L, n * 64, s)) return -2;
+    }
+    {
+        StageTimer t(ctx, 6, s);
+        CK(launch_head(ctx->rbuf[10], ctx->fc_w, ctx->fc_b, probs ? probs : ctx->ws_probs, labels ? labels : ctx->ws_labels,
+                       labels_valid ? labels_valid : ctx->ws_labels_valid, fen ? fen : ctx->ws_fen, n, flip, s));
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int pipeline_chunk(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s) {
+    float* logits = o.logits ? o.logits + off * 65536 : nullptr;
+    uint8_t* mask = o.mask ? o.mask + off * 65536 : ctx->ws_mask;
+    int32_t* quad = o.quad ? o.quad + off * 8 : ctx->ws_quad;
+    uint8_t* found = o.found ? o.found + off : ctx->ws_found;
+    int32_t* status = o.status ? o.status + off : ctx->ws_status;
+    uint8_t* board = o.board ? o.board + off * 262144 : ctx->ws_board;
+    if (unet_forward(ctx, img, n, thr, logits, mask, s)) return -2;
+    {
+        StageTimer t(ctx, 2, s);
+        CK(launch_mask_to_quad(mask, quad, found, status, ctx->ws_ncont, ctx->ws_owner, n, s));
+        ctx->launches++;
+    }
+    {
+        StageTimer t(ctx, 3, s);
+        CK(launch_homography(quad, found, ctx->ws_minv, n, 2.0f, 512, 512, s));
+        CK(launch_warp_board(img, ctx->ws_minv, found, board, n, 512, 512, s));
+        ctx->launches += 2;
+    }
+    return classify(ctx, board, n, flip, o.probs ? o.probs + off * 832 : nullptr, o.labels ? o.labels + off * 64 : nullptr,
+                    o.labels_valid ? o.labels_valid + off * 64 : nullptr, o.fen ? o.fen + off * 144 : nullptr, s);
+}
+
+int set_device(cvb_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================================
+// exported functions
+// ====================================================================================================================
+extern "C" {
+
+int cvb_version(void) { return 100; }
+
+const char* cvb_last_error(const cvb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int cvb_max_batch(const cvb_ctx* ctx) { return ctx ? ctx->max_batch : 0; }
+int64_t cvb_launch_count(const cvb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+cvb_ctx* cvb_create(int device, int max_batch) {
+    if (max_batch <= 0) return nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return nullptr;
+    cvb_ctx* ctx = new cvb_ctx();
+    ctx->device = device;
+    ctx->max_batch = max_batch;
+    auto bail = [&]() -> cvb_ctx* {
+        fprintf(stderr, "cvb_create: %s\n", ctx->err.c_str());
+        cvb_destroy(ctx);
+        return nullptr;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(); }
+    if (prop.major != 10) {
+        ctx->err = "this library contains sm_100a code only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return bail();
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (tmap_init()) { ctx->err = "cuTensorMapEncodeTiled not available from the driver"; return bail(); }
+    if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_quad() != cudaSuccess) {
+        ctx->err = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        return bail();
+    }
+    const size_t B = max_batch;
+    int rc = 0;
+    // UNet activations (fp16 NHWC)
+    rc |= dalloc(ctx, &ctx->cat0, B * 256 * 256 * 128);
+    rc |= dalloc(ctx, &ctx->t0, B * 256 * 256 * 64);
+    rc |= dalloc(ctx, &ctx->p1, B * 128 * 128 * 64);
+    rc |= dalloc(ctx, &ctx->t1, B * 128 * 128 * 128);
+    rc |= dalloc(ctx, &ctx->cat1, B * 128 * 128 * 256);
+    rc |= dalloc(ctx, &ctx->p2, B * 64 * 64 * 128);
+    rc |= dalloc(ctx, &ctx->t2, B * 64 * 64 * 256);
+    rc |= dalloc(ctx, &ctx->cat2, B * 64 * 64 * 512);
+    rc |= dalloc(ctx, &ctx->p3, B * 32 * 32 * 256);
+    rc |= dalloc(ctx, &ctx->t3, B * 32 * 32 * 512);
+    rc |= dalloc(ctx, &ctx->cat3, B * 32 * 32 * 1024);
+    rc |= dalloc(ctx, &ctx->p4, B * 16 * 16 * 512);
+    rc |= dalloc(ctx, &ctx->t4, B * 16 * 16 * 1024);
+    rc |= dalloc(ctx, &ctx->x5, B * 16 * 16 * 1024);
+    rc |= dalloc(ctx, &ctx->u1, B * 32 * 32 * 512);
+    rc |= dalloc(ctx, &ctx->u2, B * 64 * 64 * 256);
+    rc |= dalloc(ctx, &ctx->u3, B * 128 * 128 * 128);
+    rc |= dalloc(ctx, &ctx->ws_logits, B * 65536);
+    rc |= dalloc(ctx, &ctx->ws_mask, B * 65536);
+    // geometry
+    rc |= dalloc(ctx, &ctx->ws_quad, B * 8);
+    rc |= dalloc(ctx, &ctx->ws_status, B);
+    rc |= dalloc(ctx, &ctx->ws_ncont, B);
+    rc |= dalloc(ctx, &ctx->ws_owner, B * (kQuadMaxBorders + 8));
+    rc |= dalloc(ctx, &ctx->ws_found, B);
+    rc |= dalloc(ctx, &ctx->ws_minv, B * 9);
+    rc |= dalloc(ctx, &ctx->ws_board, B * 262144);
+    // classifier activations: 3 buffers per level; per square 16x16x64, 8x8x128, 4x4x256, 2x2x512 = 16384..2048 halfs
+    for (int lvl = 0; lvl < 4 && !rc; ++lvl)
+        for (int k = 0; k < 3 && !rc; ++k) rc |= dalloc(ctx, &ctx->rbuf[lvl * 3 + k], B * 64 * (16384 >> lvl));
+    rc |= dalloc(ctx, &ctx->ws_probs, B * 64 * 13);
+    rc |= dalloc(ctx, &ctx->ws_labels, B * 64);
+    rc |= dalloc(ctx, &ctx->ws_labels_valid, B * 64);
+    rc |= dalloc(ctx, &ctx->ws_fen, B * 144);
+    if (rc) return bail();
+    // host streaming resources
+    bool ok = cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) {
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
+        memset(&ctx->slot_out[i], 0, sizeof(cvb_outputs));
+        if (ok) ok = dalloc(ctx, &ctx->slot_img[i], B * 512 * 512 * 3) == 0;
+        if (ok) ok = dalloc(ctx, &ctx->slot_out[i].quad, B * 8) == 0 && dalloc(ctx, &ctx->slot_out[i].found, B) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].status, B) == 0 && dalloc(ctx, &ctx->slot_out[i].probs, B * 832) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].labels, B * 64) == 0 && dalloc(ctx, &ctx->slot_out[i].labels_valid, B * 64) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].fen, B * 144) == 0 && dalloc(ctx, &ctx->slot_out[i].logits, B * 65536) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].mask, B * 65536) == 0 && dalloc(ctx, &ctx->slot_out[i].board, B * 262144) == 0;
+    }
+    if (!ok) {
+        if (ctx->err.empty()) ctx->err = "stream/event/slot setup failed";
+        return bail();
+    }
+    return ctx;
+}
+
+void cvb_destroy(cvb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->allocs) cudaFree(p);
+    for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
+        if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    delete ctx;
+}
+
+int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
+    if (!ctx || !sd) return -1;
+    if (set_device(ctx)) return -2;
+    if (ctx->unet_loaded) return fail(ctx, -8, "UNet weights already loaded");
+    const int B = ctx->max_batch;
+    static const int width[5] = {64, 128, 256, 512, 1024};
+    if (pack_stem(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, &ctx->stem_w, &ctx->stem_b)) return -4;
+    ctx->unet_w.resize(21);
+    auto& W = ctx->unet_w;
+    int wi = 0;
+    // 0: inc.3 | 1..8: down{1..4}.{0,3} | then per up block: up, conv0, conv3
+    if (pack_conv(ctx, sd, n, "inc.double_conv.3", "inc.double_conv.4", 64, 64, 3, W[wi++])) return -4;
+    for (int d = 1; d <= 4; ++d) {
+        const std::string pre = "down" + std::to_string(d) + ".maxpool_conv.1.double_conv.";
+        if (pack_conv(ctx, sd, n, pre + "0", pre + "1", width[d], width[d - 1], 3, W[wi++])) return -4;
+        if (pack_conv(ctx, sd, n, pre + "3", pre + "4", width[d], width[d], 3, W[wi++])) return -4;
+    }
+    for (int u = 1; u <= 4; ++u) {
+        const int cin = width[5 - u], cout = width[4 - u];
+        const std::string pre = "up" + std::to_string(u);
+        if (pack_convt(ctx, sd, n, pre + ".up", cin, cin / 2, W[wi++])) return -4;
+        if (pack_conv(ctx, sd, n, pre + ".conv.double_conv.0", pre + ".conv.double_conv.1", cout, cin, 3, W[wi++])) return -4;
+        if (pack_conv(ctx, sd, n, pre + ".conv.double_conv.3", pre + ".conv.double_conv.4", cout, cout, 3, W[wi++])) return -4;
+    }
+    const cvb_tensor* ow = find(sd, n, "outc.conv.weight");
+    const cvb_tensor* ob = find(sd, n, "outc.conv.bias");
+    if (!ow || !ob || numel(ow) != 64 || numel(ob) != 1) return fail(ctx, -4, "missing/bad outc.conv tensors");
+    if (dalloc(ctx, &ctx->outc_w, 64)) return -3;
+    CK(cudaMemcpy(ctx->outc_w, ow->data, 64 * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->outc_b = ob->data[0];
+
+    // launch plan (see unet_forward for the order)
+    auto& P = ctx->unet_plan;
+    P.resize(21);
+    int rc = 0;
+    // encoder
+    rc |= build_conv(ctx, P[0], ctx->t0, B, 256, 256, 64, 0, 64, W[0], 3, 1, EPI_STORE);      set_store(P[0], ctx->cat0, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[1], ctx->p1, B, 128, 128, 64, 0, 64, W[1], 3, 1, EPI_STORE);      set_store(P[1], ctx->t1, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[2], ctx->t1, B, 128, 128, 128, 0, 128, W[2], 3, 1, EPI_STORE);    set_store(P[2], ctx->cat1, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[3], ctx->p2, B, 64, 64, 128, 0, 128, W[3], 3, 1, EPI_STORE);      set_store(P[3], ctx->t2, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[4], ctx->t2, B, 64, 64, 256, 0, 256, W[4], 3, 1, EPI_STORE);      set_store(P[4], ctx->cat2, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[5], ctx->p3, B, 32, 32, 256, 0, 256, W[5], 3, 1, EPI_STORE);      set_store(P[5], ctx->t3, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[6], ctx->t3, B, 32, 32, 512, 0, 512, W[6], 3, 1, EPI_STORE);      set_store(P[6], ctx->cat3, 1024, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[7], ctx->p4, B, 16, 16, 512, 0, 512, W[7], 3, 1, EPI_STORE);      set_store(P[7], ctx->t4, 1024, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[8], ctx->t4, B, 16, 16, 1024, 0, 1024, W[8], 3, 1, EPI_STORE);    set_store(P[8], ctx->x5, 1024, 0, 1, nullptr, 0);
+    // decoder: convT writes the upper channel half of the concat buffer (torch.cat([skip, up]), unet_parts.py:67)
+    rc |= build_conv(ctx, P[9], ctx->x5, B, 16, 16, 1024, 0, 1024, W[9], 1, 1, EPI_CONVT);    set_store(P[9], ctx->cat3, 1024, 512, 0, nullptr, 0);  P[9].p.convt_cout = 512;
+    rc |= build_conv(ctx, P[10], ctx->cat3, B, 32, 32, 1024, 0, 1024, W[10], 3, 1, EPI_STORE); set_store(P[10], ctx->t3, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[11], ctx->t3, B, 32, 32, 512, 0, 512, W[11], 3, 1, EPI_STORE);    set_store(P[11], ctx->u1, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[12], ctx->u1, B, 32, 32, 512, 0, 512, W[12], 1, 1, EPI_CONVT);    set_store(P[12], ctx->cat2, 512, 256, 0, nullptr, 0);  P[12].p.convt_cout = 256;
+    rc |= build_conv(ctx, P[13], ctx->cat2, B, 64, 64, 512, 0, 512, W[13], 3, 1, EPI_STORE);  set_store(P[13], ctx->t2, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[14], ctx->t2, B, 64, 64, 256, 0, 256, W[14], 3, 1, EPI_STORE);    set_store(P[14], ctx->u2, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[15], ctx->u2, B, 64, 64, 256, 0, 256, W[15], 1, 1, EPI_CONVT);    set_store(P[15], ctx->cat1, 256, 128, 0, nullptr, 0);  P[15].p.convt_cout = 128;
+    rc |= build_conv(ctx, P[16], ctx->cat1, B, 128, 128, 256, 0, 256, W[16], 3, 1, EPI_STORE); set_store(P[16], ctx->t1, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[17], ctx->t1, B, 128, 128, 128, 0, 128, W[17], 3, 1, EPI_STORE);  set_store(P[17], ctx->u3, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[18], ctx->u3, B, 128, 128, 128, 0, 128, W[18], 1, 1, EPI_CONVT);  set_store(P[18], ctx->cat0, 128, 64, 0, nullptr, 0);   P[18].p.convt_cout = 64;
+    rc |= build_conv(ctx, P[19], ctx->cat0, B, 256, 256, 128, 0, 128, W[19], 3, 1, EPI_STORE); set_store(P[19], ctx->t0, 64, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[20], ctx->t0, B, 256, 256, 64, 0, 64, W[20], 3, 1, EPI_OUTC);     // + outc 1x1 + sigmoid/threshold
+    P[20].p.relu = 1;
+    P[20].p.outc_w = ctx->outc_w;
+    P[20].p.outc_b = ctx->outc_b;
+    if (rc) return -5;
+    ctx->unet_loaded = true;
+    return 0;
+}
+
+int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
+    if (!ctx || !sd) return -1;
+    if (set_device(ctx)) return -2;
+    if (ctx->resnet_loaded) return fail(ctx, -8, "classifier weights already loaded");
+    const int S = ctx->max_batch * 64;
+    if (pack_stem(ctx, sd, n, "conv1", "bn1", 1, 7, &ctx->rstem_w, &ctx->rstem_b)) return -4;
+    const cvb_tensor* fw = find(sd, n, "fc.weight");
+    const cvb_tensor* fb = find(sd, n, "fc.bias");
+    if (!fw || !fb || numel(fw) != 13 * 512 || numel(fb) != 13) return fail(ctx, -4, "missing/bad fc tensors");
+    if (dalloc(ctx, &ctx->fc_w, 13 * 512) || dalloc(ctx, &ctx->fc_b, 13)) return -3;
+    CK(cudaMemcpy(ctx->fc_w, fw->data, 13 * 512 * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->fc_b, fb->data, 13 * sizeof(float), cudaMemcpyHostToDevice));
+
+    static const int width[4] = {64, 128, 256, 512};
+    ctx->res_w.reserve(32);
+    ctx->res_plan.reserve(32);
+    int rc = 0;
+    auto add = [&](const std::string& conv, const std::string& bn, const __half* in, int Hin, int cin, int cout, int k, int stride,
+                   __half* out, int relu, const __half* res) {
+        ctx->res_w.emplace_back();
+        if (pack_conv(ctx, sd, n, conv, bn, cout, cin, k, ctx->res_w.back())) { rc = -4; return; }
+        ctx->res_plan.emplace_back();
+        if (build_conv(ctx, ctx->res_plan.back(), in, S, Hin, Hin, cin, 0, cin, ctx->res_w.back(), k, stride, EPI_STORE)) { rc = -5; return; }
+        set_store(ctx->res_plan.back(), out, cout, 0, relu, res, cout);
+    };
+    // Buffers per level: a = rbuf[3l], b = rbuf[3l+1], c = rbuf[3l+2].  Level input arrives in `x`.
+    __half* x = ctx->rbuf[0];  // stem output lives in level-0 buffer a
+    int H = 16;
+    for (int l = 0; l < 4 && !rc; ++l) {
+        const std::string L = "layer" + std::to_string(l + 1);
+        __half *a = ctx->rbuf[3 * l], *b = ctx->rbuf[3 * l + 1], *c = ctx->rbuf[3 * l + 2];
+        const int cout = width[l];
+        if (l == 0) {
+            // x == a
+            add(L + ".0.conv1", L + ".0.bn1", a, H, 64, 64, 3, 1, b, 1, nullptr);
+            add(L + ".0.conv2", L + ".0.bn2", b, H, 64, 64, 3, 1, c, 1, a);
+            add(L + ".1.conv1", L + ".1.bn1", c, H, 64, 64, 3, 1, b, 1, nullptr);
+            add(L + ".1.conv2", L + ".1.bn2", b, H, 64, 64, 3, 1, a, 1, c);
+            x = a;
+        } else {
+            const int cin = width[l - 1];
+            add(L + ".0.conv1", L + ".0.bn1", x, H, cin, cout, 3, 2, a, 1, nullptr);
+            add(L + ".0.downsample.0", L + ".0.downsample.1", x, H, cin, cout, 1, 2, b, 0, nullptr);
+            H /= 2;
+            add(L + ".0.conv2", L + ".0.bn2", a, H, cout, cout, 3, 1, c, 1, b);
+            add(L + ".1.conv1", L + ".1.bn1", c, H, cout, cout, 3, 1, a, 1, nullptr);
+            add(L + ".1.conv2", L + ".1.bn2", a, H, cout, cout, 3, 1, b, 1, c);
+            x = b;
+        }
+    }
+    if (rc) return rc;
+    if (x != ctx->rbuf[10]) return fail(ctx, -9, "internal: unexpected classifier buffer rotation");  // the head reads rbuf[10]
+    ctx->resnet_loaded = true;
+    return 0;
+}
+
+int cvb_resize_area_half(cvb_ctx* ctx, const uint8_t* img, int N, int h, int w, uint8_t* out, void* stream) {
+    if (!ctx || !img || !out || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    CK(launch_resize_area_half(img, out, N, h, w, static_cast<cudaStream_t>(stream)));
+    ctx->launches++;
+    return 0;
+}
+
+int cvb_unet_forward(cvb_ctx* ctx, const uint8_t* img, int N, float thr, float* logits, uint8_t* mask, void* stream) {
+    if (!ctx || !img || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    for (int off = 0; off < N; off += ctx->max_batch) {
+        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+        if (unet_forward(ctx, img + static_cast<size_t>(off) * 786432, n, thr, logits ? logits + static_cast<size_t>(off) * 65536 : nullptr,
+                         mask ? mask + static_cast<size_t>(off) * 65536 : nullptr, static_cast<cudaStream_t>(stream)))
+            return -2;
+    }
+    return 0;
+}
+
+int cvb_mask_from_logits(cvb_ctx* ctx, const float* logits, int N, float thr, uint8_t* mask, void* stream) {
+    if (!ctx || !logits || !mask || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    CK(launch_mask_from_logits(logits, mask, thr, static_cast<long long>(N) * 65536, static_cast<cudaStream_t>(stream)));
+    ctx->launches++;
+    return 0;
+}
+
+int cvb_mask_to_quad(cvb_ctx* ctx, const uint8_t* mask, int N, int32_t* quad, uint8_t* found, int32_t* status, void* stream) {
+    if (!ctx || !mask || !quad || !found || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    for (int off = 0; off < N; off += ctx->max_batch) {
+        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+        CK(launch_mask_to_quad(mask + static_cast<size_t>(off) * 65536, quad + off * 8, found + off,
+                               status ? status + off : ctx->ws_status, ctx->ws_ncont, ctx->ws_owner, n, static_cast<cudaStream_t>(stream)));
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int cvb_warp_squares(cvb_ctx* ctx, const uint8_t* img, const int32_t* quad, const uint8_t* found, int N, int H, int W, uint8_t* board,
+                     void* stream) {
+    if (!ctx || !img || !quad || !found || !board || N < 0 || H <= 0 || W <= 0) return -1;
+    if (set_device(ctx)) return -2;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (int off = 0; off < N; off += ctx->max_batch) {
+        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+        CK(launch_homography(quad + off * 8, found + off, ctx->ws_minv, n, static_cast<float>(H) / 256.0f, 512, 512, s));
+        CK(launch_warp_board(img + static_cast<size_t>(off) * H * W * 3, ctx->ws_minv, found + off, board + static_cast<size_t>(off) * 262144, n, H, W, s));
+        ctx->launches += 2;
+    }
+    return 0;
+}
+
+int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, float* probs, uint8_t* labels, uint8_t* labels_valid, char* fen,
+                 void* stream) {
+    if (!ctx || !board || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    for (int off = 0; off < N; off += ctx->max_batch) {
+        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+        const size_t o = off;
+        if (classify(ctx, board + o * 262144, n, flip, probs ? probs + o * 832 : nullptr, labels ? labels + o * 64 : nullptr,
+                     labels_valid ? labels_valid + o * 64 : nullptr, fen ? fen + o * 144 : nullptr, static_cast<cudaStream_t>(stream)))
+            return -2;
+    }
+    return 0;
+}
+
+int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float thr, int flip, const cvb_outputs* out, void* stream) {
+    if (!ctx || !img || !out || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    for (int off = 0; off < N; off += ctx->max_batch) {
+        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+        if (pipeline_chunk(ctx, img + static_cast<size_t>(off) * 786432, n, thr, flip, *out, off, static_cast<cudaStream_t>(stream))) return -2;
+    }
+    return 0;
+}
+
+int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float thr, int flip, const cvb_outputs* oh) {
+    if (!ctx || !img_host || !oh || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    const int B = ctx->max_batch;
+    int chunk = 0;
+    for (int off = 0; off < N; off += B, ++chunk) {
+        const int n = N - off < B ? N - off : B;
+        const int sl = chunk & 1;
+        const size_t o = off;
+        const cvb_outputs& d = ctx->slot_out[sl];
+        // the slot is reusable once the copy-out of the chunk that used it two iterations ago has finished
+        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[sl], 0));
+        CK(cudaMemcpyAsync(ctx->slot_img[sl], img_host + o * 786432, static_cast<size_t>(n) * 786432, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_in));
+        CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[sl], 0));
+        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_free[sl], 0));
+        cvb_outputs dev = d;
+        if (!oh->logits) dev.logits = nullptr;
+        if (!oh->mask) dev.mask = nullptr;
+        if (!oh->board) dev.board = nullptr;
+        if (pipeline_chunk(ctx, ctx->slot_img[sl], n, thr, flip, dev, 0, ctx->s_comp)) return -2;
+        CK(cudaEventRecord(ctx->ev_comp[sl], ctx->s_comp));
+        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[sl], 0));
+        cudaStream_t so = ctx->s_out;
+        if (oh->quad) CK(cudaMemcpyAsync(oh->quad + o * 8, d.quad, n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+        if (oh->found) CK(cudaMemcpyAsync(oh->found + o, d.found, n, cudaMemcpyDeviceToHost, so));
+        if (oh->status) CK(cudaMemcpyAsync(oh->status + o, d.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+        if (oh->probs) CK(cudaMemcpyAsync(oh->probs + o * 832, d.probs, static_cast<size_t>(n) * 832 * sizeof(float), cudaMemcpyDeviceToHost, so));
+        if (oh->labels) CK(cudaMemcpyAsync(oh->labels + o * 64, d.labels, n * 64, cudaMemcpyDeviceToHost, so));
+        if (oh->labels_valid) CK(cudaMemcpyAsync(oh->labels_valid + o * 64, d.labels_valid, n * 64, cudaMemcpyDeviceToHost, so));
+        if (oh->fen) CK(cudaMemcpyAsync(oh->fen + o * 144, d.fen, n * 144, cudaMemcpyDeviceToHost, so));
+        if (oh->logits) CK(cudaMemcpyAsync(oh->logits + o * 65536, d.logits, static_cast<size_t>(n) * 65536 * sizeof(float), cudaMemcpyDeviceToHost, so));
+        if (oh->mask) CK(cudaMemcpyAsync(oh->mask + o * 65536, d.mask, static_cast<size_t>(n) * 65536, cudaMemcpyDeviceToHost, so));
+        if (oh->board) CK(cudaMemcpyAsync(oh->board + o * 262144, d.board, static_cast<size_t>(n) * 262144, cudaMemcpyDeviceToHost, so));
+        CK(cudaEventRecord(ctx->ev_free[sl], so));
+    }
+    CK(cudaStreamSynchronize(ctx->s_in));
+    CK(cudaStreamSynchronize(ctx->s_comp));
+    CK(cudaStreamSynchronize(ctx->s_out));
+    return 0;
+}
+
+int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias, int Cout,
+                   int ksize, int stride, int relu, const void* residual, void* out, void* stream) {
+    if (!ctx || !in || !w_packed || !bias || !out) return -1;
+    if (set_device(ctx)) return -2;
+    if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return fail(ctx, -5, "conv2d: ksize/stride not supported");
+    ConvWeights cw;
+    cw.w = const_cast<__half*>(static_cast<const __half*>(w_packed));
+    cw.bias = const_cast<float*>(bias);
+    cw.rows = Cout;
+    cw.K = ksize * ksize * Cin;
+    ConvLaunch L;
+    if (build_conv(ctx, L, static_cast<const __half*>(in), N, H, W, Cin, 0, Cin, cw, ksize, stride, EPI_STORE)) return -5;
+    set_store(L, static_cast<__half*>(out), Cout, 0, relu, static_cast<const __half*>(residual), Cout);
+    return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
+}
+
+int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias, int Cout,
+                     void* out, int out_c_stride, int out_c_off, void* stream) {
+    if (!ctx || !in || !w_packed || !bias || !out) return -1;
+    if (set_device(ctx)) return -2;
+    ConvWeights cw;
+    cw.w = const_cast<__half*>(static_cast<const __half*>(w_packed));
+    cw.bias = const_cast<float*>(bias);
+    cw.rows = 4 * Cout;
+    cw.K = Cin;
+    ConvLaunch L;
+    if (build_conv(ctx, L, static_cast<const __half*>(in), N, H, W, Cin, 0, Cin, cw, 1, 1, EPI_CONVT)) return -5;
+    set_store(L, static_cast<__half*>(out), out_c_stride, out_c_off, 0, nullptr, 0);
+    L.p.convt_cout = Cout;
+    return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
+}
+
+int cvb_profile(cvb_ctx* ctx, int enable) {
+    if (!ctx) return -1;
+    if (set_device(ctx)) return -2;
+    if (enable && ctx->pev.empty()) {
+        ctx->pev.resize(kMaxProfileEvents);
+        ctx->pev_stage.resize(kMaxProfileEvents);
+        for (auto& e : ctx->pev) CK(cudaEventCreate(&e));
+    }
+    ctx->profile = enable != 0;
+    ctx->pev_used = 0;
+    for (float& v : ctx->stage_ms) v = 0.f;
+    return 0;
+}
+
+int cvb_profile_read(cvb_ctx* ctx, float* ms_out, int n_stages) {
+    if (!ctx || !ms_out) return -1;
+    if (set_device(ctx)) return -2;
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i + 1 < ctx->pev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->pev[i], ctx->pev[i + 1]) == cudaSuccess) ctx->stage_ms[ctx->pev_stage[i]] += ms;
+    }
+    ctx->pev_used = 0;
+    for (int i = 0; i < n_stages && i < kStages; ++i) ms_out[i] = ctx->stage_ms[i];
+    for (float& v : ctx->stage_ms) v = 0.f;
+    return 0;
+}
+
+}  // extern "C"

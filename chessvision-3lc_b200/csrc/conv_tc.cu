@@ -1,0 +1,327 @@
+// tcgen05 implicit-GEMM convolution for the UNet board extractor and the ResNet-18 piece classifier.
+//
+// Replaces (reference, all executed by ATen/cuDNN there):
+//   Conv3x3+BN+ReLU            chessvision/pytorch_unet/unet/unet_parts.py:16-21
+//   ConvTranspose2d k2 s2      chessvision/pytorch_unet/unet/unet_parts.py:53,57   (+ the concat of :67 via out_c_off)
+//   Conv1x1 head + sigmoid>thr chessvision/pytorch_unet/unet/unet_parts.py:74, core.py:273, utils.py:109-112
+//   ResNet BasicBlock convs    timm resnet18 (utils.py:35-39)
+//
+// One persistent, warp-specialised CTA per SM:
+//   warp 0  TMA producer  : per K step one 4-D box {64 ch, tw, th, tn} of the NHWC activations (the 3x3 halo and the
+//                           padding come from shifted box coordinates + TMA zero fill) and one {64, BLOCK_N} weight box
+//   warp 1  MMA issuer    : 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per stage, fp32 accumulators in TMEM, two
+//                           accumulator buffers so the epilogue of tile i overlaps the main loop of tile i+1
+//   warp 2  TMEM allocator
+//   warps 4-7 epilogue    : tcgen05.ld 32x32b.x32 -> bias / residual / ReLU -> fp16 NHWC (or convT scatter, or the
+//                           fused 1x1 head producing logits + mask)
+#include "common.cuh"
+#include "conv_tc.h"
+
+#include <stdio.h>
+
+namespace cvb {
+
+template <int BLOCK_N>
+struct ConvCfg {
+    static constexpr int kABytes = 128 * 128;
+    static constexpr int kBBytes = BLOCK_N * 128;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+    static constexpr int kTmemCols = 2 * BLOCK_N;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr int S = Cfg::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* tiles_ptr = smem_raw + (tiles_addr - raw_addr);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + S * Cfg::kStageBytes);
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * S;
+    const uint32_t bar_tfull = bar_full + 16 * S;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.a_map[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int k_steps = p.taps * p.c_chunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n_tile = t % p.n_tiles;
+                const int m_tile = t / p.n_tiles;
+                const int w0 = (m_tile % p.tiles_w) * p.tw;
+                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+                const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    const CUtensorMap* amap = &p.a_map[p.tap_map[tap]];
+                    const int hh = h0 + p.tap_dy[tap];
+                    const int ww = w0 + p.tap_dx[tap];
+                    for (int kc = 0; kc < p.c_chunks; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t a_dst = tiles_addr + stage * Cfg::kStageBytes;
+                        const uint32_t b_dst = a_dst + Cfg::kABytes;
+                        mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+                        tma_load_4d(a_dst, amap, bar_full + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
+                        tma_load_2d(b_dst, &p.b_map, bar_full + 8 * stage, (tap * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < k_steps; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = tiles_addr + stage * Cfg::kStageBytes;
+                    const uint64_t a_desc = umma_desc_sw128(a_addr);
+                    const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar_empty + 8 * stage);
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int rn = row / (p.th * p.tw);
+        const int rh = (row / p.tw) % p.th;
+        const int rw = row % p.tw;
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int n_tile = t % p.n_tiles;
+            const int m_tile = t / p.n_tiles;
+            const int w = (m_tile % p.tiles_w) * p.tw + rw;
+            const int h = ((m_tile / p.tiles_w) % p.tiles_h) * p.th + rh;
+            const int n = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn + rn;
+            const bool valid = n < p.N;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+            const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+            float dot = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c0, v);
+                tmem_ld_wait();
+                const int col0 = n_tile * BLOCK_N + c0;
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+                if constexpr (EPI == EPI_OUTC) {
+                    const float4* w4 = reinterpret_cast<const float4*>(p.outc_w + col0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = __ldg(b4 + i);
+                        const float4 wv = __ldg(w4 + i);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
+                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
+                    }
+                } else {
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 b = __ldg(b4 + i);
+                        f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+                        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+                        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+                        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+                    }
+                    __half* dst;
+                    if constexpr (EPI == EPI_CONVT) {
+                        const int q = col0 / p.convt_cout;
+                        const int co = col0 - q * p.convt_cout;
+                        const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
+                        dst = p.out + opix * p.out_c_stride + p.out_c_off + co;
+                    } else {
+                        dst = p.out + pix * p.out_c_stride + p.out_c_off + col0;
+                        if (p.res != nullptr && valid) {
+                            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_c_stride + col0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint4 r = __ldg(r4 + i);
+                                const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 rf = __half22float2(rh2[j]);
+                                    f[8 * i + 2 * j] += rf.x;
+                                    f[8 * i + 2 * j + 1] += rf.y;
+                                }
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+                    if (valid) {
+                        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 o;
+                            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+                            d4[i] = o;
+                        }
+                    }
+                }
+            }
+            if constexpr (EPI == EPI_OUTC) {
+                if (valid) {
+                    const float logit = dot + p.outc_b;
+                    p.logits[pix] = logit;
+                    const float prob = 1.0f / (1.0f + expf(-logit));
+                    p.mask[pix] = prob > p.thr ? 255 : 0;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------ host
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+int tmap_init() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) return -1;
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return 0;
+}
+
+int tmap_act(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN, int tw,
+             int th, int tn) {
+    if (tmap_init()) return -1;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)Nv};
+    cuuint64_t strides[3] = {(cuuint64_t)sW * 2, (cuuint64_t)sH * 2, (cuuint64_t)sN * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int block_n) {
+    if (tmap_init()) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)K_total, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K_total * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+template <int BN, int EPI>
+static cudaError_t configure_one() {
+    return cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::kSmemBytes);
+}
+
+cudaError_t conv_configure() {
+    cudaError_t e;
+    if ((e = configure_one<64, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_CONVT>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_CONVT>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
+    if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_one(const ConvParams& p, int grid, cudaStream_t s) {
+    conv_tc_kernel<BN, EPI><<<grid, 256, ConvCfg<BN>::kSmemBytes, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream) {
+    ConvParams& p = L.p;
+    p.N = n_images;
+    p.tiles_n = (n_images + p.tn - 1) / p.tn;
+    p.idesc = umma_idesc_f16(128, L.block_n, 0);
+    const long long total = 1LL * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    if (total <= 0) return cudaSuccess;
+    const int grid = (int)(total < sm_count ? total : sm_count);
+    switch (L.epilogue * 1000 + L.block_n) {
+        case EPI_STORE * 1000 + 64: return launch_one<64, EPI_STORE>(p, grid, stream);
+        case EPI_STORE * 1000 + 128: return launch_one<128, EPI_STORE>(p, grid, stream);
+        case EPI_STORE * 1000 + 256: return launch_one<256, EPI_STORE>(p, grid, stream);
+        case EPI_CONVT * 1000 + 64: return launch_one<64, EPI_CONVT>(p, grid, stream);
+        case EPI_CONVT * 1000 + 128: return launch_one<128, EPI_CONVT>(p, grid, stream);
+        case EPI_CONVT * 1000 + 256: return launch_one<256, EPI_CONVT>(p, grid, stream);
+        case EPI_OUTC * 1000 + 64: return launch_one<64, EPI_OUTC>(p, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace cvb

@@ -1,0 +1,68 @@
+// Host-side description of one tcgen05 implicit-GEMM convolution launch (internal to the library).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvb {
+
+enum ConvEpilogue : int {
+    EPI_STORE = 0,   // y = acc + bias (+ residual) (ReLU optional) -> fp16 NHWC with channel stride/offset
+    EPI_CONVT = 1,   // 2x2 stride-2 transposed conv: column block q=(dy,dx) scattered to pixel (2h+dy, 2w+dx)
+    EPI_OUTC = 2,    // ReLU(acc + bias) . w_out + b_out -> fp32 logit + u8 mask (BLOCK_N == 64 == Cout)
+};
+
+// Kernel parameter block (passed __grid_constant__; the tensor maps must stay 64-byte aligned).
+struct alignas(64) ConvParams {
+    CUtensorMap a_map[4];  // activation views, 4-D {C, W, H, N}, box {64, tw, th, tn}, 128-byte swizzle
+    CUtensorMap b_map;     // packed weights, 2-D {K_total, Cout_total}, box {64, BLOCK_N}, 128-byte swizzle
+    // K loop: taps x (Cin/64) chunks.  Tap t reads view tap_map[t] at spatial offset (tap_dy[t], tap_dx[t]).
+    int taps;
+    int c_chunks;
+    int a_c_off;  // first input channel inside the activation buffer
+    int8_t tap_map[12];
+    int8_t tap_dy[12];
+    int8_t tap_dx[12];
+    // M tiling: one tile = tn images x th rows x tw columns = 128 output pixels
+    int tn, th, tw;
+    int tiles_w, tiles_h, tiles_n;
+    int N, H, W;   // output extent covered by the M tiles (N = images in this launch)
+    int n_tiles;   // Cout_total / BLOCK_N
+    uint32_t idesc;
+    // epilogue
+    int relu;
+    const float* bias;      // [Cout_total]
+    __half* out;            // NHWC fp16
+    int out_c_stride;       // channels per pixel of the output buffer
+    int out_c_off;          // first output channel
+    const __half* res;      // optional residual, NHWC fp16 (same pixel grid as out)
+    int res_c_stride;
+    int convt_cout;         // EPI_CONVT: Cout per (dy,dx) block
+    const float* outc_w;    // EPI_OUTC: [64]
+    float outc_b;
+    float* logits;          // EPI_OUTC: [N,H,W] fp32
+    uint8_t* mask;          // EPI_OUTC: [N,H,W] u8 {0,255}
+    float thr;
+};
+
+struct ConvLaunch {
+    ConvParams p;
+    int block_n;   // 64, 128 or 256
+    int epilogue;  // ConvEpilogue
+};
+
+// Resolve cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).  Returns 0 on success.
+int tmap_init();
+// 4-D NHWC activation view.  Strides are in elements of fp16 between consecutive w / h / n.
+int tmap_act(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN,
+             int tw, int th, int tn);
+// 2-D K-major weight matrix [rows = Cout_total][cols = K_total].
+int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int block_n);
+
+// Launch on `stream` for the first `n_images` images; grid sized to min(tiles, SM count).
+cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream);
+// One-time: raise the dynamic shared-memory limit of every instantiation.
+cudaError_t conv_configure();
+
+}  // namespace cvb

@@ -1,0 +1,645 @@
+// Integer / geometric half of the image->FEN path on the device (compiled with -fmad=false: every float64 result
+// below must equal what OpenCV computes on the CPU, so no contraction is allowed).
+//
+//   k_mask_to_quad   ChessVision._find_quadrangle (core.py:358-379): cv2.findContours(RETR_CCOMP, TC89_KCOS) +
+//                    _filter_contours (core.py:382-404) + arcLength/approxPolyDP (core.py:372-377) +
+//                    _rotate_quadrangle (core.py:407-411).  One warp per board, label image + contour in shared memory.
+//   k_homography     _scale_quadrangle (core.py:414-417) + cv2.getPerspectiveTransform (utils.py:127-131) + the
+//                    3x3 inversion cv2.warpPerspective performs.
+//   k_warp_board     cv2.warpPerspective (utils.py:132) + cvtColor BGR2GRAY (core.py:299) + flip (core.py:300),
+//                    written directly in the layout extract_squares (core.py:420-439) views as 64 squares.
+#include "kernels.h"
+
+#include <math.h>
+
+namespace cvb {
+
+// =====================================================================================================================
+// mask -> quad
+// =====================================================================================================================
+namespace {
+
+constexpr int LW = 258;                 // padded label row
+constexpr int kLabBytes = ((LW * LW * 2 + 15) / 16) * 16;
+constexpr int kQuadSmem = kLabBytes + kQuadMaxPoints * (4 + 4 + 2 + 1) + 64;
+constexpr unsigned FULL = 0xffffffffu;
+
+__constant__ int c_off16[16] = {1, -LW + 1, -LW, -LW - 1, -1, LW - 1, LW, LW + 1, 1, -LW + 1, -LW, -LW - 1, -1, LW - 1, LW, LW + 1};
+__constant__ int c_kcos_t[15] = {1, 2, 3, 4, 3, 2, 1, 0, 1, 2, 3, 4, 3, 2, 1};
+
+struct Contour {
+    int n;          // border points (may exceed kQuadMaxPoints -> overflow)
+    int minx, maxx, miny, maxy;
+};
+
+__device__ __forceinline__ int pack_pt(int idx) {
+    const int y = idx / LW, x = idx - y * LW;
+    return (x - 1) | ((y - 1) << 16);
+}
+__device__ __forceinline__ int px(int p) { return p & 0xffff; }
+__device__ __forceinline__ int py(int p) { return p >> 16; }
+
+// Suzuki-Abe border following from `start` (lane 0 only).
+__device__ void trace_border(int16_t* lab, int start, int nbd, bool hole, int* P, uint8_t* CODE, Contour& c) {
+    int s_end = hole ? 0 : 4;
+    int s = s_end;
+    int i1;
+    do {
+        s = (s - 1) & 7;
+        i1 = start + c_off16[s];
+    } while (lab[i1] == 0 && s != s_end);
+    const int p0 = pack_pt(start);
+    c.minx = c.maxx = px(p0);
+    c.miny = c.maxy = py(p0);
+    if (s == s_end) {  // isolated pixel
+        lab[start] = static_cast<int16_t>(-nbd);
+        P[0] = p0;
+        c.n = 1;
+        return;
+    }
+    int i3 = start, n = 0;
+    for (;;) {
+        s_end = s;
+        int i4;
+        do {
+            ++s;
+            i4 = i3 + c_off16[s & 15];
+        } while (lab[i4] == 0);
+        s &= 7;
+        if (static_cast<unsigned>(s - 1) < static_cast<unsigned>(s_end)) {
+            lab[i3] = static_cast<int16_t>(-nbd);
+        } else if (lab[i3] == 1) {
+            lab[i3] = static_cast<int16_t>(nbd);
+        }
+        const int p = pack_pt(i3);
+        if (n < kQuadMaxPoints) {
+            P[n] = p;
+            CODE[n] = static_cast<uint8_t>(s);
+        }
+        ++n;
+        c.minx = min(c.minx, px(p));
+        c.maxx = max(c.maxx, px(p));
+        c.miny = min(c.miny, py(p));
+        c.maxy = max(c.maxy, py(p));
+        if (i4 == start && i3 == i1) break;
+        i3 = i4;
+        s = (s + 4) & 7;
+    }
+    c.n = n;
+}
+
+__device__ __forceinline__ int wrap(int i, int n) {
+    i %= n;
+    return i < 0 ? i + n : i;
+}
+
+// TC89_KCOS pass 1 for point i (region of support + k-cosine); returns s, writes k.
+__device__ int kcos_point(const int* P, int n, int i, int& k_out) {
+    const int xi = px(P[i]), yi = py(P[i]);
+    int d_num = 0, l = 0, k = 1;
+    for (;; ++k) {
+        const int p1 = P[wrap(i - k, n)], p2 = P[wrap(i + k, n)];
+        const int dx = px(p2) - px(p1), dy = py(p2) - py(p1);
+        const int lk = dx * dx + dy * dy;
+        const int dk = (xi - px(p1)) * dy - (yi - py(p1)) * dx;
+        const float t = static_cast<float>(static_cast<double>(d_num) * static_cast<double>(lk) -
+                                           static_cast<double>(dk) * static_cast<double>(l));
+        if (k > 1 && (l >= lk || (d_num > 0 && t <= 0.f) || (d_num < 0 && t >= 0.f))) break;
+        d_num = dk;
+        l = lk;
+    }
+    --k;
+    k_out = k;
+    int sv = 0;
+    for (int j = k; j > 0; --j) {
+        const int pa = P[wrap(i - j, n)], pb = P[wrap(i + j, n)];
+        const int ax = px(pa) - xi, ay = py(pa) - yi, bx = px(pb) - xi, by = py(pb) - yi;
+        if ((ax | ay) == 0 || (bx | by) == 0) break;
+        const double num = static_cast<double>(ax * bx + ay * by);
+        const double den = sqrt(static_cast<double>(ax * ax + ay * ay) * static_cast<double>(bx * bx + by * by));
+        const float cs = static_cast<float>(num / den);
+        const int sk = __float_as_int(static_cast<float>(static_cast<double>(cs) + 1.1));
+        if (j < k && sk <= sv) break;
+        sv = sk;
+    }
+    return sv;
+}
+
+struct PolyStats {
+    double area;
+    int bw, bh;
+    double arclen;
+};
+
+__device__ void poly_stats(const int* R, int m, PolyStats& st) {
+    long long a2 = 0;
+    int minx = 1 << 20, maxx = -1, miny = 1 << 20, maxy = -1;
+    double total = 0.0;
+    float buf[16];
+    int nb = 0;
+    int prev = R[m - 1];
+    for (int i = 0; i < m; ++i) {
+        const int p = R[i];
+        a2 += static_cast<long long>(px(prev)) * py(p) - static_cast<long long>(py(prev)) * px(p);
+        minx = min(minx, px(p));
+        maxx = max(maxx, px(p));
+        miny = min(miny, py(p));
+        maxy = max(maxy, py(p));
+        const float dx = static_cast<float>(px(p)) - static_cast<float>(px(prev));
+        const float dy = static_cast<float>(py(p)) - static_cast<float>(py(prev));
+        buf[nb++] = __fsqrt_rn(dx * dx + dy * dy);
+        if (nb == 16 || i == m - 1) {
+            for (; nb > 0; --nb) total += static_cast<double>(buf[nb - 1]);
+        }
+        prev = p;
+    }
+    st.area = fabs(static_cast<double>(a2) * 0.5);
+    st.bw = maxx - minx + 1;
+    st.bh = maxy - miny + 1;
+    st.arclen = m > 1 ? total : 0.0;
+}
+
+// cv::approxPolyDP(closed) on R[0..m) -> number of output vertices; the vertices end up in dst[0..count).
+__device__ int approx_poly(const int* R, int m, double epsilon, int* dst, int* stack) {
+    const double eps = epsilon * epsilon;
+    int top = 0, count = 0;
+    int pos = 0, rstart = 0;
+    bool le_eps = false;
+    int sp = 0;
+    for (int it = 0; it < 3; ++it) {
+        double max_dist = 0.0;
+        pos = (pos + rstart) % m;
+        sp = R[pos];
+        pos = pos + 1 >= m ? 0 : pos + 1;
+        for (int j = 1; j < m; ++j) {
+            const int p = R[pos];
+            pos = pos + 1 >= m ? 0 : pos + 1;
+            const int dx = px(p) - px(sp), dy = py(p) - py(sp);
+            const double dist = static_cast<double>(dx * dx + dy * dy);
+            if (dist > max_dist) {
+                max_dist = dist;
+                rstart = j;
+            }
+        }
+        le_eps = max_dist <= eps;
+    }
+    if (!le_eps) {
+        const int s_start = pos % m;
+        const int s_end = (rstart + s_start) % m;
+        stack[2 * top] = s_end;  // right slice
+        stack[2 * top + 1] = s_start;
+        ++top;
+        stack[2 * top] = s_start;  // slice, popped first
+        stack[2 * top + 1] = s_end;
+        ++top;
+    } else {
+        dst[count++] = sp;
+    }
+    while (top > 0) {
+        --top;
+        const int a = stack[2 * top], b = stack[2 * top + 1];
+        const int ep = R[b];
+        pos = a;
+        sp = R[pos];
+        pos = pos + 1 >= m ? 0 : pos + 1;
+        bool le;
+        int split = 0;
+        if (pos != b) {
+            const double dx = static_cast<double>(px(ep) - px(sp)), dy = static_cast<double>(py(ep) - py(sp));
+            double max_dist = 0.0;
+            while (pos != b) {
+                const int p = R[pos];
+                pos = pos + 1 >= m ? 0 : pos + 1;
+                const double dist = fabs(static_cast<double>(py(p) - py(sp)) * dx - static_cast<double>(px(p) - px(sp)) * dy);
+                if (dist > max_dist) {
+                    max_dist = dist;
+                    split = (pos + m - 1) % m;
+                }
+            }
+            le = max_dist * max_dist <= eps * (dx * dx + dy * dy);
+        } else {
+            le = true;
+        }
+        if (le) {
+            dst[count++] = sp;
+        } else {
+            stack[2 * top] = split;
+            stack[2 * top + 1] = b;
+            ++top;
+            stack[2 * top] = a;
+            stack[2 * top + 1] = split;
+            ++top;
+        }
+    }
+    // clean-up pass, in place
+    int new_count = count;
+    pos = count - 1;
+    int start = dst[pos];
+    pos = pos + 1 >= count ? 0 : pos + 1;
+    int wpos = pos;
+    int pt = dst[pos];
+    pos = pos + 1 >= count ? 0 : pos + 1;
+    for (int i = 0; i < count && new_count > 2; ++i) {
+        const int end = dst[pos];
+        pos = pos + 1 >= count ? 0 : pos + 1;
+        const double dx = static_cast<double>(px(end) - px(start)), dy = static_cast<double>(py(end) - py(start));
+        const double dist = fabs(static_cast<double>(px(pt) - px(start)) * dy - static_cast<double>(py(pt) - py(start)) * dx);
+        const double sip = static_cast<double>((px(pt) - px(start)) * (px(end) - px(pt)) + (py(pt) - py(start)) * (py(end) - py(pt)));
+        if (dist * dist <= 0.5 * eps * (dx * dx + dy * dy) && dx != 0.0 && dy != 0.0 && sip >= 0.0) {
+            --new_count;
+            dst[wpos] = start = end;
+            wpos = wpos + 1 >= count ? 0 : wpos + 1;
+            pt = dst[pos];
+            pos = pos + 1 >= count ? 0 : pos + 1;
+            ++i;
+            continue;
+        }
+        dst[wpos] = start = pt;
+        wpos = wpos + 1 >= count ? 0 : wpos + 1;
+        pt = end;
+    }
+    return new_count;
+}
+
+__global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restrict__ mask, int32_t* __restrict__ quad,
+                                                        uint8_t* __restrict__ found, int32_t* __restrict__ status,
+                                                        int32_t* __restrict__ n_contours, int32_t* __restrict__ owner_scratch) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    int16_t* lab = reinterpret_cast<int16_t*>(smem);
+    int* P = reinterpret_cast<int*>(smem + kLabBytes);
+    int* S = P + kQuadMaxPoints;
+    uint16_t* KS = reinterpret_cast<uint16_t*>(S + kQuadMaxPoints);
+    uint8_t* CODE = reinterpret_cast<uint8_t*>(KS + kQuadMaxPoints);
+    Contour* cshare = reinterpret_cast<Contour*>(CODE + kQuadMaxPoints);
+
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const uint8_t* m = mask + static_cast<size_t>(b) * 65536;
+    int* owner = owner_scratch + static_cast<size_t>(b) * (kQuadMaxBorders + 8);
+
+    // label image: 0 / 1 with a one-pixel zero frame
+    for (int i = lane; i < LW; i += 32) {
+        lab[i] = 0;
+        lab[257 * LW + i] = 0;
+        lab[i * LW] = 0;
+        lab[i * LW + 257] = 0;
+    }
+    for (int i = lane; i < 65536 / 4; i += 32) {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(m) + i);
+        const int y = i >> 6, x = (i & 63) * 4;
+        int16_t* d = lab + (y + 1) * LW + x + 1;
+        d[0] = (v & 0xffu) ? 1 : 0;
+        d[1] = (v & 0xff00u) ? 1 : 0;
+        d[2] = (v & 0xff0000u) ? 1 : 0;
+        d[3] = (v & 0xff000000u) ? 1 : 0;
+    }
+    __syncwarp();
+
+    int nbd = 1, ncont = 0;
+    bool overflow = false;
+    // running winners
+    bool first_is4 = false;
+    int first_q[4] = {0, 0, 0, 0};
+    bool best_valid = false;
+    int best_o = -1, best_hole = 0, best_d = -1;
+    int best_q[4] = {0, 0, 0, 0};
+
+    for (int y = 1; y <= 256; ++y) {
+        const int16_t* row = lab + y * LW;
+        int x = 1;
+        int lnbd = 0;
+        while (x <= 257) {
+            const int xi = x + lane;
+            const bool in = xi <= 257;
+            const int v = in ? row[xi] : 0;
+            const int vp = in ? row[xi - 1] : 0;
+            const bool cand = in && ((v != 0) != (vp != 0));
+            const bool marked = in && vp != 0 && vp != 1;
+            const unsigned cm = __ballot_sync(FULL, cand);
+            const unsigned mm = __ballot_sync(FULL, marked);
+            if (cm == 0) {
+                if (mm) lnbd = abs(__shfl_sync(FULL, vp, 31 - __clz(mm)));
+                x += 32;
+                continue;
+            }
+            const int first = __ffs(cm) - 1;
+            const unsigned mm2 = mm & (first == 31 ? FULL : ((2u << first) - 1u));
+            if (mm2) lnbd = abs(__shfl_sync(FULL, vp, 31 - __clz(mm2)));
+            const int p = __shfl_sync(FULL, v, first);
+            const int prev = __shfl_sync(FULL, vp, first);
+            const int xc = x + first;
+            const bool outer = prev == 0 && p == 1;
+            const bool hole = !outer && p == 0 && prev >= 1;
+            if (outer || hole) {
+                ++nbd;
+                const int d = ncont++;
+                if (nbd >= kQuadMaxBorders) {
+                    overflow = true;
+                    nbd = kQuadMaxBorders - 1;  // keep labels representable; result is flagged invalid anyway
+                }
+                if (lane == 0) {
+                    Contour c;
+                    trace_border(lab, y * LW + (hole ? xc - 1 : xc), nbd, hole, P, CODE, c);
+                    *cshare = c;
+                    const int o = hole ? owner[lnbd] : d;
+                    owner[nbd] = o;
+                    cshare[1].n = o;
+                }
+                __syncwarp();
+                const Contour c = *cshare;
+                const int o = cshare[1].n;
+                __syncwarp();
+                const bool big = (c.maxx - c.minx + 1) * (c.maxy - c.miny + 1) >= 22937;
+                if (d == 0 || big) {
+                    if (c.n > kQuadMaxPoints) {
+                        overflow = true;
+                    } else if (c.n > 1) {
+                        const int n = c.n;
+                        // pass 0: candidate points (direction changes)
+                        for (int i = lane; i < n; i += 32) {
+                            const int prev_code = CODE[i == 0 ? n - 1 : i - 1];
+                            S[i] = c_kcos_t[static_cast<int>(CODE[i]) - prev_code + 7];
+                            KS[i] = 0;
+                        }
+                        __syncwarp();
+                        // pass 1: region of support and k-cosine, one candidate per lane
+                        for (int i = lane; i < n; i += 32) {
+                            if (S[i] != 0) {
+                                int k;
+                                const int sv = kcos_point(P, n, i, k);
+                                S[i] = sv;
+                                KS[i] = static_cast<uint16_t>(k);
+                            }
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            // pass 2: non-maximum suppression inside half the region of support
+                            for (int i = 0; i < n; ++i) {
+                                const int k2 = KS[i] >> 1;
+                                if (KS[i] == 0) continue;
+                                const int si = S[i];
+                                bool keep = true;
+                                for (int j = 1; j <= k2; ++j) {
+                                    if (S[wrap(i - j, n)] > si || S[wrap(i + j, n)] > si) {
+                                        keep = false;
+                                        break;
+                                    }
+                                }
+                                if (!keep) {
+                                    S[i] = 0;
+                                    KS[i] = 0;
+                                }
+                            }
+                            // pass 3 + compaction into P[0..mv)
+                            int mv = 0;
+                            for (int i = 0; i < n; ++i) {
+                                if (KS[i] == 0) continue;
+                                if (KS[i] == 1 && (S[i] <= S[wrap(i - 1, n)] || S[i] <= S[wrap(i + 1, n)])) {
+                                    S[i] = 0;
+                                    continue;
+                                }
+                                P[mv++] = P[i];
+                            }
+                            int is4 = 0, ov = 0, pass = 0;
+                            int q[4] = {0, 0, 0, 0};
+                            if (mv > kQuadMaxVertices) {
+                                ov = 1;
+                            } else if (mv > 0) {
+                                PolyStats st;
+                                poly_stats(P, mv, st);
+                                const double area = st.area / 65536.0;
+                                const int lo = min(st.bw, st.bh), hi = max(st.bw, st.bh);
+                                const double ratio = (lo == 0 || hi == 0) ? -1.0 : static_cast<double>(lo) / static_cast<double>(hi);
+                                pass = !(area < 0.35 || area > 1.0) && !(ratio < 0.6);
+                                if (d == 0 || pass) {
+                                    int* dst = S;
+                                    int* stack = S + kQuadMaxVertices;
+                                    const int cnt = approx_poly(P, mv, 0.1 * st.arclen, dst, stack);
+                                    if (cnt == 4) {
+                                        is4 = 1;
+                                        for (int j = 0; j < 4; ++j) q[j] = dst[j];
+                                    }
+                                }
+                            }
+                            int* r = reinterpret_cast<int*>(cshare);
+                            r[0] = is4;
+                            r[1] = ov;
+                            r[2] = pass;
+                            r[3] = q[0];
+                            r[4] = q[1];
+                            r[5] = q[2];
+                            r[6] = q[3];
+                        }
+                        __syncwarp();
+                        const int* r = reinterpret_cast<const int*>(cshare);
+                        const int is4 = r[0], ov = r[1], pass = r[2];
+                        const int q0 = r[3], q1 = r[4], q2 = r[5], q3 = r[6];
+                        __syncwarp();
+                        if (ov) overflow = true;
+                        if (d == 0 && is4) {
+                            first_is4 = true;
+                            first_q[0] = q0; first_q[1] = q1; first_q[2] = q2; first_q[3] = q3;
+                        }
+                        if (pass && is4) {
+                            const int hl = hole ? 1 : 0;
+                            const bool better = !best_valid || o > best_o ||
+                                                (o == best_o && (hl < best_hole || (hl == best_hole && d > best_d)));
+                            if (better) {
+                                best_valid = true;
+                                best_o = o; best_hole = hl; best_d = d;
+                                best_q[0] = q0; best_q[1] = q1; best_q[2] = q2; best_q[3] = q3;
+                            }
+                        }
+                    }
+                }
+            }
+            x = xc + 1;
+        }
+    }
+
+    if (lane == 0) {
+        bool ok = false;
+        int q[4] = {0, 0, 0, 0};
+        if (ncont == 1) {
+            ok = first_is4;
+            for (int j = 0; j < 4; ++j) q[j] = first_q[j];
+        } else if (ncont > 1) {
+            ok = best_valid;
+            for (int j = 0; j < 4; ++j) q[j] = best_q[j];
+        }
+        if (overflow) ok = false;
+        if (ok && px(q[0]) < px(q[2])) {  // _rotate_quadrangle
+            const int t = q[3];
+            q[3] = q[2]; q[2] = q[1]; q[1] = q[0]; q[0] = t;
+        }
+        for (int j = 0; j < 4; ++j) {
+            quad[(b * 4 + j) * 2 + 0] = ok ? px(q[j]) : 0;
+            quad[(b * 4 + j) * 2 + 1] = ok ? py(q[j]) : 0;
+        }
+        found[b] = ok ? 1 : 0;
+        status[b] = overflow ? QUAD_OVERFLOW : (ok ? QUAD_FOUND : QUAD_NONE);
+        n_contours[b] = ncont;
+    }
+}
+
+}  // namespace
+
+cudaError_t configure_quad() {
+    return cudaFuncSetAttribute(k_mask_to_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem);
+}
+
+cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* found, int32_t* status, int32_t* n_contours,
+                                int32_t* owner_scratch, int N, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    k_mask_to_quad<<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================================
+// homography
+// =====================================================================================================================
+namespace {
+
+__global__ void k_homography(const int32_t* __restrict__ quad, const uint8_t* __restrict__ found, double* __restrict__ minv,
+                             int N, float scale, int out_w, int out_h) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    double* out = minv + static_cast<size_t>(b) * 9;
+    if (!found[b]) {
+        for (int i = 0; i < 9; ++i) out[i] = 0.0;
+        return;
+    }
+    double A[8][8], B[8];
+    const double dstx[4] = {0.0, static_cast<double>(out_w), static_cast<double>(out_w), 0.0};
+    const double dsty[4] = {0.0, 0.0, static_cast<double>(out_h), static_cast<double>(out_h)};
+    for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < 8; ++j) A[i][j] = 0.0;
+    for (int i = 0; i < 4; ++i) {
+        // np.array(approx * sf, dtype=float32): the product is formed in float64, then rounded to float32
+        const double sx = static_cast<double>(static_cast<float>(static_cast<double>(quad[(b * 4 + i) * 2 + 0]) * static_cast<double>(scale)));
+        const double sy = static_cast<double>(static_cast<float>(static_cast<double>(quad[(b * 4 + i) * 2 + 1]) * static_cast<double>(scale)));
+        A[i][0] = A[i + 4][3] = sx;
+        A[i][1] = A[i + 4][4] = sy;
+        A[i][2] = A[i + 4][5] = 1.0;
+        A[i][6] = -sx * dstx[i];
+        A[i][7] = -sy * dstx[i];
+        A[i + 4][6] = -sx * dsty[i];
+        A[i + 4][7] = -sy * dsty[i];
+        B[i] = dstx[i];
+        B[i + 4] = dsty[i];
+    }
+    bool singular = false;
+    for (int i = 0; i < 8; ++i) {
+        int k = i;
+        for (int j = i + 1; j < 8; ++j)
+            if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (fabs(A[k][i]) < 2.220446049250313e-16 * 100) {
+            singular = true;
+            break;
+        }
+        if (k != i) {
+            for (int j = i; j < 8; ++j) {
+                const double t = A[i][j];
+                A[i][j] = A[k][j];
+                A[k][j] = t;
+            }
+            const double t = B[i];
+            B[i] = B[k];
+            B[k] = t;
+        }
+        const double d = -1.0 / A[i][i];
+        for (int j = i + 1; j < 8; ++j) {
+            const double alpha = A[j][i] * d;
+            for (int kk = i + 1; kk < 8; ++kk) A[j][kk] += alpha * A[i][kk];
+            B[j] += alpha * B[i];
+        }
+    }
+    if (singular) {
+        for (int i = 0; i < 9; ++i) out[i] = 0.0;
+        return;
+    }
+    for (int i = 7; i >= 0; --i) {
+        double s = B[i];
+        for (int kk = i + 1; kk < 8; ++kk) s -= A[i][kk] * B[kk];
+        B[i] = s / A[i][i];
+    }
+    const double a00 = B[0], a01 = B[1], a02 = B[2], a10 = B[3], a11 = B[4], a12 = B[5], a20 = B[6], a21 = B[7], a22 = 1.0;
+    const double det = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
+    const double d = 1.0 / det;
+    out[0] = (a11 * a22 - a12 * a21) * d;
+    out[1] = (a02 * a21 - a01 * a22) * d;
+    out[2] = (a01 * a12 - a02 * a11) * d;
+    out[3] = (a12 * a20 - a10 * a22) * d;
+    out[4] = (a00 * a22 - a02 * a20) * d;
+    out[5] = (a02 * a10 - a00 * a12) * d;
+    out[6] = (a10 * a21 - a11 * a20) * d;
+    out[7] = (a01 * a20 - a00 * a21) * d;
+    out[8] = (a00 * a11 - a01 * a10) * d;
+}
+
+// =====================================================================================================================
+// warp + gray + flip.  One CTA per 64x16 destination block (the block shape OpenCV evaluates coordinates in); each
+// thread produces 4 consecutive destination pixels and writes them mirrored as one 32-bit store.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
+                                                    const uint8_t* __restrict__ found, uint8_t* __restrict__ board, int H,
+                                                    int W) {
+    const int b = blockIdx.z;
+    const int bx = blockIdx.x * 64, y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const int x1 = (threadIdx.x & 15) * 4;
+    uint8_t* dst_row = board + (static_cast<size_t>(b) * 512 + y) * 512;
+    if (!found[b]) {
+        *reinterpret_cast<uint32_t*>(dst_row + (511 - (bx + x1) - 3)) = 0u;
+        return;
+    }
+    const double* m = minv + static_cast<size_t>(b) * 9;
+    const double m0 = m[0], m3 = m[3], m6 = m[6];
+    const double X0 = m0 * bx + m[1] * y + m[2];
+    const double Y0 = m3 * bx + m[4] * y + m[5];
+    const double W0 = m6 * bx + m[7] * y + m[8];
+    const uint8_t* src = img + static_cast<size_t>(b) * H * W * 3;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double xx = static_cast<double>(x1 + i);
+        double w = W0 + m6 * xx;
+        w = w != 0.0 ? 32.0 / w : 0.0;
+        const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + m0 * xx) * w));
+        const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + m3 * xx) * w));
+        const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
+        const int sx = max(-32768, min(32767, Xi >> 5)), sy = max(-32768, min(32767, Yi >> 5));
+        const int ax = Xi & 31, ay = Yi & 31;
+        const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+        int acc[3] = {16384, 16384, 16384};
+        const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
+        const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
+        const uint8_t* p = src + (static_cast<long long>(sy) * W + sx) * 3;
+        if (y0ok && x0ok) { acc[0] += w00 * p[0]; acc[1] += w00 * p[1]; acc[2] += w00 * p[2]; }
+        if (y0ok && x1ok) { acc[0] += w01 * p[3]; acc[1] += w01 * p[4]; acc[2] += w01 * p[5]; }
+        const uint8_t* p2 = p + static_cast<long long>(W) * 3;
+        if (y1ok && x0ok) { acc[0] += w10 * p2[0]; acc[1] += w10 * p2[1]; acc[2] += w10 * p2[2]; }
+        if (y1ok && x1ok) { acc[0] += w11 * p2[3]; acc[1] += w11 * p2[4]; acc[2] += w11 * p2[5]; }
+        const int bl = acc[0] >> 15, gr = acc[1] >> 15, rd = acc[2] >> 15;
+        const uint32_t gray = static_cast<uint32_t>((3735 * bl + 19235 * gr + 9798 * rd + 16384) >> 15);
+        packed |= gray << (8 * (3 - i));  // destination x -> 511 - x
+    }
+    *reinterpret_cast<uint32_t*>(dst_row + (511 - (bx + x1) - 3)) = packed;
+}
+
+}  // namespace
+
+cudaError_t launch_homography(const int32_t* quad, const uint8_t* found, double* minv, int N, float scale, int out_w,
+                              int out_h, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    k_homography<<<(N + 63) / 64, 64, 0, s>>>(quad, found, minv, N, scale, out_w, out_h);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_warp_board(const uint8_t* img, const double* minv, const uint8_t* found, uint8_t* board, int N, int H,
+                              int W, cudaStream_t s) {
+    if (N == 0) return cudaSuccess;
+    dim3 grid(8, 32, N);
+    k_warp_board<<<grid, 256, 0, s>>>(img, minv, found, board, H, W);
+    return cudaGetLastError();
+}
+
+}  // namespace cvb

@@ -1,0 +1,40 @@
+// Launchers of the non-tensor-core kernels (internal to the library).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvb {
+
+// stem.cu
+cudaError_t launch_unet_stem(const uint8_t* img, const float* wf, const float* bf, __half* out, int N, int H, int W,
+                             int out_c_stride, cudaStream_t s);
+cudaError_t launch_maxpool2(const __half* in, __half* out, int N, int H, int W, int C, int in_c_stride, cudaStream_t s);
+cudaError_t launch_mask_from_logits(const float* logits, uint8_t* mask, float thr, long long count, cudaStream_t s);
+cudaError_t launch_resize_area_half(const uint8_t* img, uint8_t* out, int N, int h, int w, cudaStream_t s);
+cudaError_t configure_resnet_stem();
+cudaError_t launch_resnet_stem(const uint8_t* board, const float* wf, const float* bf, __half* out, int n_boards,
+                               cudaStream_t s);
+cudaError_t launch_head(const __half* feat, const float* fcw, const float* fcb, float* probs, uint8_t* labels,
+                        uint8_t* labels_valid, char* fen, int n_boards, int flip, cudaStream_t s);
+
+// geometry.cu
+constexpr int kQuadMaxPoints = 8192;     // border points of one contour held in shared memory
+constexpr int kQuadMaxBorders = 32000;   // borders per mask (int16 labels)
+constexpr int kQuadMaxVertices = 2048;   // vertices after the TC89_KCOS reduction
+// status codes written per board by the quad kernel
+enum QuadStatus : int { QUAD_NONE = 0, QUAD_FOUND = 1, QUAD_OVERFLOW = 2 };
+
+cudaError_t configure_quad();
+// mask u8 [N,256,256]; quad int32 [N,4,2] (x,y in the 256x256 mask frame, after _rotate_quadrangle);
+// found u8 [N]; status int32 [N]; owner_scratch int32 [N, kQuadMaxBorders]
+cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* found, int32_t* status, int32_t* n_contours,
+                                int32_t* owner_scratch, int N, cudaStream_t s);
+// quad -> inverse homography (double[9] per board), scale = H_img / 256 applied to both axes (core.py:414-417)
+cudaError_t launch_homography(const int32_t* quad, const uint8_t* found, double* minv, int N, float scale, int out_w,
+                              int out_h, cudaStream_t s);
+// img u8 [N,H,W,3] + minv -> board u8 [N,512,512] (warpPerspective + BGR2GRAY + flip); zero where !found
+cudaError_t launch_warp_board(const uint8_t* img, const double* minv, const uint8_t* found, uint8_t* board, int N, int H,
+                              int W, cudaStream_t s);
+
+}  // namespace cvb

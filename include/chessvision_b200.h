@@ -1,0 +1,117 @@
+/* chessvision_b200.h — C ABI of the B200-native image->FEN path.
+ *
+ * The reference (gudbrandtandberg/ChessVision-3LC) has no FFI layer: its boundary is the Python class
+ * `chessvision.ChessVision` (chessvision/core.py:22-567).  These entry points are what a ctypes binding inside that
+ * class calls instead of PyTorch-eager + OpenCV; `chessvision-3lc_b200/chessvision/_native.py` is that binding and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only; every `*_dev` style pointer is a device pointer in caller-allocated
+ * memory unless the function name ends in `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = default
+ * stream); return value 0 = ok, negative = error (text via cvb_last_error); no function throws; nothing allocates
+ * device memory after cvb_create / cvb_load_*.
+ */
+#ifndef CHESSVISION_B200_H
+#define CHESSVISION_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CVB_API __attribute__((visibility("default")))
+#else
+#define CVB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cvb_ctx cvb_ctx;
+
+/* One entry of a PyTorch state_dict, host memory, float32, C-contiguous. */
+typedef struct cvb_tensor {
+    const char* name;
+    const float* data;
+    int32_t ndim;
+    int64_t shape[4];
+} cvb_tensor;
+
+/* Per-board results; any pointer may be NULL (that output is then skipped). */
+typedef struct cvb_outputs {
+    float* logits;         /* [N,256,256]  UNet logits (BoardExtractionResult.probabilities, core.py:287,306) */
+    uint8_t* mask;         /* [N,256,256]  {0,255}     (binary_mask, utils.py:101-112)                        */
+    int32_t* quad;         /* [N,4,2]      corners (x,y) in the 256x256 mask frame, after _rotate_quadrangle   */
+    uint8_t* found;        /* [N]          1 if a quadrangle was found (core.py:281)                           */
+    int32_t* status;       /* [N]          0 none, 1 found, 2 capacity overflow in the contour kernel          */
+    uint8_t* board;        /* [N,512,512]  warped, gray, flipped board (core.py:298-300); zero where !found     */
+    float* probs;          /* [N,64,13]    softmax probabilities (PositionResult.model_probabilities)          */
+    uint8_t* labels;       /* [N,64]       argmax class per square, order a8..h8,a7..h1 (core.py:326)          */
+    uint8_t* labels_valid; /* [N,64]       after rule 1 "no_pawns_on_ends" (core.py:451-469)                   */
+    char* fen;             /* [N,2,72]     [0] original_fen, [1] fen; NUL padded (core.py:336,350)             */
+} cvb_outputs;
+
+CVB_API int cvb_version(void);
+
+/* ChessVision.__init__ (core.py:25-64): context bound to one GPU; workspaces sized for `max_batch` boards per chunk. */
+CVB_API cvb_ctx* cvb_create(int device, int max_batch);
+CVB_API void cvb_destroy(cvb_ctx* ctx);
+CVB_API const char* cvb_last_error(const cvb_ctx* ctx);
+CVB_API int cvb_max_batch(const cvb_ctx* ctx);
+
+/* _initialize_board_extractor / _initialize_classifier (core.py:84-150) after utils.load_model_checkpoint
+ * (utils.py:42-86): fold BatchNorm (eps 1e-5), pack fp16 K-major weight matrices, upload. */
+CVB_API int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* state_dict, int n_tensors);
+CVB_API int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* state_dict, int n_tensors);
+
+/* cv2.resize(img, (256,256), INTER_AREA) for 512x512 inputs (core.py:212): u8[N,2h,2w,3] -> u8[N,h,w,3]. */
+CVB_API int cvb_resize_area_half(cvb_ctx* ctx, const uint8_t* img, int N, int h, int w, uint8_t* out, void* stream);
+
+/* extract_board up to the logits (core.py:212-220) + sigmoid/threshold (core.py:273-276).
+ * img u8[N,512,512,3] BGR.  logits and/or mask may be NULL. */
+CVB_API int cvb_unet_forward(cvb_ctx* ctx, const uint8_t* img, int N, float threshold, float* logits, uint8_t* mask, void* stream);
+
+/* create_binary_mask(sigmoid(logits), thr) for externally produced logits (core.py:273-276). */
+CVB_API int cvb_mask_from_logits(cvb_ctx* ctx, const float* logits, int N, float threshold, uint8_t* mask, void* stream);
+
+/* ChessVision._find_quadrangle (core.py:358-379) on N masks u8[N,256,256]. */
+CVB_API int cvb_mask_to_quad(cvb_ctx* ctx, const uint8_t* mask, int N, int32_t* quad, uint8_t* found, int32_t* status, void* stream);
+
+/* _scale_quadrangle + utils.extract_perspective + BGR2GRAY + flip (core.py:291-300): img u8[N,H,W,3] -> board. */
+CVB_API int cvb_warp_squares(cvb_ctx* ctx, const uint8_t* img, const int32_t* quad, const uint8_t* found, int N, int H, int W,
+                     uint8_t* board, void* stream);
+
+/* classify_position + process_position_probabilities (core.py:225-249, 310-355) on boards u8[N,512,512]. */
+CVB_API int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, float* probs, uint8_t* labels,
+                 uint8_t* labels_valid, char* fen, void* stream);
+
+/* process_image for a batch (core.py:152-195); all pointers on the device. */
+CVB_API int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float threshold, int flip, const cvb_outputs* out,
+                     void* stream);
+
+/* Same, from HOST buffers to HOST buffers (pinned memory recommended): chunks of max_batch boards are copied in,
+ * processed and copied out on three streams so that PCIe transfers overlap compute.  Synchronous on return. */
+CVB_API int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float threshold, int flip,
+                          const cvb_outputs* out_host);
+
+/* Building block exposed for parity tests: one convolution layer on fp16 NHWC device tensors through the tcgen05
+ * kernel.  ksize in {1,3} (pad = ksize/2), stride in {1,2}; w_packed fp16 [Cout][ksize*ksize*Cin] with
+ * k = (r*ksize+s)*Cin + ci; bias fp32 [Cout]; residual (optional) fp16 [N,Ho,Wo,Cout].  Cin % 64 == 0. */
+CVB_API int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias,
+                   int Cout, int ksize, int stride, int relu, const void* residual, void* out, void* stream);
+/* ConvTranspose2d(k=2, s=2): w_packed fp16 [4*Cout][Cin] with row = (dy*2+dx)*Cout + co; bias fp32 [4*Cout]
+ * (the per-channel bias repeated for the four taps); out fp16 [N,2H,2W,out_c_stride] at channel out_c_off. */
+CVB_API int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias,
+                     int Cout, void* out, int out_c_stride, int out_c_off, void* stream);
+
+/* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
+CVB_API int64_t cvb_launch_count(const cvb_ctx* ctx);
+
+/* Time (ms, CUDA events on the launching stream) accumulated per stage since the last reset; stage ids:
+ * 0 unet convs (tcgen05), 1 unet aux (stem, pools), 2 mask->quad, 3 homography+warp, 4 resnet stem,
+ * 5 resnet convs (tcgen05), 6 head.  Enabled with cvb_profile(ctx, 1); adds event records, so off by default. */
+CVB_API int cvb_profile(cvb_ctx* ctx, int enable);
+CVB_API int cvb_profile_read(cvb_ctx* ctx, float* ms_out, int n_stages);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHESSVISION_B200_H */

@@ -1,0 +1,73 @@
+"""Parity of the tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu) against a plain PyTorch fp32 reference of the same
+op on the same fp16-rounded operands.  Tolerance: |out - ref| <= 1e-3*|ref| + 2e-3 (one fp16 rounding of the output,
+fp32 accumulation inside)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def pack(w):  # [Cout,Cin,k,k] -> fp16 [Cout,(r*k+s)*Cin+ci]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous().half()
+
+
+def check(out, ref):
+    out = out.float()
+    err = (out - ref).abs()
+    tol = 1e-3 * ref.abs() + 2e-3
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{bad} of {err.numel()} elements out of tolerance; max err {err.max().item():.4g} (ref max {ref.abs().max().item():.4g})"
+
+
+CASES = [
+    # N, H, W, Cin, Cout, k, stride, relu, residual
+    (2, 16, 16, 64, 64, 3, 1, True, False),      # BLOCK_N 64, tile 8x16
+    (1, 32, 32, 64, 128, 3, 1, True, False),     # BLOCK_N 128
+    (3, 16, 16, 128, 256, 3, 1, False, False),   # BLOCK_N 256, 2 K chunks per tap
+    (1, 16, 16, 256, 512, 3, 1, True, False),    # 2 N tiles
+    (5, 8, 8, 128, 128, 3, 1, True, True),       # tile = 2 images x 8 x 8, ragged batch, residual
+    (19, 4, 4, 256, 256, 3, 1, True, True),      # tile = 8 images x 4 x 4, ragged batch
+    (70, 2, 2, 512, 512, 3, 1, True, True),      # tile = 32 images x 2 x 2, ragged batch
+    (4, 16, 16, 64, 128, 3, 2, True, False),     # stride 2 through the four parity views
+    (4, 16, 16, 64, 128, 1, 2, False, False),    # 1x1 stride-2 downsample
+    (9, 8, 8, 128, 256, 3, 2, True, False),
+    (33, 4, 4, 256, 512, 1, 2, False, False),
+    (1, 64, 64, 64, 64, 1, 1, False, False),     # plain GEMM
+    (2, 256, 256, 64, 64, 3, 1, True, False),    # full-size UNet level 0 (many tiles per CTA: exercises the pipeline wrap)
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,relu,residual", CASES)
+def test_conv2d(engine, N, H, W, Cin, Cout, k, stride, relu, residual):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + H + Cin + Cout + k + stride)
+    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).half().cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).half()
+    b = torch.randn(Cout, generator=g).cuda()
+    res = (torch.randn(N, H // stride, W // stride, Cout, generator=g)).half().cuda() if residual else None
+    out = engine.conv2d_f16(x, pack(w.float()).cuda(), b, k, stride, relu, res)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().cuda(), b, stride=stride, padding=k // 2).permute(0, 2, 3, 1)
+    if residual:
+        ref = ref + res.float()
+    if relu:
+        ref = ref.relu()
+    check(out, ref)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 128, 64), (1, 16, 16, 1024, 512), (3, 32, 32, 256, 128)])
+def test_convt2x2(engine, N, H, W, Cin, Cout):
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(Cin + Cout)
+    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).half().cuda()
+    w = (torch.randn(Cin, Cout, 2, 2, generator=g) / Cin ** 0.5).half()
+    b = torch.randn(Cout, generator=g)
+    wp = w.float().permute(2, 3, 1, 0).reshape(4 * Cout, Cin).contiguous().half().cuda()  # row = (dy*2+dx)*Cout + co
+    out = torch.full((N, 2 * H, 2 * W, 2 * Cout), 7.0, dtype=torch.float16, device="cuda")
+    engine.convt2x2_f16(x, wp, b.repeat(4).cuda(), Cout, out, Cout)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w.float().cuda(), b.cuda(), stride=2).permute(0, 2, 3, 1)
+    check(out[..., Cout:], ref)
+    assert (out[..., :Cout] == 7.0).all(), "the skip half of the concat buffer must stay untouched"
