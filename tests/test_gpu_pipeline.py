@@ -1,0 +1,153 @@
+"""End-to-end parity on the reference's own ``data/test`` images against golden outputs of the UNMODIFIED reference
+(tests/golden/, written by oracle/make_golden.py with the same weights).
+
+Contract (BASELINE.json north_star / SURVEY.md §8c):
+  * board bytes identical given the reference's quads; labels and both FENs identical given the reference's boards
+  * end to end (fp16 UNet vs fp32 reference): found flags identical, corners within +-1 px in the 256x256 mask frame,
+    mask IoU >= 0.99, logits max-abs <= 0.15; FEN/label agreement is reported and must be >= 99% of squares
+"""
+import json
+import os
+from pathlib import Path
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, WEIGHTS, load_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    man = json.load(open(GOLDEN / "manifest.json"))
+    arr = np.load(GOLDEN / "reference_outputs.npz")
+    imgs = np.stack([cv2.imread(str(GOLDEN / "data_test" / e["file"])) for e in man["images"]])
+    return man, arr, imgs
+
+
+@pytest.fixture(scope="module")
+def trained_engine():
+    from chessvision import _native
+    ext, cls = WEIGHTS / "best_extractor.pth", WEIGHTS / "best_classifier.pth"
+    if not ext.exists() or not cls.exists():
+        pytest.fail("weights/best_extractor.pth / best_classifier.pth missing (oracle/train_weights.py writes them)")
+    eng = _native.Engine(0, max_batch=16)
+    eng.load_unet(load_checkpoint(ext))
+    eng.load_resnet18(load_checkpoint(cls))
+    yield eng
+    eng.close()
+
+
+def test_images_decode_identically(golden):
+    import hashlib
+    man, _, imgs = golden
+    for e, im in zip(man["images"], imgs):
+        assert im.shape == (512, 512, 3)
+        assert hashlib.sha1(np.ascontiguousarray(im).tobytes()).hexdigest() == e["image_sha1"], "JPEG decode differs from the build container"
+
+
+def test_boards_bit_exact_given_reference_quads(trained_engine, golden):
+    man, arr, imgs = golden
+    idx = [i for i, e in enumerate(man["images"]) if e["found"]]
+    quads = np.array([man["images"][i]["quad"] for i in idx], np.int32)
+    board = trained_engine.warp_squares(torch.from_numpy(imgs[idx]).cuda(), torch.from_numpy(quads).cuda(),
+                                        torch.ones(len(idx), dtype=torch.uint8, device="cuda")).cpu().numpy()
+    for k, i in enumerate(idx):
+        assert np.array_equal(board[k], arr[f"board_{i}"]), f"{man['images'][i]['file']}: {(board[k] != arr[f'board_{i}']).sum()} bytes differ"
+
+
+def test_labels_and_fen_bit_exact_given_reference_boards(trained_engine, golden):
+    from chessvision._native import fen_strings
+    man, arr, _ = golden
+    idx = [i for i, e in enumerate(man["images"]) if e["found"]]
+    boards = np.stack([arr[f"board_{i}"] for i in idx])
+    probs, labels, _, fen = trained_engine.classify(torch.from_numpy(boards).cuda(), False)
+    probs, labels = probs.cpu().numpy(), labels.cpu().numpy()
+    fens = fen_strings(fen)
+    perr = max(np.abs(probs[k] - arr[f"probs_{i}"]).max() for k, i in enumerate(idx))
+    flips = sum(int((labels[k] != arr[f"labels_{i}"]).sum()) for k, i in enumerate(idx))
+    print(f"classifier given reference boards: probabilities max-abs err {perr:.4f}, label flips {flips}/{64 * len(idx)}")
+    assert perr <= 0.05
+    assert flips == 0
+    for k, i in enumerate(idx):
+        e = man["images"][i]
+        assert fens[k] == (e["original_fen"], e["fen"]), e["file"]
+
+
+def test_end_to_end_data_test(trained_engine, golden):
+    from chessvision._native import fen_strings
+    man, arr, imgs = golden
+    n = len(imgs)
+    out = trained_engine.image_to_fen(torch.from_numpy(imgs).cuda(), trained_engine.alloc_outputs(n, full=True))
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    fens = fen_strings(torch.from_numpy(out["fen"]))
+    stats = {"images": n, "found_ref": 0, "found_equal": 0, "corner_hist": {}, "fen_identical": 0, "label_flips": 0, "squares": 0,
+             "logits_maxabs": 0.0, "mask_iou_min": 1.0}
+    for i, e in enumerate(man["images"]):
+        ref_logits = arr[f"logits_{i}"].astype(np.float32)
+        stats["logits_maxabs"] = max(stats["logits_maxabs"], float(np.abs(out["logits"][i] - ref_logits).max()))
+        ref_mask = np.unpackbits(arr[f"mask_{i}"]).reshape(256, 256).astype(bool)
+        got_mask = out["mask"][i] > 0
+        union = (ref_mask | got_mask).sum()
+        if union:
+            stats["mask_iou_min"] = min(stats["mask_iou_min"], float((ref_mask & got_mask).sum() / union))
+        stats["found_ref"] += int(e["found"])
+        stats["found_equal"] += int(bool(out["found"][i]) == e["found"])
+        if e["found"] and out["found"][i]:
+            d = int(np.abs(out["quad"][i] - np.array(e["quad"])).max())
+            stats["corner_hist"][str(d)] = stats["corner_hist"].get(str(d), 0) + 1
+            stats["squares"] += 64
+            stats["label_flips"] += int((out["labels"][i] != arr[f"labels_{i}"]).sum())
+            stats["fen_identical"] += int(fens[i] == (e["original_fen"], e["fen"]))
+    print("data/test end-to-end parity:", json.dumps(stats))
+    os.makedirs(ROOT / "gpurun_out", exist_ok=True)
+    json.dump(stats, open(ROOT / "gpurun_out" / "parity_data_test.json", "w"), indent=1)
+    assert stats["found_equal"] == n
+    assert all(int(k) <= 1 for k in stats["corner_hist"]), stats["corner_hist"]
+    assert stats["mask_iou_min"] >= 0.99
+    assert stats["logits_maxabs"] <= 0.15 + 0.01  # golden logits are stored as fp16 (<= 0.01 quantisation at |x| < 16)
+    assert stats["label_flips"] <= 0.01 * stats["squares"]
+
+
+def test_host_path_equals_device_path(trained_engine, golden):
+    _, _, imgs = golden
+    eng = trained_engine
+    sel = imgs[:37]  # not a multiple of max_batch: exercises the ragged last chunk and both slots
+    dev = eng.image_to_fen(torch.from_numpy(sel).cuda(), eng.alloc_outputs(len(sel), full=True))
+    torch.cuda.synchronize()
+    host_in = torch.from_numpy(sel).pin_memory()
+    host = eng.image_to_fen_host(host_in, eng.alloc_outputs(len(sel), full=True, pinned_host=True))
+    for k in dev:
+        assert torch.equal(dev[k].cpu(), host[k]), f"output '{k}' differs between device and host entry points"
+
+
+def test_python_api_process_image(golden):
+    """The drop-in class, as the reference's tests use it (tests/test_chessvision.py:45-116): structural checks plus
+    agreement with the golden FEN for the reference's own fixture image."""
+    import chessvision
+    from chessvision import constants
+    man, _, imgs = golden
+    cvm = chessvision.ChessVision(board_extractor_weights=str(WEIGHTS / "best_extractor.pth"),
+                                  classifier_weights=str(WEIGHTS / "best_classifier.pth"), classifier_model_id="resnet18", max_batch=4)
+    i = next(k for k, e in enumerate(man["images"]) if e["file"].endswith("1bf29f73-bc30-448b-a894-bd6428754a0c.JPG"))
+    res = cvm.process_image(imgs[i])
+    be = res.board_extraction
+    assert be.binary_mask.dtype == np.uint8 and be.binary_mask.shape == (256, 256)
+    assert be.probabilities.dtype == np.float32
+    if man["images"][i]["found"]:
+        assert be.board_image.shape == constants.BOARD_SIZE and be.quadrangle.shape == (4, 1, 2) and be.quadrangle.dtype == np.float32
+        pos = res.position
+        assert pos.squares.shape == (64, 64, 64, 1) and pos.model_probabilities.shape == (64, 13)
+        assert (pos.original_fen != pos.fen) == bool(pos.validation_fixes)
+        for fix in pos.validation_fixes:
+            assert fix.square_name in pos.square_names
+        sep = cvm.classify_position(be.board_image)
+        assert sep.fen == pos.fen
+    eb = cvm.extract_board(imgs[i])
+    assert np.array_equal(eb.binary_mask, be.binary_mask)
+    with pytest.raises(AssertionError):
+        cvm.process_image(imgs[i].astype(np.float32))
