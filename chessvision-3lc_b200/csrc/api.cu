@@ -7,6 +7,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -39,6 +40,7 @@ struct cvb_ctx {
     int device = 0;
     int max_batch = 0;
     int sm_count = 148;
+    bool use_vr = true;   // CVB_NO_VR=1 forces the generic conv kernel everywhere (A/B measurements)
     std::string err;
     int64_t launches = 0;
     std::vector<void*> allocs;
@@ -275,6 +277,10 @@ int build_conv(cvb_ctx* ctx, ConvLaunch& L, const __half* in, int Nmax, int Hin,
     if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (weights) failed: %d", rc);
     p.bias = cw.bias;
     L.epilogue = epilogue;
+    if (ctx->use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
+        rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
+        if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (vertical-reuse view) failed: %d", rc);
+    }
     return 0;
 }
 
@@ -424,6 +430,7 @@ cvb_ctx* cvb_create(int device, int max_batch) {
         return bail();
     }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->use_vr = getenv("CVB_NO_VR") == nullptr;
     if (tmap_init()) { ctx->err = "cuTensorMapEncodeTiled not available from the driver"; return bail(); }
     if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_quad() != cudaSuccess) {
         ctx->err = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());

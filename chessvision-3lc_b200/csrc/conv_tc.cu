@@ -31,6 +31,89 @@ struct ConvCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one 128-row accumulator tile: thread <-> output pixel (n,h,w); columns in chunks of 32.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int n, int h, int w, bool valid, int n_tile) {
+    const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+    float dot = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        const int col0 = n_tile * BLOCK_N + c0;
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+        if constexpr (EPI == EPI_OUTC) {
+            const float4* w4 = reinterpret_cast<const float4*>(p.outc_w + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(b4 + i);
+                const float4 wv = __ldg(w4 + i);
+                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
+                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
+                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
+                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
+            }
+        } else {
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(b4 + i);
+                f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+                f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+                f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+                f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+            }
+            __half* dst;
+            if constexpr (EPI == EPI_CONVT) {
+                const int q = col0 / p.convt_cout;
+                const int co = col0 - q * p.convt_cout;
+                const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
+                dst = p.out + opix * p.out_c_stride + p.out_c_off + co;
+            } else {
+                dst = p.out + pix * p.out_c_stride + p.out_c_off + col0;
+                if (p.res != nullptr && valid) {
+                    const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_c_stride + col0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint4 r = __ldg(r4 + i);
+                        const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 rf = __half22float2(rh2[j]);
+                            f[8 * i + 2 * j] += rf.x;
+                            f[8 * i + 2 * j + 1] += rf.y;
+                        }
+                    }
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (valid) {
+                uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 o;
+                    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+                    d4[i] = o;
+                }
+            }
+        }
+    }
+    if constexpr (EPI == EPI_OUTC) {
+        if (valid) {
+            const float logit = dot + p.outc_b;
+            p.logits[pix] = logit;
+            const float prob = 1.0f / (1.0f + expf(-logit));
+            p.mask[pix] = prob > p.thr ? 255 : 0;
+        }
+    }
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N>;
@@ -148,84 +231,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
-            float dot = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                tmem_ld_wait();
-                const int col0 = n_tile * BLOCK_N + c0;
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-                if constexpr (EPI == EPI_OUTC) {
-                    const float4* w4 = reinterpret_cast<const float4*>(p.outc_w + col0);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(b4 + i);
-                        const float4 wv = __ldg(w4 + i);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
-                        dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
-                    }
-                } else {
-                    float f[32];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 b = __ldg(b4 + i);
-                        f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
-                        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-                        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
-                        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
-                    }
-                    __half* dst;
-                    if constexpr (EPI == EPI_CONVT) {
-                        const int q = col0 / p.convt_cout;
-                        const int co = col0 - q * p.convt_cout;
-                        const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
-                        dst = p.out + opix * p.out_c_stride + p.out_c_off + co;
-                    } else {
-                        dst = p.out + pix * p.out_c_stride + p.out_c_off + col0;
-                        if (p.res != nullptr && valid) {
-                            const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_c_stride + col0);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint4 r = __ldg(r4 + i);
-                                const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 rf = __half22float2(rh2[j]);
-                                    f[8 * i + 2 * j] += rf.x;
-                                    f[8 * i + 2 * j + 1] += rf.y;
-                                }
-                            }
-                        }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-                    }
-                    if (valid) {
-                        uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 o;
-                            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
-                            d4[i] = o;
-                        }
-                    }
-                }
-            }
-            if constexpr (EPI == EPI_OUTC) {
-                if (valid) {
-                    const float logit = dot + p.outc_b;
-                    p.logits[pix] = logit;
-                    const float prob = 1.0f / (1.0f + expf(-logit));
-                    p.mask[pix] = prob > p.thr ? 255 : 0;
-                }
-            }
+            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, valid, n_tile);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
@@ -236,6 +242,166 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1 variant with vertical-tap reuse (and optionally stationary weights) for the wide, shallow layers
+// (Cout = 64 or 128 at 256^2 / 128^2), which are L2->SM bandwidth bound in the generic kernel: every tap re-fetches
+// the same activations.  Here one TMA box {64 ch, 8 w, 18 h} (18 swizzle groups of 1024 B) per horizontal offset dx
+// serves the three vertical taps: tap dy is the same smem tile addressed 1024*dy bytes further (a whole 8-row group,
+// so the 128-byte swizzle phase is unchanged).  Output tile = 16 rows x 8 columns.  When the layer's packed weights
+// (9*Cin*Cout*2 B) fit beside the pipeline they are loaded once per CTA and stay in shared memory.
+// L2->SM bytes per 128x64 output tile, Cin = 64:  generic 216 KB  ->  54 KB.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int EPI, bool W_STAT>
+__global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int kABytes = 18 * 1024;
+    constexpr int kBBytes = BLOCK_N * 128;
+    constexpr int kStageBytes = kABytes + (W_STAT ? 0 : 3 * kBBytes);
+    constexpr int kTmemCols = 2 * BLOCK_N;
+    const int S = p.vr_stages;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base_addr - raw_addr);
+    const uint32_t w_bytes = W_STAT ? 9u * p.c_chunks * kBBytes : 0u;
+    const uint32_t stages_addr = base_addr + w_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + w_bytes + S * kStageBytes);
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * S;
+    const uint32_t bar_tfull = bar_full + 16 * S;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_w = bar_tfull + 32;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.a_map[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        mbar_init(bar_w, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            if (W_STAT) {
+                mbar_expect_tx(bar_w, w_bytes);
+                for (int i = 0; i < 9 * p.c_chunks; ++i) tma_load_2d(base_addr + i * kBBytes, &p.b_map, bar_w, i * 64, 0);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int n_tile = t % p.n_tiles;
+                const int m_tile = t / p.n_tiles;
+                const int w0 = (m_tile % p.tiles_w) * 8;
+                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * 16;
+                const int n0 = m_tile / (p.tiles_w * p.tiles_h);
+                for (int kc = 0; kc < p.c_chunks; ++kc) {
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t a_dst = stages_addr + stage * kStageBytes;
+                        mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                        tma_load_4d(a_dst, &p.a_map[0], bar_full + 8 * stage, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
+                        if (!W_STAT) {
+#pragma unroll
+                            for (int dy = 0; dy < 3; ++dy)
+                                tma_load_2d(a_dst + kABytes + dy * kBBytes, &p.b_map, bar_full + 8 * stage,
+                                            ((dy * 3 + dxi) * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
+                        }
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            if (W_STAT) {
+                mbar_wait(bar_w, 0);
+                tc_fence_after();
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                uint32_t first = 0;
+                for (int kc = 0; kc < p.c_chunks; ++kc) {
+                    for (int dxi = 0; dxi < 3; ++dxi) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = stages_addr + stage * kStageBytes;
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t b_addr = W_STAT ? base_addr + ((dy * 3 + dxi) * p.c_chunks + kc) * kBBytes
+                                                           : a_addr + kABytes + dy * kBBytes;
+                            const uint64_t a_desc = umma_desc_sw128(a_addr + dy * 1024);
+                            const uint64_t b_desc = umma_desc_sw128(b_addr);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc, first);
+                                first = 1;
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * stage);
+                        if (++stage == S) { stage = 0; phase ^= 1; }
+                    }
+                }
+                umma_commit(bar_tfull + 8 * acc);
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int rh = row >> 3, rw = row & 7;
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int n_tile = t % p.n_tiles;
+            const int m_tile = t / p.n_tiles;
+            const int w = (m_tile % p.tiles_w) * 8 + rw;
+            const int h = ((m_tile / p.tiles_w) % p.tiles_h) * 16 + rh;
+            const int n = m_tile / (p.tiles_w * p.tiles_h);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, n < p.N, n_tile);
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -281,6 +447,17 @@ int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int bl
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+int tmap_act_vr(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN) {
+    return tmap_act(m, base, C, Wv, Hv, Nv, sW, sH, sN, 8, 18, 1);
+}
+
+constexpr int kVrMaxSmem = 227 * 1024;
+
+template <int BN, int EPI, bool WS>
+static cudaError_t configure_vr() {
+    return cudaFuncSetAttribute(conv3x3_vr_kernel<BN, EPI, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem);
+}
+
 template <int BN, int EPI>
 static cudaError_t configure_one() {
     return cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::kSmemBytes);
@@ -295,12 +472,48 @@ cudaError_t conv_configure() {
     if ((e = configure_one<128, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
+    if ((e = configure_vr<64, EPI_STORE, true>()) != cudaSuccess) return e;
+    if ((e = configure_vr<64, EPI_STORE, false>()) != cudaSuccess) return e;
+    if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
+    if ((e = configure_vr<128, EPI_STORE, false>()) != cudaSuccess) return e;
+    if ((e = configure_vr<64, EPI_OUTC, true>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 template <int BN, int EPI>
 static cudaError_t launch_one(const ConvParams& p, int grid, cudaStream_t s) {
     conv_tc_kernel<BN, EPI><<<grid, 256, ConvCfg<BN>::kSmemBytes, s>>>(p);
+    return cudaGetLastError();
+}
+
+// Decide whether the vertical-reuse kernel applies to this launch and size its pipeline.
+bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) {
+    ConvParams& p = L.p;
+    if (ksize != 3 || stride != 1 || Ho % 16 || Wo % 8) return false;
+    if (L.block_n != 64 && L.block_n != 128) return false;
+    if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
+    const int b_bytes = L.block_n * 128;
+    const int w_bytes = 9 * (Cin / 64) * b_bytes;
+    const int budget = kVrMaxSmem - 1024 - 256;
+    const bool ws = p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
+    if (L.epilogue == EPI_OUTC && !ws) return false;
+    const int stage = 18 * 1024 + (ws ? 0 : 3 * b_bytes);
+    int stages = (budget - (ws ? w_bytes : 0)) / stage;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return false;
+    p.vr_stages = stages;
+    p.w_stationary = ws ? 1 : 0;
+    p.smem_bytes = (ws ? w_bytes : 0) + stages * stage + 1024 + 256;
+    p.tn = 1; p.th = 16; p.tw = 8;
+    p.tiles_w = Wo / 8;
+    p.tiles_h = Ho / 16;
+    L.variant = 1;
+    return true;
+}
+
+template <int BN, int EPI, bool WS>
+static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s) {
+    conv3x3_vr_kernel<BN, EPI, WS><<<grid, 256, p.smem_bytes, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -312,6 +525,12 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     const long long total = 1LL * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = (int)(total < sm_count ? total : sm_count);
+    if (L.variant == 1) {
+        const bool ws = p.w_stationary != 0;
+        if (L.epilogue == EPI_OUTC) return launch_vr<64, EPI_OUTC, true>(p, grid, stream);
+        if (L.block_n == 64) return ws ? launch_vr<64, EPI_STORE, true>(p, grid, stream) : launch_vr<64, EPI_STORE, false>(p, grid, stream);
+        return ws ? launch_vr<128, EPI_STORE, true>(p, grid, stream) : launch_vr<128, EPI_STORE, false>(p, grid, stream);
+    }
     switch (L.epilogue * 1000 + L.block_n) {
         case EPI_STORE * 1000 + 64: return launch_one<64, EPI_STORE>(p, grid, stream);
         case EPI_STORE * 1000 + 128: return launch_one<128, EPI_STORE>(p, grid, stream);

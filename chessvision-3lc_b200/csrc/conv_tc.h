@@ -30,6 +30,9 @@ struct alignas(64) ConvParams {
     int N, H, W;   // output extent covered by the M tiles (N = images in this launch)
     int n_tiles;   // Cout_total / BLOCK_N
     uint32_t idesc;
+    int vr_stages;      // vertical-reuse variant: pipeline depth, weights resident in smem, dynamic smem size
+    int w_stationary;
+    int smem_bytes;
     // epilogue
     int relu;
     const float* bias;      // [Cout_total]
@@ -50,6 +53,7 @@ struct ConvLaunch {
     ConvParams p;
     int block_n;   // 64, 128 or 256
     int epilogue;  // ConvEpilogue
+    int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel
 };
 
 // Resolve cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).  Returns 0 on success.
@@ -59,6 +63,10 @@ int tmap_act(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, in
              int tw, int th, int tn);
 // 2-D K-major weight matrix [rows = Cout_total][cols = K_total].
 int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int block_n);
+
+// Vertical-reuse 3x3 kernel: 4-D view with box {64, 8, 18, 1}; conv_try_vr switches a built launch over to it.
+int tmap_act_vr(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN);
+bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin);
 
 // Launch on `stream` for the first `n_images` images; grid sized to min(tiles, SM count).
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream);

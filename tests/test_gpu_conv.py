@@ -35,6 +35,12 @@ CASES = [
     (33, 4, 4, 256, 512, 1, 2, False, False),
     (1, 64, 64, 64, 64, 1, 1, False, False),     # plain GEMM
     (2, 256, 256, 64, 64, 3, 1, True, False),    # full-size UNet level 0 (many tiles per CTA: exercises the pipeline wrap)
+    # vertical-reuse kernel (3x3 s1, Cout 64/128, H%16==0, W%8==0): stationary and streamed weights
+    (3, 64, 64, 128, 64, 3, 1, True, False),     # Cin 128 -> 64, weights resident (147 KB), 4 stages
+    (2, 32, 32, 128, 128, 3, 1, True, True),     # 128 -> 128, weights streamed (3 stages), residual
+    (1, 64, 64, 256, 128, 3, 1, False, False),   # 256 -> 128, 4 K chunks
+    (1, 128, 128, 64, 128, 3, 1, True, False),   # 64 -> 128 resident
+    (7, 16, 8, 64, 64, 3, 1, True, True),        # a single 16x8 tile per image
 ]
 
 
