@@ -7,8 +7,9 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 mkdir -p build
 $NVCC $FLAGS -c csrc/conv_tc.cu -o build/conv_tc.o &
 $NVCC $FLAGS -c csrc/stem.cu -o build/stem.o &
+$NVCC $FLAGS -Xptxas -v -c csrc/stem_tc.cu -o build/stem_tc.o 2> build/stem_tc.ptxas.log &
 $NVCC $FLAGS -fmad=false -c csrc/geometry.cu -o build/geometry.o &
 $NVCC $FLAGS -c csrc/api.cu -o build/api.o &
 wait
-$NVCC -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/geometry.o build/api.o
+$NVCC -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o
 echo "built $(pwd)/libchessvision_b200.so"

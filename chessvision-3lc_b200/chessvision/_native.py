@@ -51,6 +51,8 @@ SYMBOLS = {
     "cvb_image_to_fen_host": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs)]),
     "cvb_conv2d_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P]),
+    "cvb_unet_stem": (_I, [_P, _P, _I, _P, _P]),
+    "cvb_resnet_stem": (_I, [_P, _P, _I, _P, _P]),
     "cvb_launch_count": (C.c_int64, [_P]),
     "cvb_profile": (_I, [_P, _I]),
     "cvb_profile_read": (_I, [_P, C.POINTER(C.c_float), _I]),
@@ -242,6 +244,20 @@ class Engine:
         n, h, w, cin = x.shape
         self._ck(self.lib.cvb_convt2x2_f16(self.h, _ptr(x), n, h, w, cin, _ptr(w_packed), _ptr(bias4), cout, _ptr(out), out.shape[3],
                                            out_c_off, _stream()), "cvb_convt2x2_f16")
+        return out
+
+    def unet_stem(self, img):
+        n = img.shape[0]
+        assert img.dtype == torch.uint8 and tuple(img.shape[1:]) == (512, 512, 3) and img.is_contiguous()
+        out = torch.empty((n, 256, 256, 64), dtype=torch.float16, device=self.device)
+        self._ck(self.lib.cvb_unet_stem(self.h, _ptr(img), n, _ptr(out), _stream()), "cvb_unet_stem")
+        return out
+
+    def resnet_stem(self, board):
+        n = board.shape[0]
+        assert board.dtype == torch.uint8 and tuple(board.shape[1:]) == (512, 512) and board.is_contiguous()
+        out = torch.empty((n * 64, 16, 16, 64), dtype=torch.float16, device=self.device)
+        self._ck(self.lib.cvb_resnet_stem(self.h, _ptr(board), n, _ptr(out), _stream()), "cvb_resnet_stem")
         return out
 
     def launch_count(self) -> int:

@@ -82,8 +82,12 @@ class ChessVision:
         max_batch: int = 16,
     ):
         logger.info("Initializing ChessVision instance...")
-        self.device = utils.get_device()
-        self._device_index = torch.cuda.current_device() if device_index is None else device_index
+        # construction is lazy like the reference's (core.py:52-64): the GPU is first touched when a model is needed,
+        # and that step raises without an sm_100 device (no CPU fallback)
+        if device_index is None:
+            device_index = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self._device_index = device_index
+        self.device = torch.device("cuda", device_index)
         self._max_batch = max_batch
         self._engine_obj: _native.Engine | None = None
         self._board_extractor: _NetHandle | None = None

@@ -47,7 +47,9 @@ struct cvb_ctx {
 
     // ---- UNet
     bool unet_loaded = false;
-    float *stem_w = nullptr, *stem_b = nullptr;        // inc.double_conv.0 folded, fp32 [27][64], [64]
+    float *stem_w = nullptr, *stem_b = nullptr;        // inc.double_conv.0 folded, fp32 [27][64], [64] (CVB_STEM_FP32 A/B path)
+    void* stem_wsw = nullptr;                          // same layer as a swizzled fp16 [64][64] tcgen05 B tile
+    bool stem_fp32 = false;                            // CVB_STEM_FP32=1: CUDA-core fp32 stems (A/B measurements only)
     float* outc_w = nullptr;                           // [64]
     float outc_b = 0.f;
     std::vector<ConvWeights> unet_w;                   // 17 conv3x3 + 4 convT, in plan order
@@ -65,6 +67,7 @@ struct cvb_ctx {
     // ---- ResNet-18
     bool resnet_loaded = false;
     float *rstem_w = nullptr, *rstem_b = nullptr;      // conv1+bn1 folded fp32 [49][64], [64]
+    void* rstem_wsw = nullptr;                         // conv1+bn1 as a swizzled fp16 [64][64] tcgen05 B tile
     float *fc_w = nullptr, *fc_b = nullptr;            // [13][512], [13]
     std::vector<ConvWeights> res_w;
     __half* rbuf[12] = {nullptr};                      // 3 per resolution level
@@ -219,6 +222,33 @@ int pack_stem(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv
     return 0;
 }
 
+// The same tiny-K layers as one tcgen05 B tile: fp16 [64 cout][64 k] in the 128-byte-swizzled K-major layout the MMA
+// descriptor expects (16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)); k = ky*ky_stride + kx*kx_stride + ci,
+// every other k is zero.  BN scale and the 256/255 factor (inputs enter as v/256, the reference divides by 255) folded.
+int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv, const std::string& bn_prefix, int Cin, int k,
+                 int ky_stride, int kx_stride, void** d_w) {
+    const cvb_tensor* w = find(sd, n, conv + ".weight");
+    if (!w || numel(w) != 64LL * Cin * k * k) return fail(ctx, -4, "missing/bad '%s.weight'", conv.c_str());
+    Bn bn;
+    if (load_bn(ctx, sd, n, bn_prefix, 64, bn)) return -4;
+    std::vector<__half> img(64 * 64, __float2half_rn(0.f));
+    for (int co = 0; co < 64; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int r = 0; r < k; ++r)
+                for (int s = 0; s < k; ++s) {
+                    const int kk = r * ky_stride + s * kx_stride + ci;
+                    const double v = static_cast<double>(w->data[((static_cast<size_t>(co) * Cin + ci) * k + r) * k + s]) *
+                                     static_cast<double>(bn.scale[co]) * (256.0 / 255.0);
+                    const size_t byte = static_cast<size_t>(co) * 128 + (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2;
+                    img[byte / 2] = __float2half_rn(static_cast<float>(v));
+                }
+    __half* d = nullptr;
+    if (dalloc(ctx, &d, img.size())) return -3;
+    CK(cudaMemcpy(d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    *d_w = d;
+    return 0;
+}
+
 void pick_tile(int Ho, int Wo, int& tn, int& th, int& tw) {
     tw = Wo < 16 ? Wo : 16;
     th = 128 / tw;
@@ -324,7 +354,8 @@ int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logi
     auto aux = [&](cudaError_t e) { ctx->launches++; return e; };
     {
         StageTimer t(ctx, 1, s);
-        CK(aux(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, ctx->t0, n, 256, 256, 64, s)));
+        if (ctx->stem_fp32) CK(aux(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, ctx->t0, n, 256, 256, 64, s)));
+        else CK(aux(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, ctx->t0, n, 64, ctx->sm_count, s)));
     }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[0], n, s)) return -2; }                       // inc.3      t0 -> cat0[0:64)
     { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat0, ctx->p1, n, 256, 256, 64, 128, s))); }
@@ -352,7 +383,8 @@ int classify(cvb_ctx* ctx, const uint8_t* board, int n, int flip, float* probs, 
     if (!ctx->resnet_loaded) return fail(ctx, -7, "classifier weights not loaded (call cvb_load_resnet18)");
     {
         StageTimer t(ctx, 4, s);
-        CK(launch_resnet_stem(board, ctx->rstem_w, ctx->rstem_b, ctx->rbuf[0], n, s));
+        if (ctx->stem_fp32) CK(launch_resnet_stem(board, ctx->rstem_w, ctx->rstem_b, ctx->rbuf[0], n, s));
+        else CK(launch_resnet_stem_tc(board, ctx->rstem_wsw, ctx->rstem_b, ctx->rbuf[0], n, ctx->sm_count, s));
         ctx->launches++;
     }
     {
@@ -432,7 +464,9 @@ cvb_ctx* cvb_create(int device, int max_batch) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->use_vr = getenv("CVB_NO_VR") == nullptr;
     if (tmap_init()) { ctx->err = "cuTensorMapEncodeTiled not available from the driver"; return bail(); }
-    if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_quad() != cudaSuccess) {
+    ctx->stem_fp32 = getenv("CVB_STEM_FP32") != nullptr;
+    if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_stems_tc() != cudaSuccess ||
+        configure_quad() != cudaSuccess) {
         ctx->err = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
         return bail();
     }
@@ -521,6 +555,7 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     const int B = ctx->max_batch;
     static const int width[5] = {64, 128, 256, 512, 1024};
     if (pack_stem(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, &ctx->stem_w, &ctx->stem_b)) return -4;
+    if (pack_stem_tc(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, 16, 4, &ctx->stem_wsw)) return -4;
     ctx->unet_w.resize(21);
     auto& W = ctx->unet_w;
     int wi = 0;
@@ -586,6 +621,7 @@ int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     if (ctx->resnet_loaded) return fail(ctx, -8, "classifier weights already loaded");
     const int S = ctx->max_batch * 64;
     if (pack_stem(ctx, sd, n, "conv1", "bn1", 1, 7, &ctx->rstem_w, &ctx->rstem_b)) return -4;
+    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, &ctx->rstem_wsw)) return -4;
     const cvb_tensor* fw = find(sd, n, "fc.weight");
     const cvb_tensor* fb = find(sd, n, "fc.bias");
     if (!fw || !fb || numel(fw) != 13 * 512 || numel(fb) != 13) return fail(ctx, -4, "missing/bad fc tensors");
@@ -786,6 +822,28 @@ int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin,
     set_store(L, static_cast<__half*>(out), out_c_stride, out_c_off, 0, nullptr, 0);
     L.p.convt_cout = Cout;
     return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
+}
+
+int cvb_unet_stem(cvb_ctx* ctx, const uint8_t* img, int N, void* out, void* stream) {
+    if (!ctx || !img || !out || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    if (!ctx->unet_loaded) return fail(ctx, -7, "UNet weights not loaded (call cvb_load_unet)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ctx->stem_fp32) CK(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, static_cast<__half*>(out), N, 256, 256, 64, s));
+    else CK(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, static_cast<__half*>(out), N, 64, ctx->sm_count, s));
+    ctx->launches++;
+    return 0;
+}
+
+int cvb_resnet_stem(cvb_ctx* ctx, const uint8_t* board, int N, void* out, void* stream) {
+    if (!ctx || !board || !out || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    if (!ctx->resnet_loaded) return fail(ctx, -7, "classifier weights not loaded (call cvb_load_resnet18)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (ctx->stem_fp32) CK(launch_resnet_stem(board, ctx->rstem_w, ctx->rstem_b, static_cast<__half*>(out), N, s));
+    else CK(launch_resnet_stem_tc(board, ctx->rstem_wsw, ctx->rstem_b, static_cast<__half*>(out), N, ctx->sm_count, s));
+    ctx->launches++;
+    return 0;
 }
 
 int cvb_profile(cvb_ctx* ctx, int enable) {

@@ -18,6 +18,13 @@ cudaError_t launch_resnet_stem(const uint8_t* board, const float* wf, const floa
 cudaError_t launch_head(const __half* feat, const float* fcw, const float* fcb, float* probs, uint8_t* labels,
                         uint8_t* labels_valid, char* fen, int n_boards, int flip, cudaStream_t s);
 
+// stem_tc.cu: the same two first layers on tcgen05 (wsw = swizzled fp16 [64][64] B tile, see pack_stem_tc in api.cu)
+cudaError_t configure_stems_tc();
+cudaError_t launch_unet_stem_tc(const uint8_t* img, const void* wsw, const float* bias, __half* out, int N, int out_c_stride,
+                                int sm_count, cudaStream_t s);
+cudaError_t launch_resnet_stem_tc(const uint8_t* board, const void* wsw, const float* bias, __half* out, int n_boards, int sm_count,
+                                  cudaStream_t s);
+
 // geometry.cu
 constexpr int kQuadMaxPoints = 8192;     // border points of one contour held in shared memory
 constexpr int kQuadMaxBorders = 32000;   // borders per mask (int16 labels)

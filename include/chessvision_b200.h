@@ -102,6 +102,13 @@ CVB_API int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, in
 CVB_API int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias,
                      int Cout, void* out, int out_c_stride, int out_c_off, void* stream);
 
+/* First layers alone (parity tests): fused preprocessing + first convolution of each network on tcgen05.
+ * cvb_unet_stem:   img u8[N,512,512,3] -> fp16 NHWC [N,256,256,64]  = ReLU(BN(conv3x3(resize_area(img)/255)))  (core.py:212-216,
+ *                  unet_parts.py:16-18);  cvb_resnet_stem: board u8[N,512,512] -> fp16 NHWC [N*64,16,16,64] = maxpool3x3s2(ReLU(BN(
+ *                  conv7x7s2(square/255)))) per square (core.py:232-237, timm resnet18 conv1..maxpool).  Need loaded weights. */
+CVB_API int cvb_unet_stem(cvb_ctx* ctx, const uint8_t* img, int N, void* out, void* stream);
+CVB_API int cvb_resnet_stem(cvb_ctx* ctx, const uint8_t* board, int N, void* out, void* stream);
+
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 CVB_API int64_t cvb_launch_count(const cvb_ctx* ctx);
 

@@ -32,12 +32,13 @@ def resize_area_half(img: np.ndarray) -> np.ndarray:
 
 
 def binary_mask(logits: np.ndarray, threshold: float = 0.5) -> np.ndarray:
-    """f32 logits -> u8 {0,255}.  The reference evaluates an fp32 sigmoid and compares ``> threshold``."""
+    """f32 logits -> u8 {0,255}.  The reference evaluates ``torch.sigmoid`` in fp32 (core.py:273) and compares
+    ``> threshold`` (utils.py:109-112); the same library call is used here because ATen's vectorised fp32 sigmoid is not
+    bit-identical to a naive ``1/(1+exp(-x))`` for 0 < x < 2e-7 (it yields > 0.5 from x = 8.94e-8 on)."""
+    import torch
     assert logits.dtype == np.float32 and 0 <= threshold <= 1
-    x = logits.astype(np.float32)
-    # torch.sigmoid on CPU fp32 == 1/(1+exp(-x)) evaluated in fp32
-    p = (np.float32(1.0) / (np.float32(1.0) + np.exp(-x, dtype=np.float32))).astype(np.float32)
-    return np.where(p > np.float32(threshold), 255, 0).astype(np.uint8)
+    p = torch.sigmoid(torch.from_numpy(np.ascontiguousarray(logits))).numpy()
+    return np.where(p > threshold, 255, 0).astype(np.uint8)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

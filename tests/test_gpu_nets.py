@@ -41,6 +41,37 @@ def random_engine():
     eng.close()
 
 
+def test_unet_stem(random_engine):
+    """Fused INTER_AREA + /255 + conv3x3(3->64) + BN + ReLU on tcgen05 vs the fp32 oracle layer; every image border
+    (zero padding) and every 32x64 work-unit seam is covered because whole images are compared."""
+    eng, unet, _ = random_engine
+    rng = np.random.default_rng(15)
+    imgs = np.stack([synth.board_image(rng)[0] for _ in range(2)] + [rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)])
+    got = eng.unet_stem(torch.from_numpy(imgs).cuda()).float().cpu().permute(0, 3, 1, 2).numpy()
+    with torch.no_grad():
+        x = torch.from_numpy(np.stack([og.resize_area_half(i) for i in imgs])).float().div(255).permute(0, 3, 1, 2)
+        ref = unet.inc.double_conv[:3](x).numpy()
+    err = np.abs(got - ref).max()
+    print(f"unet stem: max-abs err {err:.5f} (activation max {ref.max():.3f})")
+    assert err <= 2e-3 * max(1.0, float(ref.max()))
+
+
+def test_resnet_stem(random_engine):
+    eng, _, cls = random_engine
+    rng = np.random.default_rng(16)
+    boards = rng.integers(0, 256, (3, 512, 512), dtype=np.uint8)
+    boards[2] = (np.kron((np.indices((8, 8)).sum(0) % 2), np.ones((64, 64))) * 255).astype(np.uint8)
+    got = eng.resnet_stem(torch.from_numpy(boards).cuda()).float().cpu().permute(0, 3, 1, 2).numpy()
+    with torch.no_grad():
+        sq = np.stack([og.extract_squares(b) for b in boards]).reshape(-1, 64, 64, 1)
+        x = torch.from_numpy(sq).float().permute(0, 3, 1, 2) / 255.0
+        ref = torch.nn.functional.max_pool2d(torch.relu(cls.bn1(cls.conv1(x))), 3, 2, 1).numpy()
+    err = np.abs(got - ref).max()
+    print(f"resnet stem: max-abs err {err:.5f} (activation max {ref.max():.3f})")
+    assert got.shape == ref.shape == (192, 64, 16, 16)
+    assert err <= 2e-3 * max(1.0, float(ref.max()))
+
+
 def test_unet_forward_random_weights(random_engine):
     eng, unet, _ = random_engine
     rng = np.random.default_rng(5)
