@@ -466,7 +466,7 @@ cvb_ctx* cvb_create(int device, int max_batch) {
     if (tmap_init()) { ctx->err = "cuTensorMapEncodeTiled not available from the driver"; return bail(); }
     ctx->stem_fp32 = getenv("CVB_STEM_FP32") != nullptr;
     if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_stems_tc() != cudaSuccess ||
-        configure_quad() != cudaSuccess) {
+        configure_quad() != cudaSuccess || configure_warp() != cudaSuccess) {
         ctx->err = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
         return bail();
     }

@@ -577,52 +577,178 @@ __global__ void k_homography(const int32_t* __restrict__ quad, const uint8_t* __
 }
 
 // =====================================================================================================================
-// warp + gray + flip.  One CTA per 64x16 destination block (the block shape OpenCV evaluates coordinates in); each
-// thread produces 4 consecutive destination pixels and writes them mirrored as one 32-bit store.
+// warp + gray + flip.  cv2.warpPerspective evaluates, per destination pixel of a 64-wide block starting at bx,
+//     W = W0 + M6*x1;  W = W ? 32/W : 0;  X = rint((X0 + M0*x1)*W);  Y = rint((Y0 + M3*x1)*W)         (float64, no FMA)
+// and interpolates with 5-bit fractions, integer weights and (sum + 2^14) >> 15; BGR2GRAY and the mirror follow.
+//
+// One CTA per 64x64 destination tile (= one chess square of the board image).  The source footprint of the tile is
+// staged once through shared memory (coalesced 48-byte groups -> one BGR0 word per pixel, zeros outside the image),
+// the gather then runs on shared memory with packed 16x8-bit dot products.  Coordinates: the division is replaced by a
+// Newton reciprocal (2^-50 relative error); whenever the result lies within 2^-13 of a rounding boundary, outside the
+// staged patch or out of range, that pixel is recomputed by `warp_px_exact` with the literal OpenCV arithmetic, so the
+// output stays bit-identical.
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
+constexpr int kWpRows = 88;          // staged patch capacity (source rows)
+constexpr int kWpCols16 = 7;         // ... and 16-pixel column groups
+constexpr int kWpStride = 116;       // words per staged row (multiple of 4 for 128-bit stores)
+constexpr int kWpSmem = kWpRows * kWpStride * 4 + 64 * 3 * 8;
+
+// The literal arithmetic for one destination pixel (also used for the tile corners); returns the gray value.
+__device__ __noinline__ uint32_t warp_px_exact(const uint8_t* __restrict__ src, int H, int W, double X0, double Y0, double W0,
+                                              double m0, double m3, double m6, int x1, int* sx_out, int* sy_out, int* wsign) {
+    const double xx = static_cast<double>(x1);
+    double w = W0 + m6 * xx;
+    if (wsign) *wsign = w > 0.0 ? 1 : (w < 0.0 ? -1 : 0);
+    w = w != 0.0 ? 32.0 / w : 0.0;
+    const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + m0 * xx) * w));
+    const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + m3 * xx) * w));
+    const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
+    const int sx = max(-32768, min(32767, Xi >> 5)), sy = max(-32768, min(32767, Yi >> 5));
+    if (sx_out) { *sx_out = sx; *sy_out = sy; }
+    const int ax = Xi & 31, ay = Yi & 31;
+    const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+    int acc[3] = {16384, 16384, 16384};
+    const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
+    const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
+    const uint8_t* p = src + (static_cast<long long>(sy) * W + sx) * 3;
+    if (y0ok && x0ok) { acc[0] += w00 * p[0]; acc[1] += w00 * p[1]; acc[2] += w00 * p[2]; }
+    if (y0ok && x1ok) { acc[0] += w01 * p[3]; acc[1] += w01 * p[4]; acc[2] += w01 * p[5]; }
+    const uint8_t* p2 = p + static_cast<long long>(W) * 3;
+    if (y1ok && x0ok) { acc[0] += w10 * p2[0]; acc[1] += w10 * p2[1]; acc[2] += w10 * p2[2]; }
+    if (y1ok && x1ok) { acc[0] += w11 * p2[3]; acc[1] += w11 * p2[4]; acc[2] += w11 * p2[5]; }
+    const int bl = acc[0] >> 15, gr = acc[1] >> 15, rd = acc[2] >> 15;
+    return static_cast<uint32_t>((3735 * bl + 19235 * gr + 9798 * rd + 16384) >> 15);
+}
+
+__global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
                                                     const uint8_t* __restrict__ found, uint8_t* __restrict__ board, int H,
                                                     int W) {
-    const int b = blockIdx.z;
-    const int bx = blockIdx.x * 64, y = blockIdx.y * 16 + (threadIdx.x >> 4);
-    const int x1 = (threadIdx.x & 15) * 4;
-    uint8_t* dst_row = board + (static_cast<size_t>(b) * 512 + y) * 512;
+    extern __shared__ __align__(16) uint8_t wsm[];
+    uint32_t* patch = reinterpret_cast<uint32_t*>(wsm);
+    double* rowtab = reinterpret_cast<double*>(wsm + kWpRows * kWpStride * 4);   // [64][3]: X0, Y0, W0/32 per tile row
+    __shared__ int s_corner[4][3];
+    const int b = blockIdx.y, t = threadIdx.x;
+    const int bx = (blockIdx.x & 7) * 64, by = (blockIdx.x >> 3) * 64;
+    uint8_t* dst_tile = board + (static_cast<size_t>(b) * 512 + by) * 512 + (448 - bx);   // destination x -> 511 - x
     if (!found[b]) {
-        *reinterpret_cast<uint32_t*>(dst_row + (511 - (bx + x1) - 3)) = 0u;
+        *reinterpret_cast<uint4*>(dst_tile + (t >> 2) * 512 + (t & 3) * 16) = make_uint4(0, 0, 0, 0);
         return;
     }
     const double* m = minv + static_cast<size_t>(b) * 9;
     const double m0 = m[0], m3 = m[3], m6 = m[6];
-    const double X0 = m0 * bx + m[1] * y + m[2];
-    const double Y0 = m3 * bx + m[4] * y + m[5];
-    const double W0 = m6 * bx + m[7] * y + m[8];
     const uint8_t* src = img + static_cast<size_t>(b) * H * W * 3;
-    uint32_t packed = 0;
+    if (t < 64) {
+        const int y = by + t;
+        rowtab[t * 3 + 0] = m0 * bx + m[1] * y + m[2];
+        rowtab[t * 3 + 1] = m3 * bx + m[4] * y + m[5];
+        rowtab[t * 3 + 2] = (m6 * bx + m[7] * y + m[8]) * 0.03125;   // exact scaling
+    }
+    __syncthreads();
+    if (t < 4) {   // source taps of the four tile corners bound the footprint (projective image of a convex tile)
+        const int ry = (t >> 1) * 63;
+        int sx, sy, sg;
+        warp_px_exact(src, H, W, rowtab[ry * 3], rowtab[ry * 3 + 1], rowtab[ry * 3 + 2] * 32.0, m0, m3, m6, (t & 1) * 63, &sx, &sy, &sg);
+        s_corner[t][0] = sx;
+        s_corner[t][1] = sy;
+        s_corner[t][2] = sg;
+    }
+    __syncthreads();
+    int x_min = s_corner[0][0], x_max = x_min, y_min = s_corner[0][1], y_max = y_min;
+    bool fits = s_corner[0][2] != 0 && (W & 15) == 0;
+#pragma unroll
+    for (int c = 1; c < 4; ++c) {
+        x_min = min(x_min, s_corner[c][0]);
+        x_max = max(x_max, s_corner[c][0]);
+        y_min = min(y_min, s_corner[c][1]);
+        y_max = max(y_max, s_corner[c][1]);
+        fits = fits && s_corner[c][2] == s_corner[0][2];
+    }
+    const int x_lo = (x_min - 1) & ~15, y_lo = y_min - 1;
+    const int ncol16 = (x_max + 3 - x_lo + 15) >> 4;     // columns x_lo .. x_max + 2
+    const int nrows = y_max + 3 - y_lo;                  // rows    y_lo .. y_max + 2
+    fits = fits && ncol16 <= kWpCols16 && nrows <= kWpRows && x_max - x_min < 4096 && y_max - y_min < 4096;
+    if (fits) {
+        for (int g = t; g < nrows * ncol16; g += 256) {
+            const int r = g / ncol16, c16 = g - r * ncol16;
+            const int gy = y_lo + r, gx = x_lo + 16 * c16;
+            uint32_t w[12];
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(gy) * W + gx) * 3);
+                const uint4 a = __ldg(s4), c = __ldg(s4 + 1), d = __ldg(s4 + 2);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
+                w[8] = d.x; w[9] = d.y; w[10] = d.z; w[11] = d.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) w[i] = 0u;
+            }
+            uint32_t o[16];   // pixel k = bytes 3k..3k+2 -> (B,G,R,x); the top byte is never read
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                o[4 * k + 0] = w[3 * k];
+                o[4 * k + 1] = __byte_perm(w[3 * k], w[3 * k + 1], 0x6543);
+                o[4 * k + 2] = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
+                o[4 * k + 3] = w[3 * k + 2] >> 8;
+            }
+            uint4* d4 = reinterpret_cast<uint4*>(patch + r * kWpStride + 16 * c16);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) d4[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        }
+    }
+    __syncthreads();
+    const int xq = t & 15, yq = t >> 4;
+    double c0[4], c3[4], c6[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double xx = static_cast<double>(x1 + i);
-        double w = W0 + m6 * xx;
-        w = w != 0.0 ? 32.0 / w : 0.0;
-        const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + m0 * xx) * w));
-        const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + m3 * xx) * w));
-        const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
-        const int sx = max(-32768, min(32767, Xi >> 5)), sy = max(-32768, min(32767, Yi >> 5));
-        const int ax = Xi & 31, ay = Yi & 31;
-        const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
-        int acc[3] = {16384, 16384, 16384};
-        const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
-        const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
-        const uint8_t* p = src + (static_cast<long long>(sy) * W + sx) * 3;
-        if (y0ok && x0ok) { acc[0] += w00 * p[0]; acc[1] += w00 * p[1]; acc[2] += w00 * p[2]; }
-        if (y0ok && x1ok) { acc[0] += w01 * p[3]; acc[1] += w01 * p[4]; acc[2] += w01 * p[5]; }
-        const uint8_t* p2 = p + static_cast<long long>(W) * 3;
-        if (y1ok && x0ok) { acc[0] += w10 * p2[0]; acc[1] += w10 * p2[1]; acc[2] += w10 * p2[2]; }
-        if (y1ok && x1ok) { acc[0] += w11 * p2[3]; acc[1] += w11 * p2[4]; acc[2] += w11 * p2[5]; }
-        const int bl = acc[0] >> 15, gr = acc[1] >> 15, rd = acc[2] >> 15;
-        const uint32_t gray = static_cast<uint32_t>((3735 * bl + 19235 * gr + 9798 * rd + 16384) >> 15);
-        packed |= gray << (8 * (3 - i));  // destination x -> 511 - x
+        const double xx = static_cast<double>(4 * xq + i);
+        c0[i] = m0 * xx;
+        c3[i] = m3 * xx;
+        c6[i] = (m6 * xx) * 0.03125;
     }
-    *reinterpret_cast<uint32_t*>(dst_row + (511 - (bx + x1) - 3)) = packed;
+    const unsigned lim_x = static_cast<unsigned>(ncol16 * 16 - 1), lim_y = static_cast<unsigned>(nrows - 1);
+    constexpr double kMagic = 103079215104.0;   // 1.5 * 2^36: the low word of (v + kMagic) is rint(v * 2^16)
+    constexpr int kMagicHi = 0x42380000;        // high word of kMagic
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int ry = yq + 16 * j;
+        const double X0 = rowtab[ry * 3], Y0 = rowtab[ry * 3 + 1], W0s = rowtab[ry * 3 + 2];
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double Xn = X0 + c0[i], Yn = Y0 + c3[i], ws = W0s + c6[i];
+            double r = static_cast<double>(__frcp_rn(__double2float_rn(ws)));
+            double e = fma(-ws, r, 1.0);
+            r = fma(r, e, r);
+            e = fma(-ws, r, 1.0);
+            r = fma(r, e, r);
+            const double tx = Xn * r + kMagic, ty = Yn * r + kMagic;
+            const int vx = __double2loint(tx), vy = __double2loint(ty);
+            // in range (|v| < 2^15): the high word is kMagicHi, minus one when the low word borrowed
+            bool ok = fits && (__double2hiint(tx) - (vx >> 31)) == kMagicHi && (__double2hiint(ty) - (vy >> 31)) == kMagicHi;
+            const int ax16 = static_cast<int>(static_cast<unsigned>(vx) + 0x8000u), ay16 = static_cast<int>(static_cast<unsigned>(vy) + 0x8000u);
+            ok = ok && ((static_cast<unsigned>(ax16) + 8u) & 0xffffu) >= 16u && ((static_cast<unsigned>(ay16) + 8u) & 0xffffu) >= 16u;   // not within 2^-13 of a tie
+            const int Xi = ax16 >> 16, Yi = ay16 >> 16;
+            const int lx = (Xi >> 5) - x_lo, ly = (Yi >> 5) - y_lo;
+            ok = ok && static_cast<unsigned>(lx) < lim_x && static_cast<unsigned>(ly) < lim_y;
+            uint32_t gray;
+            if (ok) {
+                const uint32_t* p = patch + ly * kWpStride + lx;
+                const uint32_t p00 = p[0], p01 = p[1], p10 = p[kWpStride], p11 = p[kWpStride + 1];
+                const uint32_t ax = Xi & 31, ay = Yi & 31;
+                const uint32_t u = ax * 0xffffu + 32u;             // (32-ax) | ax << 16
+                const uint32_t wr0 = u * (32u - ay), wr1 = u * ay; // row weights, 16 bits each, sum 1024
+                const uint32_t bg0 = __byte_perm(p00, p01, 0x5140), r0 = __byte_perm(p00, p01, 0x6262);
+                const uint32_t bg1 = __byte_perm(p10, p11, 0x5140), r1 = __byte_perm(p10, p11, 0x6262);
+                const uint32_t bl = __dp2a_lo(wr1, bg1, __dp2a_lo(wr0, bg0, 512u)) >> 10;
+                const uint32_t gr = __dp2a_hi(wr1, bg1, __dp2a_hi(wr0, bg0, 512u)) >> 10;
+                const uint32_t rd = __dp2a_lo(wr1, r1, __dp2a_lo(wr0, r0, 512u)) >> 10;
+                gray = (3735u * bl + 19235u * gr + 9798u * rd + 16384u) >> 15;
+            } else {
+                gray = warp_px_exact(src, H, W, X0, Y0, W0s * 32.0, m0, m3, m6, 4 * xq + i, nullptr, nullptr, nullptr);
+            }
+            packed |= gray << (8 * (3 - i));
+        }
+        *reinterpret_cast<uint32_t*>(dst_tile + ry * 512 + (60 - 4 * xq)) = packed;
+    }
 }
 
 }  // namespace
@@ -634,11 +760,15 @@ cudaError_t launch_homography(const int32_t* quad, const uint8_t* found, double*
     return cudaGetLastError();
 }
 
+cudaError_t configure_warp() {
+    return cudaFuncSetAttribute(k_warp_board, cudaFuncAttributeMaxDynamicSharedMemorySize, kWpSmem);
+}
+
 cudaError_t launch_warp_board(const uint8_t* img, const double* minv, const uint8_t* found, uint8_t* board, int N, int H,
                               int W, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
-    dim3 grid(8, 32, N);
-    k_warp_board<<<grid, 256, 0, s>>>(img, minv, found, board, H, W);
+    dim3 grid(64, N);
+    k_warp_board<<<grid, 256, kWpSmem, s>>>(img, minv, found, board, H, W);
     return cudaGetLastError();
 }
 

@@ -33,6 +33,7 @@ constexpr int kQuadMaxVertices = 2048;   // vertices after the TC89_KCOS reducti
 enum QuadStatus : int { QUAD_NONE = 0, QUAD_FOUND = 1, QUAD_OVERFLOW = 2 };
 
 cudaError_t configure_quad();
+cudaError_t configure_warp();
 // mask u8 [N,256,256]; quad int32 [N,4,2] (x,y in the 256x256 mask frame, after _rotate_quadrangle);
 // found u8 [N]; status int32 [N]; owner_scratch int32 [N, kQuadMaxBorders]
 cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* found, int32_t* status, int32_t* n_contours,

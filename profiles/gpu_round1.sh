@@ -8,4 +8,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python profiles/prof_step.py --boards 128 --warmup 1 --steps 1 > gpurun_out/prof_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'conv|stem' -s 43 -c 43 -o gpurun_out/prof_conv \
     python profiles/prof_step.py --boards 32 --warmup 1 --steps 1 > gpurun_out/prof_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'mask_to_quad|warp_board' -s 2 -c 2 -o gpurun_out/prof_geom \
+    python profiles/prof_step.py --boards 128 --warmup 1 --steps 1 > gpurun_out/prof_geom.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.json
