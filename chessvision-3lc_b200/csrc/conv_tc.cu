@@ -21,6 +21,8 @@
 
 namespace cvb {
 
+constexpr int kEpiConstBytes = 256 * 4 + 64 * 4;   // per-tile bias (<= 256 columns) + the 1x1 head weights
+
 template <int BLOCK_N>
 struct ConvCfg {
     static constexpr int kABytes = 128 * 128;
@@ -28,81 +30,94 @@ struct ConvCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
     static constexpr int kTmemCols = 2 * BLOCK_N;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiConstBytes;
 };
 
-// Epilogue of one 128-row accumulator tile: thread <-> output pixel (n,h,w); columns in chunks of 32.
+// Epilogue of one 32-column chunk held in registers: thread <-> output pixel (n,h,w).  s_bias / s_outw live in shared memory.
 template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int n, int h, int w, bool valid, int n_tile) {
-    const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
-    float dot = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c0, v);
-        tmem_ld_wait();
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int c0, size_t pix, int n, int h, int w,
+                                               bool valid, int n_tile, const float* s_bias, const float* s_outw, float& dot) {
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
+    if constexpr (EPI == EPI_OUTC) {
+        const float4* w4 = reinterpret_cast<const float4*>(s_outw + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = b4[i];
+            const float4 wv = w4[i];
+            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
+            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
+            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
+            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
+        }
+    } else {
         const int col0 = n_tile * BLOCK_N + c0;
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-        if constexpr (EPI == EPI_OUTC) {
-            const float4* w4 = reinterpret_cast<const float4*>(p.outc_w + col0);
+        float f[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(b4 + i);
-                const float4 wv = __ldg(w4 + i);
-                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
-                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
-                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
-                dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
-            }
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = b4[i];
+            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+        }
+        __half* dst;
+        if constexpr (EPI == EPI_CONVT) {
+            const int q = col0 / p.convt_cout;
+            const int co = col0 - q * p.convt_cout;
+            const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
+            dst = p.out + opix * p.out_c_stride + p.out_c_off + co;
         } else {
-            float f[32];
+            dst = p.out + pix * p.out_c_stride + p.out_c_off + col0;
+            if (p.res != nullptr && valid) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_c_stride + col0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 b = __ldg(b4 + i);
-                f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
-                f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-                f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
-                f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
-            }
-            __half* dst;
-            if constexpr (EPI == EPI_CONVT) {
-                const int q = col0 / p.convt_cout;
-                const int co = col0 - q * p.convt_cout;
-                const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
-                dst = p.out + opix * p.out_c_stride + p.out_c_off + co;
-            } else {
-                dst = p.out + pix * p.out_c_stride + p.out_c_off + col0;
-                if (p.res != nullptr && valid) {
-                    const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_c_stride + col0);
+                for (int i = 0; i < 4; ++i) {
+                    const uint4 r = __ldg(r4 + i);
+                    const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint4 r = __ldg(r4 + i);
-                        const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 rf = __half22float2(rh2[j]);
-                            f[8 * i + 2 * j] += rf.x;
-                            f[8 * i + 2 * j + 1] += rf.y;
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 rf = __half22float2(rh2[j]);
+                        f[8 * i + 2 * j] += rf.x;
+                        f[8 * i + 2 * j + 1] += rf.y;
                     }
                 }
             }
-            if (p.relu) {
+        }
+        if (p.relu) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            if (valid) {
-                uint4* d4 = reinterpret_cast<uint4*>(dst);
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (valid) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint4 o;
-                    __half2* oh = reinterpret_cast<__half2*>(&o);
+            for (int i = 0; i < 4; ++i) {
+                uint4 o;
+                __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
-                    d4[i] = o;
-                }
+                for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
+                d4[i] = o;
             }
         }
+    }
+}
+
+// Epilogue of one 128-row accumulator tile: the TMEM load of chunk c+1 is in flight while chunk c is processed.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int n, int h, int w, bool valid, int n_tile,
+                                              const float* s_bias, const float* s_outw) {
+    constexpr int NC = BLOCK_N / 32;
+    const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
+    float dot = 0.f;
+    uint32_t va[32], vb[32];
+    tmem_ld_32x32(taddr, va);
+#pragma unroll
+    for (int c = 0; c < NC; c += 2) {
+        tmem_ld_wait(va);
+        tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+        epilogue_chunk<BLOCK_N, EPI>(p, va, c * 32, pix, n, h, w, valid, n_tile, s_bias, s_outw, dot);
+        tmem_ld_wait(vb);
+        if (c + 2 < NC) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+        epilogue_chunk<BLOCK_N, EPI>(p, vb, (c + 1) * 32, pix, n, h, w, valid, n_tile, s_bias, s_outw, dot);
     }
     if constexpr (EPI == EPI_OUTC) {
         if (valid) {
@@ -112,6 +127,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             p.mask[pix] = prob > p.thr ? 255 : 0;
         }
     }
+}
+
+// Epilogue warps: (re)load the per-column constants of `n_tile` into shared memory (all 128 epilogue threads call this).
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_consts(const ConvParams& p, int n_tile, float* s_bias, float* s_outw, int etid) {
+    named_bar_sync(1, 128);   // nobody still reads the previous tile's constants
+    for (int i = etid; i < BLOCK_N; i += 128) s_bias[i] = __ldg(p.bias + n_tile * BLOCK_N + i);
+    if constexpr (EPI == EPI_OUTC) {
+        if (etid < 64) s_outw[etid] = __ldg(p.outc_w + etid);
+    }
+    named_bar_sync(1, 128);
 }
 
 template <int BLOCK_N, int EPI>
@@ -159,45 +185,46 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     const int k_steps = p.taps * p.c_chunks;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n_tile = t % p.n_tiles;
-                const int m_tile = t / p.n_tiles;
-                const int w0 = (m_tile % p.tiles_w) * p.tw;
-                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-                const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    const CUtensorMap* amap = &p.a_map[p.tap_map[tap]];
-                    const int hh = h0 + p.tap_dy[tap];
-                    const int ww = w0 + p.tap_dx[tap];
-                    for (int kc = 0; kc < p.c_chunks; ++kc) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n_tile = t % p.n_tiles;
+            const int m_tile = t / p.n_tiles;
+            const int w0 = (m_tile % p.tiles_w) * p.tw;
+            const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                const CUtensorMap* amap = &p.a_map[p.tap_map[tap]];
+                const int hh = h0 + p.tap_dy[tap];
+                const int ww = w0 + p.tap_dx[tap];
+                for (int kc = 0; kc < p.c_chunks; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
                         const uint32_t a_dst = tiles_addr + stage * Cfg::kStageBytes;
                         const uint32_t b_dst = a_dst + Cfg::kABytes;
                         mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
                         tma_load_4d(a_dst, amap, bar_full + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
                         tma_load_2d(b_dst, &p.b_map, bar_full + 8 * stage, (tap * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
-                        if (++stage == S) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int iter = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-                const int acc = iter & 1;
-                const uint32_t acc_phase = (iter >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kb = 0; kb < k_steps; ++kb) {
+                mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < k_steps; ++kb) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t a_addr = tiles_addr + stage * Cfg::kStageBytes;
                     const uint64_t a_desc = umma_desc_sw128(a_addr);
                     const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
@@ -207,9 +234,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                         umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(bar_empty + 8 * stage);
-                    if (++stage == S) { stage = 0; phase ^= 1; }
+                    if (kb == k_steps - 1) umma_commit(bar_tfull + 8 * acc);
                 }
-                umma_commit(bar_tfull + 8 * acc);
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -218,12 +246,18 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         const int rn = row / (p.th * p.tw);
         const int rh = (row / p.tw) % p.th;
         const int rw = row % p.tw;
-        int iter = 0;
+        float* s_bias = reinterpret_cast<float*>(tiles_ptr + S * Cfg::kStageBytes + 256);
+        float* s_outw = s_bias + 256;
+        int iter = 0, cur_nt = -1;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int n_tile = t % p.n_tiles;
             const int m_tile = t / p.n_tiles;
+            if (n_tile != cur_nt) {
+                epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
+                cur_nt = n_tile;
+            }
             const int w = (m_tile % p.tiles_w) * p.tw + rw;
             const int h = ((m_tile / p.tiles_w) % p.tiles_h) * p.th + rh;
             const int n = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn + rn;
@@ -231,7 +265,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, valid, n_tile);
+            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, valid, n_tile, s_bias, s_outw);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
@@ -305,22 +339,23 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
 
     if (warp == 0) {
-        if (lane == 0) {
-            if (W_STAT) {
-                mbar_expect_tx(bar_w, w_bytes);
-                for (int i = 0; i < 9 * p.c_chunks; ++i) tma_load_2d(base_addr + i * kBBytes, &p.b_map, bar_w, i * 64, 0);
-            }
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int n_tile = t % p.n_tiles;
-                const int m_tile = t / p.n_tiles;
-                const int w0 = (m_tile % p.tiles_w) * 8;
-                const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * 16;
-                const int n0 = m_tile / (p.tiles_w * p.tiles_h);
-                for (int kc = 0; kc < p.c_chunks; ++kc) {
-                    for (int dxi = 0; dxi < 3; ++dxi) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+        if (W_STAT && elect_one()) {
+            mbar_expect_tx(bar_w, w_bytes);
+            for (int i = 0; i < 9 * p.c_chunks; ++i) tma_load_2d(base_addr + i * kBBytes, &p.b_map, bar_w, i * 64, 0);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int n_tile = t % p.n_tiles;
+            const int m_tile = t / p.n_tiles;
+            const int w0 = (m_tile % p.tiles_w) * 8;
+            const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * 16;
+            const int n0 = m_tile / (p.tiles_w * p.tiles_h);
+            for (int kc = 0; kc < p.c_chunks; ++kc) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
                         const uint32_t a_dst = stages_addr + stage * kStageBytes;
                         mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
                         tma_load_4d(a_dst, &p.a_map[0], bar_full + 8 * stage, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
@@ -330,68 +365,74 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
                                 tma_load_2d(a_dst + kABytes + dy * kBBytes, &p.b_map, bar_full + 8 * stage,
                                             ((dy * 3 + dxi) * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
                         }
-                        if (++stage == S) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            if (W_STAT) {
-                mbar_wait(bar_w, 0);
-                tc_fence_after();
-            }
-            int stage = 0;
-            uint32_t phase = 0;
-            int iter = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-                const int acc = iter & 1;
-                const uint32_t acc_phase = (iter >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                uint32_t first = 0;
-                for (int kc = 0; kc < p.c_chunks; ++kc) {
-                    for (int dxi = 0; dxi < 3; ++dxi) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
+        if (W_STAT) {
+            mbar_wait(bar_w, 0);
+            tc_fence_after();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+            for (int kc = 0; kc < p.c_chunks; ++kc) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t a_addr = stages_addr + stage * kStageBytes;
+                        const uint64_t a_desc0 = umma_desc_sw128(a_addr);
+                        const uint64_t b_desc0 = umma_desc_sw128(W_STAT ? base_addr + (dxi * p.c_chunks + kc) * kBBytes : a_addr + kABytes);
+                        // tap dy: the A tile 1024 B (one 8-row swizzle group) further, the weight tile 3*c_chunks (or 1) tiles further
+                        const uint32_t b_step = (W_STAT ? 3u * p.c_chunks * kBBytes : static_cast<uint32_t>(kBBytes)) >> 4;
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
-                            const uint32_t b_addr = W_STAT ? base_addr + ((dy * 3 + dxi) * p.c_chunks + kc) * kBBytes
-                                                           : a_addr + kABytes + dy * kBBytes;
-                            const uint64_t a_desc = umma_desc_sw128(a_addr + dy * 1024);
-                            const uint64_t b_desc = umma_desc_sw128(b_addr);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc, first);
-                                first = 1;
-                            }
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(d_tmem, a_desc0 + dy * 64 + 2 * k, b_desc0 + dy * b_step + 2 * k, p.idesc,
+                                         (kc | dxi | dy | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(bar_empty + 8 * stage);
-                        if (++stage == S) { stage = 0; phase ^= 1; }
+                        if (kc == p.c_chunks - 1 && dxi == 2) umma_commit(bar_tfull + 8 * acc);
                     }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(bar_tfull + 8 * acc);
             }
         }
     } else if (warp >= 4) {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int rh = row >> 3, rw = row & 7;
-        int iter = 0;
+        float* s_bias = reinterpret_cast<float*>(base_ptr + w_bytes + S * kStageBytes + 256);
+        float* s_outw = s_bias + 256;
+        int iter = 0, cur_nt = -1;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int n_tile = t % p.n_tiles;
             const int m_tile = t / p.n_tiles;
+            if (n_tile != cur_nt) {
+                epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
+                cur_nt = n_tile;
+            }
             const int w = (m_tile % p.tiles_w) * 8 + rw;
             const int h = ((m_tile / p.tiles_w) % p.tiles_h) * 16 + rh;
             const int n = m_tile / (p.tiles_w * p.tiles_h);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, n < p.N, n_tile);
+            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, n < p.N, n_tile, s_bias, s_outw);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
@@ -494,7 +535,7 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
     const int b_bytes = L.block_n * 128;
     const int w_bytes = 9 * (Cin / 64) * b_bytes;
-    const int budget = kVrMaxSmem - 1024 - 256;
+    const int budget = kVrMaxSmem - 1024 - 256 - kEpiConstBytes;
     const bool ws = p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
     if (L.epilogue == EPI_OUTC && !ws) return false;
     const int stage = 18 * 1024 + (ws ? 0 : 3 * b_bytes);
@@ -503,7 +544,7 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     if (stages < 2) return false;
     p.vr_stages = stages;
     p.w_stationary = ws ? 1 : 0;
-    p.smem_bytes = (ws ? w_bytes : 0) + stages * stage + 1024 + 256;
+    p.smem_bytes = (ws ? w_bytes : 0) + stages * stage + 1024 + 256 + kEpiConstBytes;
     p.tn = 1; p.th = 16; p.tw = 8;
     p.tiles_w = Wo / 8;
     p.tiles_h = Ho / 16;

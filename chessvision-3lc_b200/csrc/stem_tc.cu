@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* _
                 }
             }
         }
-    } else if (lane == 0) {
+    } else {
         // ------------------------------------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_f16(128, 64, 0);
         int stage = 0, iter = 0;
@@ -240,9 +240,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* _
                 mbar_wait(b.tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
                 mbar_wait(b.full + 8 * stage, phase);
                 tc_fence_after();
-                mma_tile(base_addr + kRsOffA + stage * kABytes, base_addr, tmem_base + acc * 64, idesc);
-                umma_commit(b.empty + 8 * stage);
-                umma_commit(b.tfull + 8 * acc);
+                if (elect_one()) {
+                    mma_tile(base_addr + kRsOffA + stage * kABytes, base_addr, tmem_base + acc * 64, idesc);
+                    umma_commit(b.empty + 8 * stage);
+                    umma_commit(b.tfull + 8 * acc);
+                }
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
                 }
             }
         }
-    } else if (lane == 0) {
+    } else {
         // ------------------------------------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_f16(128, 64, 0);
         int stage = 0, iter = 0;
@@ -397,9 +400,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
                 mbar_wait(b.tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
                 mbar_wait(b.full + 8 * stage, phase);
                 tc_fence_after();
-                mma_tile(base_addr + kUsOffA + stage * kABytes, base_addr, tmem_base + acc * 64, idesc);
-                umma_commit(b.empty + 8 * stage);
-                umma_commit(b.tfull + 8 * acc);
+                if (elect_one()) {
+                    mma_tile(base_addr + kUsOffA + stage * kABytes, base_addr, tmem_base + acc * 64, idesc);
+                    umma_commit(b.empty + 8 * stage);
+                    umma_commit(b.tfull + 8 * acc);
+                }
+                __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
