@@ -307,6 +307,7 @@ int build_conv(cvb_ctx* ctx, ConvLaunch& L, const __half* in, int Nmax, int Hin,
     if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (weights) failed: %d", rc);
     p.bias = cw.bias;
     L.epilogue = epilogue;
+    L.n_max = Nmax;
     if (ctx->use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
         if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (vertical-reuse view) failed: %d", rc);
@@ -314,13 +315,33 @@ int build_conv(cvb_ctx* ctx, ConvLaunch& L, const __half* in, int Nmax, int Hin,
     return 0;
 }
 
-void set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride) {
-    L.p.out = out;
-    L.p.out_c_stride = out_c_stride;
-    L.p.out_c_off = out_c_off;
-    L.p.relu = relu;
-    L.p.res = res;
-    L.p.res_c_stride = res_c_stride;
+// Output side of a launch: NHWC fp16 buffer with `out_c_stride` channels per pixel, first output channel `out_c_off`.
+// Builds the TMA store views (box {64 ch, tw, th, tn}); the transposed convolution gets one stride-2 view per (dy,dx).
+int set_store(cvb_ctx* ctx, ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride) {
+    ConvParams& p = L.p;
+    p.out = out;
+    p.out_c_stride = out_c_stride;
+    p.out_c_off = out_c_off;
+    p.relu = relu;
+    p.res = res;
+    p.res_c_stride = res_c_stride;
+    if (L.epilogue == EPI_OUTC) {
+        p.out_bufs = 0;
+        return 0;
+    }
+    if (L.variant == 0) p.out_bufs = 2;
+    int rc = 0;
+    const int64_t C = out_c_stride;
+    if (L.epilogue == EPI_CONVT) {
+        const int64_t W2 = 2 * p.W, H2 = 2 * p.H;
+        for (int q = 0; q < 4 && !rc; ++q)
+            rc = tmap_act(&p.o_map[q], out + ((q >> 1) * W2 + (q & 1)) * C, out_c_stride, p.W, p.H, L.n_max, 2 * C, 2 * W2 * C, H2 * W2 * C,
+                          p.tw, p.th, p.tn);
+    } else {
+        rc = tmap_act(&p.o_map[0], out, out_c_stride, p.W, p.H, L.n_max, C, p.W * C, static_cast<int64_t>(p.H) * p.W * C, p.tw, p.th, p.tn);
+    }
+    if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (output view) failed: %d", rc);
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------------ profiling
@@ -585,29 +606,30 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     P.resize(21);
     int rc = 0;
     // encoder
-    rc |= build_conv(ctx, P[0], ctx->t0, B, 256, 256, 64, 0, 64, W[0], 3, 1, EPI_STORE);      set_store(P[0], ctx->cat0, 128, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[1], ctx->p1, B, 128, 128, 64, 0, 64, W[1], 3, 1, EPI_STORE);      set_store(P[1], ctx->t1, 128, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[2], ctx->t1, B, 128, 128, 128, 0, 128, W[2], 3, 1, EPI_STORE);    set_store(P[2], ctx->cat1, 256, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[3], ctx->p2, B, 64, 64, 128, 0, 128, W[3], 3, 1, EPI_STORE);      set_store(P[3], ctx->t2, 256, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[4], ctx->t2, B, 64, 64, 256, 0, 256, W[4], 3, 1, EPI_STORE);      set_store(P[4], ctx->cat2, 512, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[5], ctx->p3, B, 32, 32, 256, 0, 256, W[5], 3, 1, EPI_STORE);      set_store(P[5], ctx->t3, 512, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[6], ctx->t3, B, 32, 32, 512, 0, 512, W[6], 3, 1, EPI_STORE);      set_store(P[6], ctx->cat3, 1024, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[7], ctx->p4, B, 16, 16, 512, 0, 512, W[7], 3, 1, EPI_STORE);      set_store(P[7], ctx->t4, 1024, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[8], ctx->t4, B, 16, 16, 1024, 0, 1024, W[8], 3, 1, EPI_STORE);    set_store(P[8], ctx->x5, 1024, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[0], ctx->t0, B, 256, 256, 64, 0, 64, W[0], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[0], ctx->cat0, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[1], ctx->p1, B, 128, 128, 64, 0, 64, W[1], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[1], ctx->t1, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[2], ctx->t1, B, 128, 128, 128, 0, 128, W[2], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[2], ctx->cat1, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[3], ctx->p2, B, 64, 64, 128, 0, 128, W[3], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[3], ctx->t2, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[4], ctx->t2, B, 64, 64, 256, 0, 256, W[4], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[4], ctx->cat2, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[5], ctx->p3, B, 32, 32, 256, 0, 256, W[5], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[5], ctx->t3, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[6], ctx->t3, B, 32, 32, 512, 0, 512, W[6], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[6], ctx->cat3, 1024, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[7], ctx->p4, B, 16, 16, 512, 0, 512, W[7], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[7], ctx->t4, 1024, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[8], ctx->t4, B, 16, 16, 1024, 0, 1024, W[8], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[8], ctx->x5, 1024, 0, 1, nullptr, 0);
     // decoder: convT writes the upper channel half of the concat buffer (torch.cat([skip, up]), unet_parts.py:67)
-    rc |= build_conv(ctx, P[9], ctx->x5, B, 16, 16, 1024, 0, 1024, W[9], 1, 1, EPI_CONVT);    set_store(P[9], ctx->cat3, 1024, 512, 0, nullptr, 0);  P[9].p.convt_cout = 512;
-    rc |= build_conv(ctx, P[10], ctx->cat3, B, 32, 32, 1024, 0, 1024, W[10], 3, 1, EPI_STORE); set_store(P[10], ctx->t3, 512, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[11], ctx->t3, B, 32, 32, 512, 0, 512, W[11], 3, 1, EPI_STORE);    set_store(P[11], ctx->u1, 512, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[12], ctx->u1, B, 32, 32, 512, 0, 512, W[12], 1, 1, EPI_CONVT);    set_store(P[12], ctx->cat2, 512, 256, 0, nullptr, 0);  P[12].p.convt_cout = 256;
-    rc |= build_conv(ctx, P[13], ctx->cat2, B, 64, 64, 512, 0, 512, W[13], 3, 1, EPI_STORE);  set_store(P[13], ctx->t2, 256, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[14], ctx->t2, B, 64, 64, 256, 0, 256, W[14], 3, 1, EPI_STORE);    set_store(P[14], ctx->u2, 256, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[15], ctx->u2, B, 64, 64, 256, 0, 256, W[15], 1, 1, EPI_CONVT);    set_store(P[15], ctx->cat1, 256, 128, 0, nullptr, 0);  P[15].p.convt_cout = 128;
-    rc |= build_conv(ctx, P[16], ctx->cat1, B, 128, 128, 256, 0, 256, W[16], 3, 1, EPI_STORE); set_store(P[16], ctx->t1, 128, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[17], ctx->t1, B, 128, 128, 128, 0, 128, W[17], 3, 1, EPI_STORE);  set_store(P[17], ctx->u3, 128, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[18], ctx->u3, B, 128, 128, 128, 0, 128, W[18], 1, 1, EPI_CONVT);  set_store(P[18], ctx->cat0, 128, 64, 0, nullptr, 0);   P[18].p.convt_cout = 64;
-    rc |= build_conv(ctx, P[19], ctx->cat0, B, 256, 256, 128, 0, 128, W[19], 3, 1, EPI_STORE); set_store(P[19], ctx->t0, 64, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[9], ctx->x5, B, 16, 16, 1024, 0, 1024, W[9], 1, 1, EPI_CONVT);    rc |= set_store(ctx, P[9], ctx->cat3, 1024, 512, 0, nullptr, 0);  P[9].p.convt_cout = 512;
+    rc |= build_conv(ctx, P[10], ctx->cat3, B, 32, 32, 1024, 0, 1024, W[10], 3, 1, EPI_STORE); rc |= set_store(ctx, P[10], ctx->t3, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[11], ctx->t3, B, 32, 32, 512, 0, 512, W[11], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[11], ctx->u1, 512, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[12], ctx->u1, B, 32, 32, 512, 0, 512, W[12], 1, 1, EPI_CONVT);    rc |= set_store(ctx, P[12], ctx->cat2, 512, 256, 0, nullptr, 0);  P[12].p.convt_cout = 256;
+    rc |= build_conv(ctx, P[13], ctx->cat2, B, 64, 64, 512, 0, 512, W[13], 3, 1, EPI_STORE);  rc |= set_store(ctx, P[13], ctx->t2, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[14], ctx->t2, B, 64, 64, 256, 0, 256, W[14], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[14], ctx->u2, 256, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[15], ctx->u2, B, 64, 64, 256, 0, 256, W[15], 1, 1, EPI_CONVT);    rc |= set_store(ctx, P[15], ctx->cat1, 256, 128, 0, nullptr, 0);  P[15].p.convt_cout = 128;
+    rc |= build_conv(ctx, P[16], ctx->cat1, B, 128, 128, 256, 0, 256, W[16], 3, 1, EPI_STORE); rc |= set_store(ctx, P[16], ctx->t1, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[17], ctx->t1, B, 128, 128, 128, 0, 128, W[17], 3, 1, EPI_STORE);  rc |= set_store(ctx, P[17], ctx->u3, 128, 0, 1, nullptr, 0);
+    rc |= build_conv(ctx, P[18], ctx->u3, B, 128, 128, 128, 0, 128, W[18], 1, 1, EPI_CONVT);  rc |= set_store(ctx, P[18], ctx->cat0, 128, 64, 0, nullptr, 0);   P[18].p.convt_cout = 64;
+    rc |= build_conv(ctx, P[19], ctx->cat0, B, 256, 256, 128, 0, 128, W[19], 3, 1, EPI_STORE); rc |= set_store(ctx, P[19], ctx->t0, 64, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[20], ctx->t0, B, 256, 256, 64, 0, 64, W[20], 3, 1, EPI_OUTC);     // + outc 1x1 + sigmoid/threshold
     P[20].p.relu = 1;
+    P[20].p.out_bufs = 0;
     P[20].p.outc_w = ctx->outc_w;
     P[20].p.outc_b = ctx->outc_b;
     if (rc) return -5;
@@ -639,7 +661,7 @@ int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
         if (pack_conv(ctx, sd, n, conv, bn, cout, cin, k, ctx->res_w.back())) { rc = -4; return; }
         ctx->res_plan.emplace_back();
         if (build_conv(ctx, ctx->res_plan.back(), in, S, Hin, Hin, cin, 0, cin, ctx->res_w.back(), k, stride, EPI_STORE)) { rc = -5; return; }
-        set_store(ctx->res_plan.back(), out, cout, 0, relu, res, cout);
+        if (set_store(ctx, ctx->res_plan.back(), out, cout, 0, relu, res, cout)) { rc = -6; return; }
     };
     // Buffers per level: a = rbuf[3l], b = rbuf[3l+1], c = rbuf[3l+2].  Level input arrives in `x`.
     __half* x = ctx->rbuf[0];  // stem output lives in level-0 buffer a
@@ -804,7 +826,7 @@ int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, c
     cw.K = ksize * ksize * Cin;
     ConvLaunch L;
     if (build_conv(ctx, L, static_cast<const __half*>(in), N, H, W, Cin, 0, Cin, cw, ksize, stride, EPI_STORE)) return -5;
-    set_store(L, static_cast<__half*>(out), Cout, 0, relu, static_cast<const __half*>(residual), Cout);
+    if (set_store(ctx, L, static_cast<__half*>(out), Cout, 0, relu, static_cast<const __half*>(residual), Cout)) return -6;
     return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
 }
 
@@ -819,7 +841,7 @@ int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin,
     cw.K = Cin;
     ConvLaunch L;
     if (build_conv(ctx, L, static_cast<const __half*>(in), N, H, W, Cin, 0, Cin, cw, 1, 1, EPI_CONVT)) return -5;
-    set_store(L, static_cast<__half*>(out), out_c_stride, out_c_off, 0, nullptr, 0);
+    if (set_store(ctx, L, static_cast<__half*>(out), out_c_stride, out_c_off, 0, nullptr, 0)) return -6;
     L.p.convt_cout = Cout;
     return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
 }

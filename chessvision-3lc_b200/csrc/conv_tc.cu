@@ -30,101 +30,126 @@ struct ConvCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
     static constexpr int kTmemCols = 2 * BLOCK_N;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiConstBytes;
+    static constexpr int kOutBytes = 2 * 128 * 128;   // two staging buffers for the TMA tile store
+    static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiConstBytes;
 };
 
-// Epilogue of one 32-column chunk held in registers: thread <-> output pixel (n,h,w).  s_bias / s_outw live in shared memory.
-template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int c0, size_t pix, int n, int h, int w,
-                                               bool valid, int n_tile, const float* s_bias, const float* s_outw, float& dot) {
-    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c0);
-    if constexpr (EPI == EPI_OUTC) {
-        const float4* w4 = reinterpret_cast<const float4*>(s_outw + c0);
+constexpr int kOutBufBytes = 128 * 128;   // one staged store group: 128 pixels x 64 channels fp16
+
+// 32 accumulator columns of one pixel -> bias (+ residual) (+ ReLU) -> 16 packed fp16 pairs.
+__device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float* s_bias, const __half* res, bool relu, uint32_t (&o)[16]) {
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias);
+    float f[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = b4[i];
-            const float4 wv = w4[i];
-            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
-            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
-            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
-            dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
-        }
-    } else {
-        const int col0 = n_tile * BLOCK_N + c0;
-        float f[32];
+    for (int i = 0; i < 8; ++i) {
+        const float4 b = b4[i];
+        f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
+        f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
+        f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
+        f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
+    }
+    if (res != nullptr) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(res);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = b4[i];
-            f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + b.x;
-            f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b.y;
-            f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
-            f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
-        }
-        __half* dst;
-        if constexpr (EPI == EPI_CONVT) {
-            const int q = col0 / p.convt_cout;
-            const int co = col0 - q * p.convt_cout;
-            const size_t opix = (static_cast<size_t>(n) * (2 * p.H) + 2 * h + (q >> 1)) * (2 * p.W) + 2 * w + (q & 1);
-            dst = p.out + opix * p.out_c_stride + p.out_c_off + co;
-        } else {
-            dst = p.out + pix * p.out_c_stride + p.out_c_off + col0;
-            if (p.res != nullptr && valid) {
-                const uint4* r4 = reinterpret_cast<const uint4*>(p.res + pix * p.res_c_stride + col0);
+        for (int i = 0; i < 4; ++i) {
+            const uint4 r = __ldg(r4 + i);
+            const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint4 r = __ldg(r4 + i);
-                    const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 rf = __half22float2(rh2[j]);
-                        f[8 * i + 2 * j] += rf.x;
-                        f[8 * i + 2 * j + 1] += rf.y;
-                    }
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float2 rf = __half22float2(rh2[j]);
+                f[8 * i + 2 * j] += rf.x;
+                f[8 * i + 2 * j + 1] += rf.y;
             }
         }
-        if (p.relu) {
+    }
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (valid) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint4 o;
-                __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[8 * i + 2 * j], f[8 * i + 2 * j + 1]);
-                d4[i] = o;
-            }
-        }
+    for (int i = 0; i < 16; ++i) {
+        const float a = relu ? fmaxf(f[2 * i], 0.f) : f[2 * i], b = relu ? fmaxf(f[2 * i + 1], 0.f) : f[2 * i + 1];
+        const __half2 h = __floats2half2_rn(a, b);
+        o[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
 }
 
-// Epilogue of one 128-row accumulator tile: the TMEM load of chunk c+1 is in flight while chunk c is processed.
+// Epilogue of one 128-row accumulator tile (thread <-> TMEM lane <-> output pixel `row` of the tile).
+//   EPI_STORE / EPI_CONVT: 64 columns at a time are converted, staged in shared memory in the 128-byte-swizzled box
+//   layout and written by one TMA tile store (full 128-byte lines; the pixel-shuffle of the transposed convolution is a
+//   strided output view per (dy,dx)).  EPI_OUTC: fused 1x1 head, one logit + mask byte per pixel.
+//   The TMEM load of chunk c+1 is in flight while chunk c is processed.
 template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int n, int h, int w, bool valid, int n_tile,
-                                              const float* s_bias, const float* s_outw) {
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int row, int n0, int h0, int w0, int n, int h, int w,
+                                              bool valid, int n_tile, const float* s_bias, const float* s_outw, uint8_t* s_out,
+                                              uint32_t s_out_addr, int& store_count, int etid) {
     constexpr int NC = BLOCK_N / 32;
     const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
-    float dot = 0.f;
     uint32_t va[32], vb[32];
     tmem_ld_32x32(taddr, va);
-#pragma unroll
-    for (int c = 0; c < NC; c += 2) {
-        tmem_ld_wait(va);
-        tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-        epilogue_chunk<BLOCK_N, EPI>(p, va, c * 32, pix, n, h, w, valid, n_tile, s_bias, s_outw, dot);
-        tmem_ld_wait(vb);
-        if (c + 2 < NC) tmem_ld_32x32(taddr + (c + 2) * 32, va);
-        epilogue_chunk<BLOCK_N, EPI>(p, vb, (c + 1) * 32, pix, n, h, w, valid, n_tile, s_bias, s_outw, dot);
-    }
     if constexpr (EPI == EPI_OUTC) {
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < NC; c += 2) {
+            tmem_ld_wait(va);
+            tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t(&v)[32] = half ? vb : va;
+                if (half) {
+                    tmem_ld_wait(vb);
+                    if (c + 2 < NC) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                }
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + (c + half) * 32);
+                const float4* w4 = reinterpret_cast<const float4*>(s_outw + (c + half) * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b = b4[i];
+                    const float4 wv = w4[i];
+                    dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 0]) + b.x, 0.f), wv.x, dot);
+                    dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 1]) + b.y, 0.f), wv.y, dot);
+                    dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 2]) + b.z, 0.f), wv.z, dot);
+                    dot = fmaf(fmaxf(__uint_as_float(v[4 * i + 3]) + b.w, 0.f), wv.w, dot);
+                }
+            }
+        }
         if (valid) {
             const float logit = dot + p.outc_b;
             p.logits[pix] = logit;
             const float prob = 1.0f / (1.0f + expf(-logit));
             p.mask[pix] = prob > p.thr ? 255 : 0;
+        }
+    } else {
+        const bool relu = p.relu != 0;
+#pragma unroll
+        for (int c = 0; c < NC; c += 2) {
+            const int col0 = n_tile * BLOCK_N + c * 32;   // first of the 64 columns of this store group
+            const __half* res = (EPI == EPI_STORE && p.res != nullptr && valid) ? p.res + pix * p.res_c_stride + col0 : nullptr;
+            uint32_t o[32];
+            tmem_ld_wait(va);
+            tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+            pack_chunk(va, s_bias + c * 32, res, relu, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+            tmem_ld_wait(vb);
+            if (c + 2 < NC) tmem_ld_32x32(taddr + (c + 2) * 32, va);
+            pack_chunk(vb, s_bias + c * 32 + 32, res ? res + 32 : nullptr, relu, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+            // staging buffer: free once the store issued `out_bufs` groups ago has read it
+            const int buf = p.out_bufs == 2 ? (store_count & 1) : 0;
+            if (etid == 0) {
+                if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+            }
+            named_bar_sync(1, 128);
+            uint8_t* dst = s_out + buf * kOutBufBytes + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (etid == 0) {
+                if constexpr (EPI == EPI_CONVT) {
+                    const int q = col0 / p.convt_cout;
+                    tma_store_4d(&p.o_map[q], s_out_addr + buf * kOutBufBytes, p.out_c_off + col0 - q * p.convt_cout, w0, h0, n0);
+                } else {
+                    tma_store_4d(&p.o_map[0], s_out_addr + buf * kOutBufBytes, p.out_c_off + col0, w0, h0, n0);
+                }
+                bulk_commit();
+            }
+            ++store_count;
         }
     }
 }
@@ -149,7 +174,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
     uint8_t* tiles_ptr = smem_raw + (tiles_addr - raw_addr);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles_ptr + S * Cfg::kStageBytes);
+    uint8_t* s_out = tiles_ptr + S * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + Cfg::kOutBytes);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * S;
     const uint32_t bar_tfull = bar_full + 16 * S;
@@ -246,7 +272,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         const int rn = row / (p.th * p.tw);
         const int rh = (row / p.tw) % p.th;
         const int rw = row % p.tw;
-        float* s_bias = reinterpret_cast<float*>(tiles_ptr + S * Cfg::kStageBytes + 256);
+        float* s_bias = reinterpret_cast<float*>(s_out + Cfg::kOutBytes + 256);
+        int store_count = 0;
         float* s_outw = s_bias + 256;
         int iter = 0, cur_nt = -1;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
@@ -265,10 +292,12 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, valid, n_tile, s_bias, s_outw);
+            epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n - rn, h - rh, w - rw, n, h, w, valid, n_tile, s_bias, s_outw, s_out,
+                                        tiles_addr + S * Cfg::kStageBytes, store_count, threadIdx.x - 128);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (threadIdx.x == 128) bulk_wait_all();   // the staged tiles must have left shared memory before the CTA exits
     }
 
     tc_fence_before();
@@ -303,7 +332,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     uint8_t* base_ptr = smem_raw + (base_addr - raw_addr);
     const uint32_t w_bytes = W_STAT ? 9u * p.c_chunks * kBBytes : 0u;
     const uint32_t stages_addr = base_addr + w_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + w_bytes + S * kStageBytes);
+    uint8_t* s_out = base_ptr + w_bytes + S * kStageBytes;
+    const uint32_t out_bytes = EPI == EPI_OUTC ? 0u : static_cast<uint32_t>(kOutBufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + out_bytes);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * S;
     const uint32_t bar_tfull = bar_full + 16 * S;
@@ -414,7 +445,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int rh = row >> 3, rw = row & 7;
-        float* s_bias = reinterpret_cast<float*>(base_ptr + w_bytes + S * kStageBytes + 256);
+        float* s_bias = reinterpret_cast<float*>(s_out + out_bytes + 256);
+        int store_count = 0;
         float* s_outw = s_bias + 256;
         int iter = 0, cur_nt = -1;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
@@ -432,10 +464,12 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            epilogue_tile<BLOCK_N, EPI>(p, taddr, n, h, w, n < p.N, n_tile, s_bias, s_outw);
+            epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n, h - rh, w - rw, n, h, w, n < p.N, n_tile, s_bias, s_outw, s_out,
+                                        stages_addr + S * kStageBytes, store_count, threadIdx.x - 128);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (threadIdx.x == 128) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -535,7 +569,8 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
     const int b_bytes = L.block_n * 128;
     const int w_bytes = 9 * (Cin / 64) * b_bytes;
-    const int budget = kVrMaxSmem - 1024 - 256 - kEpiConstBytes;
+    const int out_bytes = L.epilogue == EPI_OUTC ? 0 : kOutBufBytes;
+    const int budget = kVrMaxSmem - 1024 - 256 - kEpiConstBytes - out_bytes;
     const bool ws = p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
     if (L.epilogue == EPI_OUTC && !ws) return false;
     const int stage = 18 * 1024 + (ws ? 0 : 3 * b_bytes);
@@ -544,7 +579,8 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     if (stages < 2) return false;
     p.vr_stages = stages;
     p.w_stationary = ws ? 1 : 0;
-    p.smem_bytes = (ws ? w_bytes : 0) + stages * stage + 1024 + 256 + kEpiConstBytes;
+    p.smem_bytes = (ws ? w_bytes : 0) + stages * stage + out_bytes + 1024 + 256 + kEpiConstBytes;
+    p.out_bufs = L.epilogue == EPI_OUTC ? 0 : 1;
     p.tn = 1; p.th = 16; p.tw = 8;
     p.tiles_w = Wo / 8;
     p.tiles_h = Ho / 16;

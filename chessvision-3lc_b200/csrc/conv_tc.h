@@ -17,6 +17,8 @@ enum ConvEpilogue : int {
 struct alignas(64) ConvParams {
     CUtensorMap a_map[4];  // activation views, 4-D {C, W, H, N}, box {64, tw, th, tn}, 128-byte swizzle
     CUtensorMap b_map;     // packed weights, 2-D {K_total, Cout_total}, box {64, BLOCK_N}, 128-byte swizzle
+    CUtensorMap o_map[4];  // output views for the TMA tile store, box {64, tw, th, tn}; convT: one strided view per (dy,dx)
+    int out_bufs;          // 16 KB staging buffers for the store (0: EPI_OUTC, 1 or 2 otherwise)
     // K loop: taps x (Cin/64) chunks.  Tap t reads view tap_map[t] at spatial offset (tap_dy[t], tap_dx[t]).
     int taps;
     int c_chunks;
@@ -54,6 +56,7 @@ struct ConvLaunch {
     int block_n;   // 64, 128 or 256
     int epilogue;  // ConvEpilogue
     int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel
+    int n_max;     // images the activation / output views were built for
 };
 
 // Resolve cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).  Returns 0 on success.
