@@ -38,7 +38,10 @@ struct ConvWeights {
 
 struct cvb_ctx {
     int device = 0;
-    int max_batch = 0;
+    int max_batch = 0;        // boards per network chunk (activation workspaces)
+    int group_chunks = 8;     // chunks per geometry group: mask->quad / warp run once over up to group_chunks*max_batch boards
+    int group = 0;            // = group_chunks * max_batch
+    bool quad_full_only = false;   // CVB_QUAD_FULL=1: skip the compact mask->quad kernel (A/B measurements, tests)
     int sm_count = 148;
     bool use_vr = true;   // CVB_NO_VR=1 forces the generic conv kernel everywhere (A/B measurements)
     std::string err;
@@ -78,7 +81,8 @@ struct cvb_ctx {
 
     // ---- host streaming
     cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_in[2];   // one per chunk of a group: the network of chunk c starts when its images have landed
+    cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     uint8_t* slot_img[2] = {nullptr, nullptr};
     // per-slot device outputs for the host path
     cvb_outputs slot_out[2];
@@ -422,18 +426,31 @@ int classify(cvb_ctx* ctx, const uint8_t* board, int n, int flip, float* probs, 
     return 0;
 }
 
-int pipeline_chunk(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s) {
+// One geometry group (n <= ctx->group boards): both networks run chunk by chunk (max_batch boards, their activation
+// workspaces), the latency-bound mask->quad kernel and the warp run ONCE over the whole group so that many boards are
+// resident per SM and the slow boards of a launch overlap with the rest.  `o` may hold NULL members (workspaces are
+// used); `off` = index of the group's first board inside the caller's output arrays.  in_ready[c] (optional): event the
+// network of chunk c has to wait for (host path: the chunk's host->device copy).
+int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s,
+                   const cudaEvent_t* in_ready) {
+    const int B = ctx->max_batch;
     float* logits = o.logits ? o.logits + off * 65536 : nullptr;
     uint8_t* mask = o.mask ? o.mask + off * 65536 : ctx->ws_mask;
     int32_t* quad = o.quad ? o.quad + off * 8 : ctx->ws_quad;
     uint8_t* found = o.found ? o.found + off : ctx->ws_found;
     int32_t* status = o.status ? o.status + off : ctx->ws_status;
     uint8_t* board = o.board ? o.board + off * 262144 : ctx->ws_board;
-    if (unet_forward(ctx, img, n, thr, logits, mask, s)) return -2;
+    for (int c = 0, c0 = 0; c0 < n; ++c, c0 += B) {
+        const int nb = n - c0 < B ? n - c0 : B;
+        if (in_ready) CK(cudaStreamWaitEvent(s, in_ready[c], 0));
+        if (unet_forward(ctx, img + static_cast<size_t>(c0) * 786432, nb, thr, logits ? logits + static_cast<size_t>(c0) * 65536 : nullptr,
+                         mask + static_cast<size_t>(c0) * 65536, s))
+            return -2;
+    }
     {
         StageTimer t(ctx, 2, s);
-        CK(launch_mask_to_quad(mask, quad, found, status, ctx->ws_ncont, ctx->ws_owner, n, s));
-        ctx->launches++;
+        CK(launch_mask_to_quad(mask, quad, found, status, ctx->ws_ncont, ctx->ws_owner, n, ctx->quad_full_only, s));
+        ctx->launches += ctx->quad_full_only ? 1 : 2;
     }
     {
         StageTimer t(ctx, 3, s);
@@ -441,8 +458,15 @@ int pipeline_chunk(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip,
         CK(launch_warp_board(img, ctx->ws_minv, found, board, n, 512, 512, s));
         ctx->launches += 2;
     }
-    return classify(ctx, board, n, flip, o.probs ? o.probs + off * 832 : nullptr, o.labels ? o.labels + off * 64 : nullptr,
-                    o.labels_valid ? o.labels_valid + off * 64 : nullptr, o.fen ? o.fen + off * 144 : nullptr, s);
+    for (int c0 = 0; c0 < n; c0 += B) {
+        const int nb = n - c0 < B ? n - c0 : B;
+        const size_t q = off + c0;
+        if (classify(ctx, board + static_cast<size_t>(c0) * 262144, nb, flip, o.probs ? o.probs + q * 832 : nullptr,
+                     o.labels ? o.labels + q * 64 : nullptr, o.labels_valid ? o.labels_valid + q * 64 : nullptr,
+                     o.fen ? o.fen + q * 144 : nullptr, s))
+            return -2;
+    }
+    return 0;
 }
 
 int set_device(cvb_ctx* ctx) {
@@ -486,12 +510,15 @@ cvb_ctx* cvb_create(int device, int max_batch) {
     ctx->use_vr = getenv("CVB_NO_VR") == nullptr;
     if (tmap_init()) { ctx->err = "cuTensorMapEncodeTiled not available from the driver"; return bail(); }
     ctx->stem_fp32 = getenv("CVB_STEM_FP32") != nullptr;
+    ctx->quad_full_only = getenv("CVB_QUAD_FULL") != nullptr;
+    if (const char* g = getenv("CVB_GROUP_CHUNKS")) ctx->group_chunks = atoi(g) > 0 ? atoi(g) : 1;
+    ctx->group = ctx->group_chunks * max_batch;
     if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_stems_tc() != cudaSuccess ||
         configure_quad() != cudaSuccess || configure_warp() != cudaSuccess) {
         ctx->err = std::string("kernel attribute setup failed: ") + cudaGetErrorString(cudaGetLastError());
         return bail();
     }
-    const size_t B = max_batch;
+    const size_t B = max_batch, G = ctx->group;
     int rc = 0;
     // UNet activations (fp16 NHWC)
     rc |= dalloc(ctx, &ctx->cat0, B * 256 * 256 * 128);
@@ -512,15 +539,15 @@ cvb_ctx* cvb_create(int device, int max_batch) {
     rc |= dalloc(ctx, &ctx->u2, B * 64 * 64 * 256);
     rc |= dalloc(ctx, &ctx->u3, B * 128 * 128 * 128);
     rc |= dalloc(ctx, &ctx->ws_logits, B * 65536);
-    rc |= dalloc(ctx, &ctx->ws_mask, B * 65536);
-    // geometry
-    rc |= dalloc(ctx, &ctx->ws_quad, B * 8);
-    rc |= dalloc(ctx, &ctx->ws_status, B);
-    rc |= dalloc(ctx, &ctx->ws_ncont, B);
-    rc |= dalloc(ctx, &ctx->ws_owner, B * (kQuadMaxBorders + 8));
-    rc |= dalloc(ctx, &ctx->ws_found, B);
-    rc |= dalloc(ctx, &ctx->ws_minv, B * 9);
-    rc |= dalloc(ctx, &ctx->ws_board, B * 262144);
+    rc |= dalloc(ctx, &ctx->ws_mask, G * 65536);
+    // geometry (per group)
+    rc |= dalloc(ctx, &ctx->ws_quad, G * 8);
+    rc |= dalloc(ctx, &ctx->ws_status, G);
+    rc |= dalloc(ctx, &ctx->ws_ncont, G);
+    rc |= dalloc(ctx, &ctx->ws_owner, G * (kQuadMaxBorders + 8));
+    rc |= dalloc(ctx, &ctx->ws_found, G);
+    rc |= dalloc(ctx, &ctx->ws_minv, G * 9);
+    rc |= dalloc(ctx, &ctx->ws_board, G * 262144);
     // classifier activations: 3 buffers per level; per square 16x16x64, 8x8x128, 4x4x256, 2x2x512 = 16384..2048 halfs
     for (int lvl = 0; lvl < 4 && !rc; ++lvl)
         for (int k = 0; k < 3 && !rc; ++k) rc |= dalloc(ctx, &ctx->rbuf[lvl * 3 + k], B * 64 * (16384 >> lvl));
@@ -534,16 +561,17 @@ cvb_ctx* cvb_create(int device, int max_batch) {
               cudaStreamCreateWithFlags(&ctx->s_comp, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) {
-        ok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+        ctx->ev_in[i].assign(ctx->group_chunks, nullptr);
+        for (auto& e : ctx->ev_in[i]) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming) == cudaSuccess;
         memset(&ctx->slot_out[i], 0, sizeof(cvb_outputs));
-        if (ok) ok = dalloc(ctx, &ctx->slot_img[i], B * 512 * 512 * 3) == 0;
-        if (ok) ok = dalloc(ctx, &ctx->slot_out[i].quad, B * 8) == 0 && dalloc(ctx, &ctx->slot_out[i].found, B) == 0 &&
-                     dalloc(ctx, &ctx->slot_out[i].status, B) == 0 && dalloc(ctx, &ctx->slot_out[i].probs, B * 832) == 0 &&
-                     dalloc(ctx, &ctx->slot_out[i].labels, B * 64) == 0 && dalloc(ctx, &ctx->slot_out[i].labels_valid, B * 64) == 0 &&
-                     dalloc(ctx, &ctx->slot_out[i].fen, B * 144) == 0 && dalloc(ctx, &ctx->slot_out[i].logits, B * 65536) == 0 &&
-                     dalloc(ctx, &ctx->slot_out[i].mask, B * 65536) == 0 && dalloc(ctx, &ctx->slot_out[i].board, B * 262144) == 0;
+        if (ok) ok = dalloc(ctx, &ctx->slot_img[i], G * 512 * 512 * 3) == 0;
+        if (ok) ok = dalloc(ctx, &ctx->slot_out[i].quad, G * 8) == 0 && dalloc(ctx, &ctx->slot_out[i].found, G) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].status, G) == 0 && dalloc(ctx, &ctx->slot_out[i].probs, G * 832) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].labels, G * 64) == 0 && dalloc(ctx, &ctx->slot_out[i].labels_valid, G * 64) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].fen, G * 144) == 0 && dalloc(ctx, &ctx->slot_out[i].logits, G * 65536) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].mask, G * 65536) == 0 && dalloc(ctx, &ctx->slot_out[i].board, G * 262144) == 0;
     }
     if (!ok) {
         if (ctx->err.empty()) ctx->err = "stream/event/slot setup failed";
@@ -559,7 +587,8 @@ void cvb_destroy(cvb_ctx* ctx) {
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
-        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        for (cudaEvent_t e : ctx->ev_in[i])
+            if (e) cudaEventDestroy(e);
         if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]);
         if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
     }
@@ -725,11 +754,12 @@ int cvb_mask_from_logits(cvb_ctx* ctx, const float* logits, int N, float thr, ui
 int cvb_mask_to_quad(cvb_ctx* ctx, const uint8_t* mask, int N, int32_t* quad, uint8_t* found, int32_t* status, void* stream) {
     if (!ctx || !mask || !quad || !found || N < 0) return -1;
     if (set_device(ctx)) return -2;
-    for (int off = 0; off < N; off += ctx->max_batch) {
-        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+    for (int off = 0; off < N; off += ctx->group) {
+        const int n = N - off < ctx->group ? N - off : ctx->group;
         CK(launch_mask_to_quad(mask + static_cast<size_t>(off) * 65536, quad + off * 8, found + off,
-                               status ? status + off : ctx->ws_status, ctx->ws_ncont, ctx->ws_owner, n, static_cast<cudaStream_t>(stream)));
-        ctx->launches++;
+                               status ? status + off : ctx->ws_status, ctx->ws_ncont, ctx->ws_owner, n, ctx->quad_full_only,
+                               static_cast<cudaStream_t>(stream)));
+        ctx->launches += ctx->quad_full_only ? 1 : 2;
     }
     return 0;
 }
@@ -739,8 +769,8 @@ int cvb_warp_squares(cvb_ctx* ctx, const uint8_t* img, const int32_t* quad, cons
     if (!ctx || !img || !quad || !found || !board || N < 0 || H <= 0 || W <= 0) return -1;
     if (set_device(ctx)) return -2;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    for (int off = 0; off < N; off += ctx->max_batch) {
-        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
+    for (int off = 0; off < N; off += ctx->group) {
+        const int n = N - off < ctx->group ? N - off : ctx->group;
         CK(launch_homography(quad + off * 8, found + off, ctx->ws_minv, n, static_cast<float>(H) / 256.0f, 512, 512, s));
         CK(launch_warp_board(img + static_cast<size_t>(off) * H * W * 3, ctx->ws_minv, found + off, board + static_cast<size_t>(off) * 262144, n, H, W, s));
         ctx->launches += 2;
@@ -765,9 +795,10 @@ int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, float* pro
 int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float thr, int flip, const cvb_outputs* out, void* stream) {
     if (!ctx || !img || !out || N < 0) return -1;
     if (set_device(ctx)) return -2;
-    for (int off = 0; off < N; off += ctx->max_batch) {
-        const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
-        if (pipeline_chunk(ctx, img + static_cast<size_t>(off) * 786432, n, thr, flip, *out, off, static_cast<cudaStream_t>(stream))) return -2;
+    for (int off = 0; off < N; off += ctx->group) {
+        const int n = N - off < ctx->group ? N - off : ctx->group;
+        if (pipeline_group(ctx, img + static_cast<size_t>(off) * 786432, n, thr, flip, *out, off, static_cast<cudaStream_t>(stream), nullptr))
+            return -2;
     }
     return 0;
 }
@@ -775,24 +806,27 @@ int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float thr, int fli
 int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float thr, int flip, const cvb_outputs* oh) {
     if (!ctx || !img_host || !oh || N < 0) return -1;
     if (set_device(ctx)) return -2;
-    const int B = ctx->max_batch;
-    int chunk = 0;
-    for (int off = 0; off < N; off += B, ++chunk) {
-        const int n = N - off < B ? N - off : B;
-        const int sl = chunk & 1;
+    const int B = ctx->max_batch, G = ctx->group;
+    int g = 0;
+    for (int off = 0; off < N; off += G, ++g) {
+        const int n = N - off < G ? N - off : G;
+        const int sl = g & 1;
         const size_t o = off;
         const cvb_outputs& d = ctx->slot_out[sl];
-        // the slot is reusable once the copy-out of the chunk that used it two iterations ago has finished
-        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[sl], 0));
-        CK(cudaMemcpyAsync(ctx->slot_img[sl], img_host + o * 786432, static_cast<size_t>(n) * 786432, cudaMemcpyHostToDevice, ctx->s_in));
-        CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_in));
-        CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_in[sl], 0));
-        if (chunk >= 2) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_free[sl], 0));
+        // the slot is reusable once the copy-out of the group that used it two iterations ago has finished
+        if (g >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_free[sl], 0));
+        for (int c = 0, c0 = 0; c0 < n; ++c, c0 += B) {
+            const int nb = n - c0 < B ? n - c0 : B;
+            CK(cudaMemcpyAsync(ctx->slot_img[sl] + static_cast<size_t>(c0) * 786432, img_host + (o + c0) * 786432,
+                               static_cast<size_t>(nb) * 786432, cudaMemcpyHostToDevice, ctx->s_in));
+            CK(cudaEventRecord(ctx->ev_in[sl][c], ctx->s_in));
+        }
+        if (g >= 2) CK(cudaStreamWaitEvent(ctx->s_comp, ctx->ev_free[sl], 0));
         cvb_outputs dev = d;
         if (!oh->logits) dev.logits = nullptr;
         if (!oh->mask) dev.mask = nullptr;
         if (!oh->board) dev.board = nullptr;
-        if (pipeline_chunk(ctx, ctx->slot_img[sl], n, thr, flip, dev, 0, ctx->s_comp)) return -2;
+        if (pipeline_group(ctx, ctx->slot_img[sl], n, thr, flip, dev, 0, ctx->s_comp, ctx->ev_in[sl].data())) return -2;
         CK(cudaEventRecord(ctx->ev_comp[sl], ctx->s_comp));
         CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[sl], 0));
         cudaStream_t so = ctx->s_out;

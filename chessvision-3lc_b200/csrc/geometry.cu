@@ -89,8 +89,14 @@ __device__ void trace_border(int16_t* lab, int start, int nbd, bool hole, int* P
 }
 
 __device__ __forceinline__ int wrap(int i, int n) {
-    i %= n;
-    return i < 0 ? i + n : i;
+    if (i < 0) {
+        i += n;
+        if (i < 0) { i %= n; if (i < 0) i += n; }
+    } else if (i >= n) {
+        i -= n;
+        if (i >= n) i %= n;
+    }
+    return i;
 }
 
 // TC89_KCOS pass 1 for point i (region of support + k-cosine); returns s, writes k.
@@ -263,7 +269,8 @@ __device__ int approx_poly(const int* R, int m, double epsilon, int* dst, int* s
 
 __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restrict__ mask, int32_t* __restrict__ quad,
                                                         uint8_t* __restrict__ found, int32_t* __restrict__ status,
-                                                        int32_t* __restrict__ n_contours, int32_t* __restrict__ owner_scratch) {
+                                                        int32_t* __restrict__ n_contours, int32_t* __restrict__ owner_scratch,
+                                                        int only_flagged) {
     extern __shared__ __align__(16) uint8_t smem[];
     int16_t* lab = reinterpret_cast<int16_t*>(smem);
     int* P = reinterpret_cast<int*>(smem + kLabBytes);
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
     Contour* cshare = reinterpret_cast<Contour*>(CODE + kQuadMaxPoints);
 
     const int b = blockIdx.x, lane = threadIdx.x;
+    if (only_flagged && status[b] != QUAD_NEED_FULL) return;   // resolved by k_mask_to_quad_fast
     const uint8_t* m = mask + static_cast<size_t>(b) * 65536;
     int* owner = owner_scratch + static_cast<size_t>(b) * (kQuadMaxBorders + 8);
 
@@ -481,16 +489,341 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Compact variant of the same algorithm: ~46 KB of shared memory per board instead of 223 KB, so four boards are resident
+// per SM and the (latency-bound, single-warp) work of different boards overlaps.  State per pixel is three bit planes
+// with a one-pixel zero frame (rows of 288 bits): F foreground (never changes: border following only ever relabels
+// non-zero pixels), V visited, N "right-bound" (negative label).  Border identities are not kept, which is all that
+// ownership of HOLE borders needs; a hole large enough to pass the area filter is therefore not decided here: the board
+// is flagged QUAD_NEED_FULL (as is any capacity overflow) and k_mask_to_quad re-runs exactly those boards.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FW = 9;                       // 32-bit words per bit-plane row (258 used bits)
+constexpr int FBITS = FW * 32;              // linear bit index = y * 288 + x
+constexpr int kPlaneWords = 258 * FW;
+constexpr int kFastPoints = 2048;           // border points of one contour
+constexpr int kFastVertices = 512;          // vertices after TC89_KCOS
+constexpr int kFastSmem = 3 * kPlaneWords * 4 + kFastPoints * (2 + 1 + 4 + 2) + 64;
+
+__constant__ int c_boff16[16] = {1, -FBITS + 1, -FBITS, -FBITS - 1, -1, FBITS - 1, FBITS, FBITS + 1,
+                                 1, -FBITS + 1, -FBITS, -FBITS - 1, -1, FBITS - 1, FBITS, FBITS + 1};
+
+__device__ __forceinline__ int bit_get(const uint32_t* pl, int i) { return (pl[i >> 5] >> (i & 31)) & 1; }
+__device__ __forceinline__ void bit_set(uint32_t* pl, int i) { pl[i >> 5] |= 1u << (i & 31); }
+__device__ __forceinline__ int pack16(int i) {
+    const int y = i / FBITS, x = i - y * FBITS;
+    return (x - 1) | ((y - 1) << 8);
+}
+__device__ __forceinline__ int qx(int p) { return p & 255; }
+__device__ __forceinline__ int qy(int p) { return p >> 8; }
+
+// Suzuki-Abe border following on the bit planes (lane 0 only); same control flow as trace_border.
+__device__ void trace_border_bits(const uint32_t* F, uint32_t* V, uint32_t* N, int start, bool hole, uint16_t* P, uint8_t* CODE, Contour& c) {
+    int s_end = hole ? 0 : 4;
+    int s = s_end;
+    int i1;
+    do {
+        s = (s - 1) & 7;
+        i1 = start + c_boff16[s];
+    } while (!bit_get(F, i1) && s != s_end);
+    const int p0 = pack16(start);
+    c.minx = c.maxx = qx(p0);
+    c.miny = c.maxy = qy(p0);
+    if (s == s_end) {  // isolated pixel: labelled -nbd
+        bit_set(V, start);
+        bit_set(N, start);
+        P[0] = static_cast<uint16_t>(p0);
+        c.n = 1;
+        return;
+    }
+    int i3 = start, n = 0;
+    for (;;) {
+        s_end = s;
+        int i4;
+        do {
+            ++s;
+            i4 = i3 + c_boff16[s & 15];
+        } while (!bit_get(F, i4));
+        s &= 7;
+        if (static_cast<unsigned>(s - 1) < static_cast<unsigned>(s_end)) {
+            bit_set(V, i3);
+            bit_set(N, i3);
+        } else {
+            bit_set(V, i3);   // "if (label == 1) label = nbd": a visited pixel keeps its sign
+        }
+        const int p = pack16(i3);
+        if (n < kFastPoints) {
+            P[n] = static_cast<uint16_t>(p);
+            CODE[n] = static_cast<uint8_t>(s);
+        }
+        ++n;
+        c.minx = min(c.minx, qx(p));
+        c.maxx = max(c.maxx, qx(p));
+        c.miny = min(c.miny, qy(p));
+        c.maxy = max(c.maxy, qy(p));
+        if (i4 == start && i3 == i1) break;
+        i3 = i4;
+        s = (s + 4) & 7;
+    }
+    c.n = n;
+}
+
+// TC89_KCOS pass 1 on 16-bit packed points (same arithmetic as kcos_point).
+__device__ int kcos_point16(const uint16_t* P, int n, int i, int& k_out) {
+    const int xi = qx(P[i]), yi = qy(P[i]);
+    int d_num = 0, l = 0, k = 1;
+    for (;; ++k) {
+        const int p1 = P[wrap(i - k, n)], p2 = P[wrap(i + k, n)];
+        const int dx = qx(p2) - qx(p1), dy = qy(p2) - qy(p1);
+        const int lk = dx * dx + dy * dy;
+        const int dk = (xi - qx(p1)) * dy - (yi - qy(p1)) * dx;
+        const float t = static_cast<float>(static_cast<double>(d_num) * static_cast<double>(lk) -
+                                           static_cast<double>(dk) * static_cast<double>(l));
+        if (k > 1 && (l >= lk || (d_num > 0 && t <= 0.f) || (d_num < 0 && t >= 0.f))) break;
+        d_num = dk;
+        l = lk;
+    }
+    --k;
+    k_out = k;
+    int sv = 0;
+    for (int j = k; j > 0; --j) {
+        const int pa = P[wrap(i - j, n)], pb = P[wrap(i + j, n)];
+        const int ax = qx(pa) - xi, ay = qy(pa) - yi, bx = qx(pb) - xi, by = qy(pb) - yi;
+        if ((ax | ay) == 0 || (bx | by) == 0) break;
+        const double num = static_cast<double>(ax * bx + ay * by);
+        const double den = sqrt(static_cast<double>(ax * ax + ay * ay) * static_cast<double>(bx * bx + by * by));
+        const float cs = static_cast<float>(num / den);
+        const int sk = __float_as_int(static_cast<float>(static_cast<double>(cs) + 1.1));
+        if (j < k && sk <= sv) break;
+        sv = sk;
+    }
+    return sv;
+}
+
+__global__ void __launch_bounds__(32, 4) k_mask_to_quad_fast(const uint8_t* __restrict__ mask, int32_t* __restrict__ quad,
+                                                             uint8_t* __restrict__ found, int32_t* __restrict__ status,
+                                                             int32_t* __restrict__ n_contours) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t* F = reinterpret_cast<uint32_t*>(smem);
+    uint32_t* V = F + kPlaneWords;
+    uint32_t* N = V + kPlaneWords;
+    int* S = reinterpret_cast<int*>(N + kPlaneWords);
+    uint16_t* P = reinterpret_cast<uint16_t*>(S + kFastPoints);
+    uint16_t* KS = P + kFastPoints;
+    uint8_t* CODE = reinterpret_cast<uint8_t*>(KS + kFastPoints);
+    Contour* cshare = reinterpret_cast<Contour*>(CODE + kFastPoints);
+
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const uint8_t* m = mask + static_cast<size_t>(b) * 65536;
+
+    for (int i = lane; i < 2 * kPlaneWords; i += 32) V[i] = 0u;   // V and N are contiguous
+    for (int i = lane; i < FW; i += 32) {
+        F[i] = 0u;
+        F[257 * FW + i] = 0u;
+    }
+    // foreground plane: 16 mask bytes per lane -> 16 bits, two lanes make one word-aligned half... assembled by shuffles
+    for (int it = 0; it < 128; ++it) {       // 512 pixels (two rows) per iteration
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(m) + it * 32 + lane);
+        uint32_t bits = 0;
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bits |= (w[k] & 0xffu ? 1u : 0u) << (4 * k);
+            bits |= (w[k] & 0xff00u ? 1u : 0u) << (4 * k + 1);
+            bits |= (w[k] & 0xff0000u ? 1u : 0u) << (4 * k + 2);
+            bits |= (w[k] & 0xff000000u ? 1u : 0u) << (4 * k + 3);
+        }
+        // lanes 0..15 hold row y = 2*it, lanes 16..31 row y + 1; lane j of a half holds pixels 16j..16j+15
+        const uint32_t hi = __shfl_down_sync(FULL, bits, 1);
+        const uint32_t word = bits | (hi << 16);                 // valid in even lanes: pixels 32k..32k+31, k = (lane&15)/2
+        // shift the row by one bit (frame column 0): plane word k = (pix word k << 1) | (pix word k-1 >> 31)
+        const uint32_t prev = __shfl_up_sync(FULL, word, 2);
+        if ((lane & 1) == 0) {
+            const int k = (lane & 15) >> 1, y = 2 * it + (lane >> 4) + 1;
+            F[y * FW + k] = (word << 1) | (k ? prev >> 31 : 0u);
+            if (k == 7) F[y * FW + 8] = word >> 31;              // pixel 255 -> bit 256 of the row, bit 257 stays 0
+        }
+    }
+    __syncwarp();
+
+    int ncont = 0;
+    bool need_full = false;
+    bool first_is4 = false;
+    int first_q[4] = {0, 0, 0, 0};
+    bool best_valid = false;
+    int best_d = -1;
+    int best_q[4] = {0, 0, 0, 0};
+
+    for (int y = 1; y <= 256 && !need_full; ++y) {
+        uint32_t carry = 0;
+        for (int wi = 0; wi < FW && !need_full; ++wi) {
+            const uint32_t Fw = F[y * FW + wi];
+            uint32_t T = Fw ^ ((Fw << 1) | carry);
+            carry = Fw >> 31;
+            while (T && !need_full) {
+                const int bpos = __ffs(T) - 1;
+                T &= T - 1;
+                const int idx = y * FBITS + wi * 32 + bpos;
+                const bool fg = (Fw >> bpos) & 1u;
+                // outer border: prev == 0 && p == 1 (unvisited).  hole border: p == 0 && prev >= 1 (not a right bound)
+                const bool outer = fg && !bit_get(V, idx);
+                const bool hole = !fg && !bit_get(N, idx - 1);
+                if (!(outer || hole)) continue;
+                const int d = ncont++;
+                if (lane == 0) {
+                    Contour c;
+                    trace_border_bits(F, V, N, hole ? idx - 1 : idx, hole, P, CODE, c);
+                    *cshare = c;
+                }
+                __syncwarp();
+                const Contour c = *cshare;
+                __syncwarp();
+                const bool big = (c.maxx - c.minx + 1) * (c.maxy - c.miny + 1) >= 22937;
+                if (!(d == 0 || big)) continue;
+                if (hole || c.n > kFastPoints) {   // (a first contour is never a hole)
+                    need_full = true;
+                    break;
+                }
+                if (c.n <= 1) continue;
+                const int n = c.n;
+                for (int i = lane; i < n; i += 32) {
+                    const int prev_code = CODE[i == 0 ? n - 1 : i - 1];
+                    S[i] = c_kcos_t[static_cast<int>(CODE[i]) - prev_code + 7];
+                    KS[i] = 0;
+                }
+                __syncwarp();
+                for (int i = lane; i < n; i += 32) {
+                    if (S[i] != 0) {
+                        int k;
+                        const int sv = kcos_point16(P, n, i, k);
+                        S[i] = sv;
+                        KS[i] = static_cast<uint16_t>(k);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    for (int i = 0; i < n; ++i) {
+                        const int k2 = KS[i] >> 1;
+                        if (KS[i] == 0) continue;
+                        const int si = S[i];
+                        bool keep = true;
+                        for (int j = 1; j <= k2; ++j) {
+                            if (S[wrap(i - j, n)] > si || S[wrap(i + j, n)] > si) {
+                                keep = false;
+                                break;
+                            }
+                        }
+                        if (!keep) {
+                            S[i] = 0;
+                            KS[i] = 0;
+                        }
+                    }
+                    int mv = 0;
+                    for (int i = 0; i < n; ++i) {
+                        if (KS[i] == 0) continue;
+                        if (KS[i] == 1 && (S[i] <= S[wrap(i - 1, n)] || S[i] <= S[wrap(i + 1, n)])) {
+                            S[i] = 0;
+                            continue;
+                        }
+                        P[mv++] = P[i];
+                    }
+                    int is4 = 0, ov = 0, pass = 0;
+                    int q[4] = {0, 0, 0, 0};
+                    if (mv > kFastVertices) {
+                        ov = 1;
+                    } else if (mv > 0) {
+                        int* R = reinterpret_cast<int*>(KS);      // the k values are dead: reduced vertices as x | y << 16
+                        for (int i = 0; i < mv; ++i) R[i] = qx(P[i]) | (qy(P[i]) << 16);
+                        PolyStats st;
+                        poly_stats(R, mv, st);
+                        const double area = st.area / 65536.0;
+                        const int lo = min(st.bw, st.bh), hi = max(st.bw, st.bh);
+                        const double ratio = (lo == 0 || hi == 0) ? -1.0 : static_cast<double>(lo) / static_cast<double>(hi);
+                        pass = !(area < 0.35 || area > 1.0) && !(ratio < 0.6);
+                        if (d == 0 || pass) {
+                            const int cnt = approx_poly(R, mv, 0.1 * st.arclen, S, S + kFastVertices);
+                            if (cnt == 4) {
+                                is4 = 1;
+                                for (int j = 0; j < 4; ++j) q[j] = S[j];
+                            }
+                        }
+                    }
+                    int* r = reinterpret_cast<int*>(cshare);
+                    r[0] = is4; r[1] = ov; r[2] = pass; r[3] = q[0]; r[4] = q[1]; r[5] = q[2]; r[6] = q[3];
+                }
+                __syncwarp();
+                const int* r = reinterpret_cast<const int*>(cshare);
+                const int is4 = r[0], ov = r[1], pass = r[2];
+                const int q0 = r[3], q1 = r[4], q2 = r[5], q3 = r[6];
+                __syncwarp();
+                if (ov) {
+                    need_full = true;
+                    break;
+                }
+                if (d == 0 && is4) {
+                    first_is4 = true;
+                    first_q[0] = q0; first_q[1] = q1; first_q[2] = q2; first_q[3] = q3;
+                }
+                // all candidates here are outer borders: cv2 lists outer borders in reverse discovery order
+                if (pass && is4 && d > best_d) {
+                    best_valid = true;
+                    best_d = d;
+                    best_q[0] = q0; best_q[1] = q1; best_q[2] = q2; best_q[3] = q3;
+                }
+            }
+        }
+    }
+
+    if (lane == 0) {
+        if (need_full) {
+            status[b] = QUAD_NEED_FULL;
+            found[b] = 0;
+            for (int j = 0; j < 8; ++j) quad[b * 8 + j] = 0;
+            return;
+        }
+        bool ok = false;
+        int q[4] = {0, 0, 0, 0};
+        if (ncont == 1) {
+            ok = first_is4;
+            for (int j = 0; j < 4; ++j) q[j] = first_q[j];
+        } else if (ncont > 1) {
+            ok = best_valid;
+            for (int j = 0; j < 4; ++j) q[j] = best_q[j];
+        }
+        if (ok && px(q[0]) < px(q[2])) {  // _rotate_quadrangle
+            const int t = q[3];
+            q[3] = q[2]; q[2] = q[1]; q[1] = q[0]; q[0] = t;
+        }
+        for (int j = 0; j < 4; ++j) {
+            quad[(b * 4 + j) * 2 + 0] = ok ? px(q[j]) : 0;
+            quad[(b * 4 + j) * 2 + 1] = ok ? py(q[j]) : 0;
+        }
+        found[b] = ok ? 1 : 0;
+        status[b] = ok ? QUAD_FOUND : QUAD_NONE;
+        n_contours[b] = ncont;
+    }
+}
+
 }  // namespace
 
 cudaError_t configure_quad() {
+    cudaError_t e = cudaFuncSetAttribute(k_mask_to_quad_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_mask_to_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem);
 }
 
 cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* found, int32_t* status, int32_t* n_contours,
-                                int32_t* owner_scratch, int N, cudaStream_t s) {
+                                int32_t* owner_scratch, int N, bool full_only, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
-    k_mask_to_quad<<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch);
+    if (full_only) {
+        k_mask_to_quad<<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch, 0);
+        return cudaGetLastError();
+    }
+    // compact kernel for every board, then the full-state kernel for the boards it flagged (early exit otherwise)
+    k_mask_to_quad_fast<<<N, 32, kFastSmem, s>>>(mask, quad, found, status, n_contours);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_mask_to_quad<<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch, 1);
     return cudaGetLastError();
 }
 

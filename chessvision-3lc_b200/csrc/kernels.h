@@ -30,14 +30,16 @@ constexpr int kQuadMaxPoints = 8192;     // border points of one contour held in
 constexpr int kQuadMaxBorders = 32000;   // borders per mask (int16 labels)
 constexpr int kQuadMaxVertices = 2048;   // vertices after the TC89_KCOS reduction
 // status codes written per board by the quad kernel
-enum QuadStatus : int { QUAD_NONE = 0, QUAD_FOUND = 1, QUAD_OVERFLOW = 2 };
+enum QuadStatus : int { QUAD_NONE = 0, QUAD_FOUND = 1, QUAD_OVERFLOW = 2, QUAD_NEED_FULL = 3 /* internal: compact kernel -> full kernel */ };
 
 cudaError_t configure_quad();
 cudaError_t configure_warp();
 // mask u8 [N,256,256]; quad int32 [N,4,2] (x,y in the 256x256 mask frame, after _rotate_quadrangle);
 // found u8 [N]; status int32 [N]; owner_scratch int32 [N, kQuadMaxBorders]
+// full_only: run only the full-state kernel (A/B measurements, tests); otherwise the compact kernel runs first and the
+// full-state kernel re-runs the boards it flagged.
 cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* found, int32_t* status, int32_t* n_contours,
-                                int32_t* owner_scratch, int N, cudaStream_t s);
+                                int32_t* owner_scratch, int N, bool full_only, cudaStream_t s);
 // quad -> inverse homography (double[9] per board), scale = H_img / 256 applied to both axes (core.py:414-417)
 cudaError_t launch_homography(const int32_t* quad, const uint8_t* found, double* minv, int N, float scale, int out_w,
                               int out_h, cudaStream_t s);

@@ -50,6 +50,50 @@ def test_mask_to_quad_matches_oracle(engine):
     assert n_found >= 30
 
 
+def _check_quads(eng, masks):
+    quad, found, status = eng.mask_to_quad(torch.from_numpy(masks).cuda())
+    quad, found, status = quad.cpu().numpy(), found.cpu().numpy(), status.cpu().numpy()
+    n_found = 0
+    for i, m in enumerate(masks):
+        want = og.find_quadrangle(m)
+        assert status[i] in (0, 1), f"mask {i}: status {status[i]}"
+        assert bool(found[i]) == (want is not None), f"mask {i}: found flag differs from the oracle"
+        if want is not None:
+            n_found += 1
+            assert np.array_equal(quad[i], want.reshape(4, 2)), f"mask {i}: {quad[i].tolist()} != {want.reshape(4, 2).tolist()}"
+    return n_found
+
+
+def test_mask_to_quad_compact_and_full_kernels_agree_with_oracle(monkeypatch):
+    """The compact kernel (bit planes, 4 boards per SM) defers big holes / capacity overflows to the full-state kernel;
+    both routes, and the full-state kernel alone (CVB_QUAD_FULL=1), must reproduce the oracle on a second, larger suite
+    that includes frames (a hole that passes the area filter), nested shapes and very ragged masks."""
+    from chessvision import _native
+    masks = list(synth.mask_suite(seed=23, n=96))
+    frame = np.full((256, 256), 255, np.uint8)
+    frame[20:236, 24:230] = 0                       # big hole: only hole border and image-frame outer border
+    ring = np.zeros((256, 256), np.uint8)
+    ring[16:240, 16:240] = 255
+    ring[40:216, 40:216] = 0
+    ring[60:196, 60:196] = 255                      # component nested inside the hole of another
+    rng = np.random.default_rng(4)
+    noisy = (rng.random((256, 256)) < 0.5).astype(np.uint8) * 255   # thousands of tiny borders
+    speck = synth.quad_mask(rng, specks=0)
+    speck[::7, ::5] ^= 255                           # isolated pixels and pin holes everywhere
+    masks = np.stack(masks + [frame, ring, noisy, speck])
+    eng = _native.Engine(0, max_batch=8)
+    try:
+        assert _check_quads(eng, masks) >= 40
+    finally:
+        eng.close()
+    monkeypatch.setenv("CVB_QUAD_FULL", "1")
+    eng = _native.Engine(0, max_batch=8)
+    try:
+        assert _check_quads(eng, masks) >= 40
+    finally:
+        eng.close()
+
+
 def test_warp_squares_bit_exact(engine):
     rng = np.random.default_rng(3)
     imgs, quads = zip(*[synth.board_image(rng) for _ in range(6)])

@@ -125,6 +125,25 @@ def test_host_path_equals_device_path(trained_engine, golden):
         assert torch.equal(dev[k].cpu(), host[k]), f"output '{k}' differs between device and host entry points"
 
 
+def test_host_path_with_small_groups(golden, monkeypatch):
+    """Same with one chunk per geometry group (CVB_GROUP_CHUNKS=1): several groups, both staging slots and a ragged tail."""
+    from chessvision import _native
+    _, _, imgs = golden
+    monkeypatch.setenv("CVB_GROUP_CHUNKS", "1")
+    eng = _native.Engine(0, max_batch=8)
+    try:
+        eng.load_unet(load_checkpoint(WEIGHTS / "best_extractor.pth"))
+        eng.load_resnet18(load_checkpoint(WEIGHTS / "best_classifier.pth"))
+        sel = imgs[:29]
+        dev = eng.image_to_fen(torch.from_numpy(sel).cuda(), eng.alloc_outputs(len(sel), full=True))
+        torch.cuda.synchronize()
+        host = eng.image_to_fen_host(torch.from_numpy(sel).pin_memory(), eng.alloc_outputs(len(sel), full=True, pinned_host=True))
+        for k in dev:
+            assert torch.equal(dev[k].cpu(), host[k]), f"output '{k}' differs between device and host entry points"
+    finally:
+        eng.close()
+
+
 def test_python_api_process_image(golden):
     """The drop-in class, as the reference's tests use it (tests/test_chessvision.py:45-116): structural checks plus
     agreement with the golden FEN for the reference's own fixture image."""
