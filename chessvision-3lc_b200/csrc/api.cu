@@ -52,6 +52,7 @@ struct cvb_ctx {
     bool unet_loaded = false;
     float *stem_w = nullptr, *stem_b = nullptr;        // inc.double_conv.0 folded, fp32 [27][64], [64] (CVB_STEM_FP32 A/B path)
     void* stem_wsw = nullptr;                          // same layer as a swizzled fp16 [64][64] tcgen05 B tile
+    CUtensorMap stem_omap;                             // TMA store view of t0 for the stem kernel
     bool stem_fp32 = false;                            // CVB_STEM_FP32=1: CUDA-core fp32 stems (A/B measurements only)
     float* outc_w = nullptr;                           // [64]
     float outc_b = 0.f;
@@ -380,7 +381,7 @@ int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logi
     {
         StageTimer t(ctx, 1, s);
         if (ctx->stem_fp32) CK(aux(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, ctx->t0, n, 256, 256, 64, s)));
-        else CK(aux(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, ctx->t0, n, 64, ctx->sm_count, s)));
+        else CK(aux(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, &ctx->stem_omap, n, ctx->sm_count, s)));
     }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[0], n, s)) return -2; }                       // inc.3      t0 -> cat0[0:64)
     { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat0, ctx->p1, n, 256, 256, 64, 128, s))); }
@@ -606,6 +607,8 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     static const int width[5] = {64, 128, 256, 512, 1024};
     if (pack_stem(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, &ctx->stem_w, &ctx->stem_b)) return -4;
     if (pack_stem_tc(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, 16, 4, &ctx->stem_wsw)) return -4;
+    if (tmap_act(&ctx->stem_omap, ctx->t0, 64, 256, 256, B, 64, 256 * 64, 65536LL * 64, 64, 2, 1))
+        return fail(ctx, -6, "cuTensorMapEncodeTiled (stem output view) failed");
     ctx->unet_w.resize(21);
     auto& W = ctx->unet_w;
     int wi = 0;
@@ -885,8 +888,13 @@ int cvb_unet_stem(cvb_ctx* ctx, const uint8_t* img, int N, void* out, void* stre
     if (set_device(ctx)) return -2;
     if (!ctx->unet_loaded) return fail(ctx, -7, "UNet weights not loaded (call cvb_load_unet)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (ctx->stem_fp32) CK(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, static_cast<__half*>(out), N, 256, 256, 64, s));
-    else CK(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, static_cast<__half*>(out), N, 64, ctx->sm_count, s));
+    if (ctx->stem_fp32) {
+        CK(launch_unet_stem(img, ctx->stem_w, ctx->stem_b, static_cast<__half*>(out), N, 256, 256, 64, s));
+    } else {
+        CUtensorMap om;
+        if (tmap_act(&om, out, 64, 256, 256, N, 64, 256 * 64, 65536LL * 64, 64, 2, 1)) return fail(ctx, -6, "cuTensorMapEncodeTiled failed");
+        CK(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, &om, N, ctx->sm_count, s));
+    }
     ctx->launches++;
     return 0;
 }

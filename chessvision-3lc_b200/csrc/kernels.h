@@ -1,5 +1,6 @@
 // Launchers of the non-tensor-core kernels (internal to the library).
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,8 +21,9 @@ cudaError_t launch_head(const __half* feat, const float* fcw, const float* fcb, 
 
 // stem_tc.cu: the same two first layers on tcgen05 (wsw = swizzled fp16 [64][64] B tile, see pack_stem_tc in api.cu)
 cudaError_t configure_stems_tc();
-cudaError_t launch_unet_stem_tc(const uint8_t* img, const void* wsw, const float* bias, __half* out, int N, int out_c_stride,
-                                int sm_count, cudaStream_t s);
+// omap: 4-D view {C, 256, 256, N} of the fp16 NHWC output with box {64, 64, 2, 1} (128-byte swizzle) for the tile store
+cudaError_t launch_unet_stem_tc(const uint8_t* img, const void* wsw, const float* bias, const CUtensorMap* omap, int N, int sm_count,
+                                cudaStream_t s);
 cudaError_t launch_resnet_stem_tc(const uint8_t* board, const void* wsw, const float* bias, __half* out, int n_boards, int sm_count,
                                   cudaStream_t s);
 

@@ -11,15 +11,17 @@
 //   k_resnet_stem_tc  extract_squares (core.py:420-439) -> /255 (core.py:236-237) -> Conv7x7 s2 p3 (1->64) + BN + ReLU
 //                     -> MaxPool3x3 s2 p1 (timm resnet18 conv1/bn1/act1/maxpool)   -> fp16 NHWC [N*64,16,16,64]
 //
-// Warp roles (288 threads): warps 0-3 producers (input staging + im2col rows), warps 4-7 epilogue (TMEM lanes 32*(w&3)),
-// warp 8 TMEM allocation + MMA issue.  One CTA per SM, persistent over squares / image blocks.
+// Warp roles: warps 0-3 producers (input staging + im2col rows), then epilogue warpgroups (TMEM lanes 32*(w&3); the
+// ResNet stem has two, one per 32-channel half, because its pooling epilogue is the long pole), last warp TMEM allocation
+// + MMA issue.  One CTA per SM, persistent over squares / image blocks.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace cvb {
 namespace {
 
-constexpr int kThreads = 288;
+constexpr int kThreads = 288;      // UNet stem: 4 producer + 4 epilogue + 1 MMA warps
+constexpr int kRsThreads = 416;    // ResNet stem: 4 producer + 8 epilogue + 1 MMA warps
 constexpr int kStages = 4;
 constexpr int kABytes = 128 * 128;   // 128 im2col rows x 64 fp16
 constexpr int kBBytes = 64 * 128;    // 64 output channels x 64 fp16
@@ -49,12 +51,13 @@ struct Bars {
 };
 
 // Common prologue: barriers + TMEM (128 columns = two 64-column accumulators).  Called by all threads.
+template <int kMmaWarp, int kEpiThreads>
 __device__ __forceinline__ uint32_t setup(uint64_t* bars, uint32_t* tmem_slot, Bars& b, int warp, int lane) {
     b.full = smem_u32(bars);
     b.empty = b.full + 8 * kStages;
     b.tfull = b.empty + 8 * kStages;
     b.tempty = b.tfull + 16;
-    if (warp == 8) {
+    if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int i = 0; i < kStages; ++i) {
                 mbar_init(b.full + 8 * i, 128);
@@ -62,7 +65,7 @@ __device__ __forceinline__ uint32_t setup(uint64_t* bars, uint32_t* tmem_slot, B
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(b.tfull + 8 * i, 1);
-                mbar_init(b.tempty + 8 * i, 128);
+                mbar_init(b.tempty + 8 * i, kEpiThreads);
             }
             mbar_fence_init();
         }
@@ -92,10 +95,11 @@ constexpr int kRsInBytes = ((kRsInHalfs * 2 + 1023) / 1024) * 1024;
 constexpr int kRsOffA = kBBytes;
 constexpr int kRsOffIn = kRsOffA + kStages * kABytes;
 constexpr int kRsOffH = kRsOffIn + 2 * kRsInBytes;       // ring of 16 horizontally pooled conv rows [16 px][64 ch]
-constexpr int kRsOffBars = kRsOffH + 16 * 2048;
+constexpr int kRsOffBias = kRsOffH + 16 * 2048;
+constexpr int kRsOffBars = kRsOffBias + 256;
 constexpr int kRsSmem = kRsOffBars + 256 + 1024;
 
-__global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* __restrict__ board, const uint4* __restrict__ wsw,
+__global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t* __restrict__ board, const uint4* __restrict__ wsw,
                                                                const float* __restrict__ bias, __half* __restrict__ out,
                                                                int n_squares) {
     extern __shared__ uint8_t smem_raw[];
@@ -106,12 +110,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* _
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    for (int i = tid; i < kBBytes / 16; i += kThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
-    for (int i = tid; i < 2 * kRsInBytes / 16; i += kThreads) reinterpret_cast<uint4*>(base + kRsOffIn)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kStages * 128; i += kThreads)   // K columns 56..63 (the padding chunk) stay zero for ever
+    for (int i = tid; i < kBBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
+    for (int i = tid; i < 2 * kRsInBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base + kRsOffIn)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kStages * 128; i += kRsThreads)   // K columns 56..63 (the padding chunk) stay zero for ever
         *reinterpret_cast<uint4*>(base + kRsOffA + (i >> 7) * kABytes + sw128(i & 127, 7)) = make_uint4(0, 0, 0, 0);
+    if (tid < 64) reinterpret_cast<float*>(base + kRsOffBias)[tid] = __ldg(bias + tid);
     Bars b;
-    const uint32_t tmem_base = setup(bars, tmem_slot, b, warp, lane);
+    const uint32_t tmem_base = setup<12, 256>(bars, tmem_slot, b, warp, lane);
 
     if (warp < 4) {
         // ------------------------------------------------------------------------------------------------ producers
@@ -170,36 +175,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* _
             }
             buf ^= 1;
         }
-    } else if (warp < 8) {
+    } else if (warp < 12) {
         // ------------------------------------------------------------------------------------------------ epilogue
-        const int e = warp & 3, etid = tid - 128;
+        // warpgroup g (warps 4-7 / 8-11) owns channels 32g .. 32g+31 of every conv pixel
+        const int e = warp & 3, g = (warp - 4) >> 2, etid = (tid - 128) & 127;
         uint8_t* sH = base + kRsOffH;
+        const float4* b4 = reinterpret_cast<const float4*>(base + kRsOffBias) + 8 * g;
         int iter = 0;
         for (int sq = blockIdx.x; sq < n_squares; sq += gridDim.x) {
             for (int t = 0; t < 8; ++t, ++iter) {
                 const int acc = iter & 1;
                 mbar_wait(b.tfull + 8 * acc, (iter >> 1) & 1);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + acc * 64;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(taddr, v0);
-                tmem_ld_32x32(taddr + 32, v1);
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + acc * 64 + g * 32, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(b.tempty + 8 * acc);
                 // conv pixel (y = 4t + e, x = lane): bias + ReLU -> fp16, then the horizontal half of the 3x3 max pool
-                uint32_t hv[32];
+                uint32_t hv[16];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float4 ba = __ldg(reinterpret_cast<const float4*>(bias) + i);
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + 8 + i);
-                    hv[2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[4 * i]) + ba.x, 0.f), fmaxf(__uint_as_float(v0[4 * i + 1]) + ba.y, 0.f)));
-                    hv[2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[4 * i + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v0[4 * i + 3]) + ba.w, 0.f)));
-                    hv[16 + 2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[4 * i + 1]) + bb.y, 0.f)));
-                    hv[16 + 2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[4 * i + 3]) + bb.w, 0.f)));
+                    const float4 bb = b4[i];
+                    hv[2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v[4 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * i + 1]) + bb.y, 0.f)));
+                    hv[2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v[4 * i + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) + bb.w, 0.f)));
                 }
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     const uint32_t up = __shfl_up_sync(0xffffffffu, hv[i], 1);       // lane 0 keeps its own value
                     const uint32_t dn = __shfl_down_sync(0xffffffffu, hv[i], 1);
                     hv[i] = h2_bits(__hmax2(bits_h2(hv[i]), __hmax2(bits_h2(up), bits_h2(dn))));
@@ -208,14 +210,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* _
                     const int px = lane >> 1;
                     uint8_t* dst = sH + ((iter * 4 + e) & 15) * 2048 + px * 128;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        *reinterpret_cast<uint4*>(dst + ((c ^ (px & 7)) << 4)) = make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(dst + (((4 * g + c) ^ (px & 7)) << 4)) = make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
                 }
-                named_bar(2, 128);
-                // vertical half: pooled rows 2t (conv rows 4t-1..4t+1) and 2t+1 (conv rows 4t+1..4t+3)
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int px = (etid >> 3) & 15, c = etid & 7;
+                named_bar(2 + g, 128);
+                // vertical half: pooled rows 2t (conv rows 4t-1..4t+1) and 2t+1 (conv rows 4t+1..4t+3); one 16-byte item per thread
+                {
+                    const int k = etid >> 6, px = (etid >> 2) & 15, c = 4 * g + (etid & 3);
                     const int first = k ? 1 : (t == 0 ? 0 : -1);
                     uint4 m = make_uint4(0, 0, 0, 0);   // activations are >= 0, so 0 is the identity of max
                     for (int dy = first; dy <= (k ? 3 : 1); ++dy) {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_resnet_stem_tc(const uint8_t* _
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 128);
     }
@@ -267,12 +268,14 @@ constexpr int kUsRedBytes = ((34 * 68 * 8 + 1023) / 1024) * 1024;   // reduced p
 constexpr int kUsOffA = kBBytes;
 constexpr int kUsOffRaw = kUsOffA + kStages * kABytes;
 constexpr int kUsOffRed = kUsOffRaw + 2 * kUsRawBytes;
-constexpr int kUsOffBars = kUsOffRed + kUsRedBytes;
+constexpr int kUsOffOut = kUsOffRed + kUsRedBytes;          // two 16 KB staging buffers for the TMA tile store
+constexpr int kUsOffBias = kUsOffOut + 2 * kABytes;
+constexpr int kUsOffBars = kUsOffBias + 256;
 constexpr int kUsSmem = kUsOffBars + 256 + 1024;
 
 __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __restrict__ img, const uint4* __restrict__ wsw,
-                                                             const float* __restrict__ bias, __half* __restrict__ out,
-                                                             int n_images, int out_c_stride) {
+                                                             const float* __restrict__ bias, const __grid_constant__ CUtensorMap omap,
+                                                             int n_images) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
@@ -285,8 +288,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
     for (int i = tid; i < kBBytes / 16; i += kThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
     for (int i = tid; i < kStages * 128 * 2; i += kThreads)   // K columns 48..63 stay zero
         *reinterpret_cast<uint4*>(base + kUsOffA + (i >> 8) * kABytes + sw128((i >> 1) & 127, 6 + (i & 1))) = make_uint4(0, 0, 0, 0);
+    if (tid < 64) reinterpret_cast<float*>(base + kUsOffBias)[tid] = __ldg(bias + tid);
+    if (tid == 0) tma_prefetch_desc(&omap);
     Bars b;
-    const uint32_t tmem_base = setup(bars, tmem_slot, b, warp, lane);
+    const uint32_t tmem_base = setup<8, 128>(bars, tmem_slot, b, warp, lane);
 
     if (warp < 4) {
         // ------------------------------------------------------------------------------------------------ producers
@@ -350,8 +355,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
         }
     } else if (warp < 8) {
         // ------------------------------------------------------------------------------------------------ epilogue
-        const int e = warp & 3;
-        const int row = e * 32 + lane, ty = row >> 6, x = row & 63;
+        // TMEM -> bias + ReLU -> fp16 -> swizzled staging tile -> one TMA store of the 2-row x 64-column x 64-channel box
+        const int e = warp & 3, etid = tid - 128;
+        const int row = e * 32 + lane;
+        const float4* b4 = reinterpret_cast<const float4*>(base + kUsOffBias);
         int iter = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int n = unit >> 5, y0 = ((unit >> 2) & 7) * 32, x0 = (unit & 3) * 64;
@@ -366,29 +373,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(b.tempty + 8 * acc);
-                uint4* dst = reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * 256 + y0 + 2 * t + ty) * 256 + x0 + x) * out_c_stride);
+                uint32_t o[32];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * i + 1);
-                    uint4 o;
-                    o.x = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[8 * i]) + b0.x, 0.f), fmaxf(__uint_as_float(v0[8 * i + 1]) + b0.y, 0.f)));
-                    o.y = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[8 * i + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v0[8 * i + 3]) + b0.w, 0.f)));
-                    o.z = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[8 * i + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v0[8 * i + 5]) + b1.y, 0.f)));
-                    o.w = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[8 * i + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v0[8 * i + 7]) + b1.w, 0.f)));
-                    dst[i] = o;
+                for (int i = 0; i < 8; ++i) {
+                    const float4 ba = b4[i], bb = b4[8 + i];
+                    o[2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[4 * i]) + ba.x, 0.f), fmaxf(__uint_as_float(v0[4 * i + 1]) + ba.y, 0.f)));
+                    o[2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[4 * i + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v0[4 * i + 3]) + ba.w, 0.f)));
+                    o[16 + 2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[4 * i + 1]) + bb.y, 0.f)));
+                    o[16 + 2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[4 * i + 3]) + bb.w, 0.f)));
                 }
+                const int buf = iter & 1;
+                if (etid == 0) bulk_wait_read<1>();   // the store issued two tiles ago has finished reading this buffer
+                named_bar(2, 128);
+                uint8_t* dst = base + kUsOffOut + buf * kABytes;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 8 + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 9 + 2 * i);
-                    uint4 o;
-                    o.x = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[8 * i]) + b0.x, 0.f), fmaxf(__uint_as_float(v1[8 * i + 1]) + b0.y, 0.f)));
-                    o.y = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[8 * i + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v1[8 * i + 3]) + b0.w, 0.f)));
-                    o.z = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[8 * i + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v1[8 * i + 5]) + b1.y, 0.f)));
-                    o.w = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[8 * i + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v1[8 * i + 7]) + b1.w, 0.f)));
-                    dst[4 + i] = o;
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + sw128(row, j)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                fence_proxy_async();
+                named_bar(2, 128);
+                if (etid == 0) {
+                    tma_store_4d(&omap, base_addr + kUsOffOut + buf * kABytes, 0, x0, y0 + 2 * t, n);
+                    bulk_commit();
                 }
             }
         }
+        if (etid == 0) bulk_wait_all();
     } else {
         // ------------------------------------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_f16(128, 64, 0);
@@ -430,17 +439,16 @@ cudaError_t launch_resnet_stem_tc(const uint8_t* board, const void* wsw, const f
                                   cudaStream_t s) {
     const int n_squares = n_boards * 64;
     if (n_squares == 0) return cudaSuccess;
-    k_resnet_stem_tc<<<n_squares < sm_count ? n_squares : sm_count, kThreads, kRsSmem, s>>>(board, static_cast<const uint4*>(wsw), bias, out,
+    k_resnet_stem_tc<<<n_squares < sm_count ? n_squares : sm_count, kRsThreads, kRsSmem, s>>>(board, static_cast<const uint4*>(wsw), bias, out,
                                                                                            n_squares);
     return cudaGetLastError();
 }
 
-cudaError_t launch_unet_stem_tc(const uint8_t* img, const void* wsw, const float* bias, __half* out, int N, int out_c_stride,
-                                int sm_count, cudaStream_t s) {
+cudaError_t launch_unet_stem_tc(const uint8_t* img, const void* wsw, const float* bias, const CUtensorMap* omap, int N, int sm_count,
+                                cudaStream_t s) {
     const int n_units = N * 32;
     if (n_units == 0) return cudaSuccess;
-    k_unet_stem_tc<<<n_units < sm_count ? n_units : sm_count, kThreads, kUsSmem, s>>>(img, static_cast<const uint4*>(wsw), bias, out, N,
-                                                                                     out_c_stride);
+    k_unet_stem_tc<<<n_units < sm_count ? n_units : sm_count, kThreads, kUsSmem, s>>>(img, static_cast<const uint4*>(wsw), bias, *omap, N);
     return cudaGetLastError();
 }
 
