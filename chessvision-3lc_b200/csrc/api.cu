@@ -18,111 +18,9 @@
 
 using namespace cvb;
 
-namespace {
-
-constexpr int kStages = 7;
-constexpr int kMaxProfileEvents = 8192;
-
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-};
-
-struct ConvWeights {
-    __half* w = nullptr;   // [rows][K]
-    float* bias = nullptr; // [rows]
-    int rows = 0, K = 0;
-};
-
-}  // namespace
-
-struct cvb_ctx {
-    int device = 0;
-    int max_batch = 0;        // boards per network chunk (activation workspaces)
-    int group_chunks = 8;     // chunks per geometry group: mask->quad / warp run once over up to group_chunks*max_batch boards
-    int group = 0;            // = group_chunks * max_batch
-    bool quad_full_only = false;   // CVB_QUAD_FULL=1: skip the compact mask->quad kernel (A/B measurements, tests)
-    int sm_count = 148;
-    bool use_vr = true;   // CVB_NO_VR=1 forces the generic conv kernel everywhere (A/B measurements)
-    std::string err;
-    int64_t launches = 0;
-    std::vector<void*> allocs;
-
-    // ---- UNet
-    bool unet_loaded = false;
-    float *stem_w = nullptr, *stem_b = nullptr;        // inc.double_conv.0 folded, fp32 [27][64], [64] (CVB_STEM_FP32 A/B path)
-    void* stem_wsw = nullptr;                          // same layer as a swizzled fp16 [64][64] tcgen05 B tile
-    CUtensorMap stem_omap;                             // TMA store view of t0 for the stem kernel
-    bool stem_fp32 = false;                            // CVB_STEM_FP32=1: CUDA-core fp32 stems (A/B measurements only)
-    float* outc_w = nullptr;                           // [64]
-    float outc_b = 0.f;
-    std::vector<ConvWeights> unet_w;                   // 17 conv3x3 + 4 convT, in plan order
-    __half *cat0, *t0, *p1, *t1, *cat1, *p2, *t2, *cat2, *p3, *t3, *cat3, *p4, *t4, *x5, *u1, *u2, *u3;
-    std::vector<ConvLaunch> unet_plan;                 // indices documented in build_unet_plan
-    float* ws_logits = nullptr;                        // [B,256,256]
-    uint8_t* ws_mask = nullptr;                        // [B,256,256]
-
-    // ---- geometry
-    int32_t *ws_quad = nullptr, *ws_status = nullptr, *ws_ncont = nullptr, *ws_owner = nullptr;
-    uint8_t* ws_found = nullptr;
-    double* ws_minv = nullptr;
-    uint8_t* ws_board = nullptr;                       // [B,512,512]
-
-    // ---- ResNet-18
-    bool resnet_loaded = false;
-    float *rstem_w = nullptr, *rstem_b = nullptr;      // conv1+bn1 folded fp32 [49][64], [64]
-    void* rstem_wsw = nullptr;                         // conv1+bn1 as a swizzled fp16 [64][64] tcgen05 B tile
-    float *fc_w = nullptr, *fc_b = nullptr;            // [13][512], [13]
-    std::vector<ConvWeights> res_w;
-    __half* rbuf[12] = {nullptr};                      // 3 per resolution level
-    std::vector<ConvLaunch> res_plan;
-    float* ws_probs = nullptr;
-    uint8_t *ws_labels = nullptr, *ws_labels_valid = nullptr;
-    char* ws_fen = nullptr;
-
-    // ---- host streaming
-    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-    std::vector<cudaEvent_t> ev_in[2];   // one per chunk of a group: the network of chunk c starts when its images have landed
-    cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    uint8_t* slot_img[2] = {nullptr, nullptr};
-    // per-slot device outputs for the host path
-    cvb_outputs slot_out[2];
-
-    // ---- profiling
-    bool profile = false;
-    std::vector<cudaEvent_t> pev;
-    std::vector<int> pev_stage;
-    int pev_used = 0;
-    float stage_ms[kStages] = {0};
-};
+#include "ctx.h"
 
 namespace {
-
-int fail(cvb_ctx* c, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (c) c->err = buf;
-    return code;
-}
-
-#define CK(call)                                                                                          \
-    do {                                                                                                  \
-        cudaError_t e_ = (call);                                                                          \
-        if (e_ != cudaSuccess) return fail(ctx, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-template <class T>
-int dalloc(cvb_ctx* ctx, T** p, size_t count) {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
-    if (e != cudaSuccess) return fail(ctx, -3, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-    ctx->allocs.push_back(q);
-    *p = static_cast<T*>(q);
-    return 0;
-}
 
 const cvb_tensor* find(const cvb_tensor* sd, int n, const std::string& name) {
     for (int i = 0; i < n; ++i)
@@ -254,97 +152,18 @@ int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& c
     return 0;
 }
 
-void pick_tile(int Ho, int Wo, int& tn, int& th, int& tw) {
-    tw = Wo < 16 ? Wo : 16;
-    th = 128 / tw;
-    if (th > Ho) th = Ho;
-    tn = 128 / (tw * th);
-}
-
-// Describe one conv (ksize 1|3, stride 1|2, pad ksize/2) over an NHWC fp16 buffer whose pixel stride is in_c_stride.
+// Thin wrappers over conv_build / conv_set_store (conv_tc.cu) that turn their error codes into context messages.
 int build_conv(cvb_ctx* ctx, ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int in_c_stride, int in_c_off, int Cin,
                const ConvWeights& cw, int ksize, int stride, int epilogue) {
-    memset(&L, 0, sizeof L);
-    ConvParams& p = L.p;
-    const int Ho = Hin / stride, Wo = Win / stride;
-    if (Cin % 64 || cw.K != ksize * ksize * Cin) return fail(ctx, -5, "conv: Cin=%d K=%d ksize=%d not supported", Cin, cw.K, ksize);
-    pick_tile(Ho, Wo, p.tn, p.th, p.tw);
-    if (Wo % p.tw || Ho % p.th || p.tn * p.th * p.tw != 128) return fail(ctx, -5, "conv: %dx%d output cannot be tiled", Ho, Wo);
-    p.H = Ho;
-    p.W = Wo;
-    p.tiles_w = Wo / p.tw;
-    p.tiles_h = Ho / p.th;
-    p.taps = ksize * ksize;
-    p.c_chunks = Cin / 64;
-    p.a_c_off = in_c_off;
-    const int64_t sW = in_c_stride, sH = static_cast<int64_t>(Win) * in_c_stride, sN = static_cast<int64_t>(Hin) * Win * in_c_stride;
-    int rc = 0;
-    if (stride == 1) {
-        rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, p.th, p.tn);
-        for (int r = 0; r < ksize; ++r)
-            for (int s = 0; s < ksize; ++s) {
-                p.tap_map[r * ksize + s] = 0;
-                p.tap_dy[r * ksize + s] = static_cast<int8_t>(r - ksize / 2);
-                p.tap_dx[r * ksize + s] = static_cast<int8_t>(s - ksize / 2);
-            }
-    } else {
-        // stride 2: four parity views (py,px) of the input, each with doubled strides; tap r reads parity (r+1)&1 at
-        // view offset -1 (r == 0) or 0, and the zero fill of the view at -1 is exactly the padding row/column.
-        for (int py = 0; py < 2 && !rc; ++py)
-            for (int px = 0; px < 2 && !rc; ++px)
-                rc = tmap_act(&p.a_map[py * 2 + px], in + (static_cast<int64_t>(py) * Win + px) * in_c_stride, in_c_stride,
-                              Win / 2, Hin / 2, Nmax, 2 * sW, 2 * sH, sN, p.tw, p.th, p.tn);
-        for (int r = 0; r < ksize; ++r)
-            for (int s = 0; s < ksize; ++s) {
-                const int rr = ksize == 1 ? 1 : r, ss = ksize == 1 ? 1 : s;  // 1x1: the centre tap
-                const int py = (rr + 1) & 1, px = (ss + 1) & 1;
-                p.tap_map[r * ksize + s] = static_cast<int8_t>(py * 2 + px);
-                p.tap_dy[r * ksize + s] = static_cast<int8_t>(rr == 0 ? -1 : 0);
-                p.tap_dx[r * ksize + s] = static_cast<int8_t>(ss == 0 ? -1 : 0);
-            }
-    }
-    if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (activations) failed: %d", rc);
-    L.block_n = cw.rows % 256 == 0 ? 256 : (cw.rows % 128 == 0 ? 128 : 64);
-    if (epilogue == EPI_OUTC) L.block_n = 64;
-    if (cw.rows % L.block_n) return fail(ctx, -5, "conv: Cout=%d not a multiple of %d", cw.rows, L.block_n);
-    p.n_tiles = cw.rows / L.block_n;
-    rc = tmap_weights(&p.b_map, cw.w, cw.K, cw.rows, L.block_n);
-    if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (weights) failed: %d", rc);
-    p.bias = cw.bias;
-    L.epilogue = epilogue;
-    L.n_max = Nmax;
-    if (ctx->use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
-        rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
-        if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (vertical-reuse view) failed: %d", rc);
-    }
+    const int rc = conv_build(L, in, Nmax, Hin, Win, in_c_stride, in_c_off, Cin, cw.w, cw.bias, cw.rows, cw.K, ksize, stride, epilogue,
+                              ctx->use_vr);
+    if (rc == -5) return fail(ctx, -5, "conv: Cin=%d Cout=%d K=%d ksize=%d on %dx%d not supported", Cin, cw.rows, cw.K, ksize, Hin, Win);
+    if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (conv operands) failed: %d", rc);
     return 0;
 }
 
-// Output side of a launch: NHWC fp16 buffer with `out_c_stride` channels per pixel, first output channel `out_c_off`.
-// Builds the TMA store views (box {64 ch, tw, th, tn}); the transposed convolution gets one stride-2 view per (dy,dx).
 int set_store(cvb_ctx* ctx, ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride) {
-    ConvParams& p = L.p;
-    p.out = out;
-    p.out_c_stride = out_c_stride;
-    p.out_c_off = out_c_off;
-    p.relu = relu;
-    p.res = res;
-    p.res_c_stride = res_c_stride;
-    if (L.epilogue == EPI_OUTC) {
-        p.out_bufs = 0;
-        return 0;
-    }
-    if (L.variant == 0) p.out_bufs = 2;
-    int rc = 0;
-    const int64_t C = out_c_stride;
-    if (L.epilogue == EPI_CONVT) {
-        const int64_t W2 = 2 * p.W, H2 = 2 * p.H;
-        for (int q = 0; q < 4 && !rc; ++q)
-            rc = tmap_act(&p.o_map[q], out + ((q >> 1) * W2 + (q & 1)) * C, out_c_stride, p.W, p.H, L.n_max, 2 * C, 2 * W2 * C, H2 * W2 * C,
-                          p.tw, p.th, p.tn);
-    } else {
-        rc = tmap_act(&p.o_map[0], out, out_c_stride, p.W, p.H, L.n_max, C, p.W * C, static_cast<int64_t>(p.H) * p.W * C, p.tw, p.th, p.tn);
-    }
+    const int rc = conv_set_store(L, out, out_c_stride, out_c_off, relu, res, res_c_stride);
     if (rc) return fail(ctx, -6, "cuTensorMapEncodeTiled (output view) failed: %d", rc);
     return 0;
 }

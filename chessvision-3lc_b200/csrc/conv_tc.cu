@@ -18,6 +18,7 @@
 #include "conv_tc.h"
 
 #include <stdio.h>
+#include <string.h>
 
 namespace cvb {
 
@@ -524,6 +525,140 @@ int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int bl
 
 int tmap_act_vr(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN) {
     return tmap_act(m, base, C, Wv, Hv, Nv, sW, sH, sN, 8, 18, 1);
+}
+
+static void pick_tile(int Ho, int Wo, int& tn, int& th, int& tw) {
+    tw = Wo < 16 ? Wo : 16;
+    th = 128 / tw;
+    if (th > Ho) th = Ho;
+    tn = 128 / (tw * th);
+}
+
+// Describe one conv (ksize 1|3, stride 1|2, pad ksize/2) over an NHWC fp16 buffer whose pixel stride is in_c_stride.
+// Returns 0, -5 (shape not supported) or a cuTensorMapEncodeTiled error (< -1000).
+int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int in_c_stride, int in_c_off, int Cin, const __half* w,
+               const float* bias, int rows, int K, int ksize, int stride, int epilogue, bool use_vr) {
+    memset(&L, 0, sizeof L);
+    ConvParams& p = L.p;
+    const int Ho = Hin / stride, Wo = Win / stride;
+    if (Cin % 64 || K != ksize * ksize * Cin) return -5;
+    pick_tile(Ho, Wo, p.tn, p.th, p.tw);
+    if (Wo % p.tw || Ho % p.th || p.tn * p.th * p.tw != 128) return -5;
+    p.H = Ho;
+    p.W = Wo;
+    p.tiles_w = Wo / p.tw;
+    p.tiles_h = Ho / p.th;
+    p.taps = ksize * ksize;
+    p.c_chunks = Cin / 64;
+    p.a_c_off = in_c_off;
+    const int64_t sW = in_c_stride, sH = static_cast<int64_t>(Win) * in_c_stride, sN = static_cast<int64_t>(Hin) * Win * in_c_stride;
+    int rc = 0;
+    if (stride == 1) {
+        rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, p.th, p.tn);
+        for (int r = 0; r < ksize; ++r)
+            for (int s = 0; s < ksize; ++s) {
+                p.tap_map[r * ksize + s] = 0;
+                p.tap_dy[r * ksize + s] = static_cast<int8_t>(r - ksize / 2);
+                p.tap_dx[r * ksize + s] = static_cast<int8_t>(s - ksize / 2);
+            }
+    } else {
+        // stride 2: four parity views (py,px) of the input, each with doubled strides; tap r reads parity (r+1)&1 at
+        // view offset -1 (r == 0) or 0, and the zero fill of the view at -1 is exactly the padding row/column.
+        for (int py = 0; py < 2 && !rc; ++py)
+            for (int px = 0; px < 2 && !rc; ++px)
+                rc = tmap_act(&p.a_map[py * 2 + px], in + (static_cast<int64_t>(py) * Win + px) * in_c_stride, in_c_stride,
+                              Win / 2, Hin / 2, Nmax, 2 * sW, 2 * sH, sN, p.tw, p.th, p.tn);
+        for (int r = 0; r < ksize; ++r)
+            for (int s = 0; s < ksize; ++s) {
+                const int rr = ksize == 1 ? 1 : r, ss = ksize == 1 ? 1 : s;  // 1x1: the centre tap
+                const int py = (rr + 1) & 1, px = (ss + 1) & 1;
+                p.tap_map[r * ksize + s] = static_cast<int8_t>(py * 2 + px);
+                p.tap_dy[r * ksize + s] = static_cast<int8_t>(rr == 0 ? -1 : 0);
+                p.tap_dx[r * ksize + s] = static_cast<int8_t>(ss == 0 ? -1 : 0);
+            }
+    }
+    if (rc) return rc;
+    L.block_n = rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64);
+    if (epilogue == EPI_OUTC) L.block_n = 64;
+    if (rows % L.block_n) return -5;
+    p.n_tiles = rows / L.block_n;
+    rc = tmap_weights(&p.b_map, w, K, rows, L.block_n);
+    if (rc) return rc;
+    p.bias = bias;
+    L.epilogue = epilogue;
+    L.n_max = Nmax;
+    if (use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
+        rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// "Convolution" with kernel 2x2, stride 2, no padding over an NHWC buffer [Nmax, 2*Ho, 2*Wo, in_c_stride]: tap q = (dy,dx)
+// reads the parity view q at the output pixel itself.  This is the data gradient of ConvTranspose2d(k=2, s=2)
+// (unet_parts.py:53): dx[p][ci] = sum_{q,co} dy[2p+q][co] * W[ci][co][q], weights packed [rows = Cin_t][K = 4*C] with
+// k = q*C + co.  C = channels read per tap (from in_c_off).
+int conv_build_k2s2(ConvLaunch& L, const __half* in, int Nmax, int Ho, int Wo, int in_c_stride, int in_c_off, int C, const __half* w,
+                    const float* bias, int rows, int K) {
+    memset(&L, 0, sizeof L);
+    ConvParams& p = L.p;
+    if (C % 64 || K != 4 * C) return -5;
+    pick_tile(Ho, Wo, p.tn, p.th, p.tw);
+    if (Wo % p.tw || Ho % p.th || p.tn * p.th * p.tw != 128) return -5;
+    p.H = Ho;
+    p.W = Wo;
+    p.tiles_w = Wo / p.tw;
+    p.tiles_h = Ho / p.th;
+    p.taps = 4;
+    p.c_chunks = C / 64;
+    p.a_c_off = in_c_off;
+    const int Win = 2 * Wo, Hin = 2 * Ho;
+    const int64_t sW = in_c_stride, sH = static_cast<int64_t>(Win) * in_c_stride, sN = static_cast<int64_t>(Hin) * Win * in_c_stride;
+    int rc = 0;
+    for (int q = 0; q < 4 && !rc; ++q) {
+        rc = tmap_act(&p.a_map[q], in + (static_cast<int64_t>(q >> 1) * Win + (q & 1)) * in_c_stride, in_c_stride, Wo, Ho, Nmax, 2 * sW,
+                      2 * sH, sN, p.tw, p.th, p.tn);
+        p.tap_map[q] = static_cast<int8_t>(q);
+        p.tap_dy[q] = p.tap_dx[q] = 0;
+    }
+    if (rc) return rc;
+    L.block_n = rows % 256 == 0 ? 256 : (rows % 128 == 0 ? 128 : 64);
+    if (rows % L.block_n) return -5;
+    p.n_tiles = rows / L.block_n;
+    rc = tmap_weights(&p.b_map, w, K, rows, L.block_n);
+    if (rc) return rc;
+    p.bias = bias;
+    L.epilogue = EPI_STORE;
+    L.n_max = Nmax;
+    return 0;
+}
+
+// Output side of a launch: NHWC fp16 buffer with `out_c_stride` channels per pixel, first output channel `out_c_off`.
+// Builds the TMA store views (box {64 ch, tw, th, tn}); the transposed convolution gets one stride-2 view per (dy,dx).
+int conv_set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride) {
+    ConvParams& p = L.p;
+    p.out = out;
+    p.out_c_stride = out_c_stride;
+    p.out_c_off = out_c_off;
+    p.relu = relu;
+    p.res = res;
+    p.res_c_stride = res_c_stride;
+    if (L.epilogue == EPI_OUTC) {
+        p.out_bufs = 0;
+        return 0;
+    }
+    if (L.variant == 0) p.out_bufs = 2;
+    int rc = 0;
+    const int64_t C = out_c_stride;
+    if (L.epilogue == EPI_CONVT) {
+        const int64_t W2 = 2 * p.W, H2 = 2 * p.H;
+        for (int q = 0; q < 4 && !rc; ++q)
+            rc = tmap_act(&p.o_map[q], out + ((q >> 1) * W2 + (q & 1)) * C, out_c_stride, p.W, p.H, L.n_max, 2 * C, 2 * W2 * C, H2 * W2 * C,
+                          p.tw, p.th, p.tn);
+    } else {
+        rc = tmap_act(&p.o_map[0], out, out_c_stride, p.W, p.H, L.n_max, C, p.W * C, static_cast<int64_t>(p.H) * p.W * C, p.tw, p.th, p.tn);
+    }
+    return rc;
 }
 
 constexpr int kVrMaxSmem = 227 * 1024;

@@ -71,6 +71,13 @@ int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int bl
 int tmap_act_vr(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN);
 bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin);
 
+// Host-side construction of a launch (api.cu / train.cu).  Return 0, -5 (shape not supported) or a tensor-map error.
+int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int in_c_stride, int in_c_off, int Cin, const __half* w,
+               const float* bias, int rows, int K, int ksize, int stride, int epilogue, bool use_vr);
+int conv_build_k2s2(ConvLaunch& L, const __half* in, int Nmax, int Ho, int Wo, int in_c_stride, int in_c_off, int C, const __half* w,
+                    const float* bias, int rows, int K);
+int conv_set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride);
+
 // Launch on `stream` for the first `n_images` images; grid sized to min(tiles, SM count).
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream);
 // One-time: raise the dynamic shared-memory limit of every instantiation.

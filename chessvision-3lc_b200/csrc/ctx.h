@@ -1,0 +1,121 @@
+// Internal: the context object behind the C ABI (shared by api.cu and train.cu).
+#pragma once
+#include "../../include/chessvision_b200.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "conv_tc.h"
+
+struct cvb_trainer;   // train.cu
+
+using namespace cvb;
+
+constexpr int kStages = 7;
+constexpr int kMaxProfileEvents = 8192;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct ConvWeights {
+    __half* w = nullptr;   // [rows][K]
+    float* bias = nullptr; // [rows]
+    int rows = 0, K = 0;
+};
+
+struct cvb_ctx {
+    int device = 0;
+    int max_batch = 0;        // boards per network chunk (activation workspaces)
+    int group_chunks = 8;     // chunks per geometry group: mask->quad / warp run once over up to group_chunks*max_batch boards
+    int group = 0;            // = group_chunks * max_batch
+    bool quad_full_only = false;   // CVB_QUAD_FULL=1: skip the compact mask->quad kernel (A/B measurements, tests)
+    int sm_count = 148;
+    bool use_vr = true;   // CVB_NO_VR=1 forces the generic conv kernel everywhere (A/B measurements)
+    std::string err;
+    int64_t launches = 0;
+    std::vector<void*> allocs;
+
+    // ---- UNet
+    bool unet_loaded = false;
+    float *stem_w = nullptr, *stem_b = nullptr;        // inc.double_conv.0 folded, fp32 [27][64], [64] (CVB_STEM_FP32 A/B path)
+    void* stem_wsw = nullptr;                          // same layer as a swizzled fp16 [64][64] tcgen05 B tile
+    CUtensorMap stem_omap;                             // TMA store view of t0 for the stem kernel
+    bool stem_fp32 = false;                            // CVB_STEM_FP32=1: CUDA-core fp32 stems (A/B measurements only)
+    float* outc_w = nullptr;                           // [64]
+    float outc_b = 0.f;
+    std::vector<ConvWeights> unet_w;                   // 17 conv3x3 + 4 convT, in plan order
+    __half *cat0, *t0, *p1, *t1, *cat1, *p2, *t2, *cat2, *p3, *t3, *cat3, *p4, *t4, *x5, *u1, *u2, *u3;
+    std::vector<ConvLaunch> unet_plan;                 // indices documented in build_unet_plan
+    float* ws_logits = nullptr;                        // [B,256,256]
+    uint8_t* ws_mask = nullptr;                        // [B,256,256]
+
+    // ---- geometry
+    int32_t *ws_quad = nullptr, *ws_status = nullptr, *ws_ncont = nullptr, *ws_owner = nullptr;
+    uint8_t* ws_found = nullptr;
+    double* ws_minv = nullptr;
+    uint8_t* ws_board = nullptr;                       // [B,512,512]
+
+    // ---- ResNet-18
+    bool resnet_loaded = false;
+    float *rstem_w = nullptr, *rstem_b = nullptr;      // conv1+bn1 folded fp32 [49][64], [64]
+    void* rstem_wsw = nullptr;                         // conv1+bn1 as a swizzled fp16 [64][64] tcgen05 B tile
+    float *fc_w = nullptr, *fc_b = nullptr;            // [13][512], [13]
+    std::vector<ConvWeights> res_w;
+    __half* rbuf[12] = {nullptr};                      // 3 per resolution level
+    std::vector<ConvLaunch> res_plan;
+    float* ws_probs = nullptr;
+    uint8_t *ws_labels = nullptr, *ws_labels_valid = nullptr;
+    char* ws_fen = nullptr;
+
+    // ---- host streaming
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in[2];   // one per chunk of a group: the network of chunk c starts when its images have landed
+    cudaEvent_t ev_comp[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    uint8_t* slot_img[2] = {nullptr, nullptr};
+    // per-slot device outputs for the host path
+    cvb_outputs slot_out[2];
+
+    // ---- UNet training step (train.cu); owned, destroyed with the context
+    cvb_trainer* trainer = nullptr;
+
+    // ---- profiling
+    bool profile = false;
+    std::vector<cudaEvent_t> pev;
+    std::vector<int> pev_stage;
+    int pev_used = 0;
+    float stage_ms[kStages] = {0};
+};
+
+inline int fail(cvb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(ctx, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+inline int dalloc(cvb_ctx* ctx, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T));
+    if (e != cudaSuccess) return fail(ctx, -3, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    ctx->allocs.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
