@@ -10,6 +10,9 @@ $NVCC $FLAGS -c csrc/stem.cu -o build/stem.o &
 $NVCC $FLAGS -Xptxas -v -c csrc/stem_tc.cu -o build/stem_tc.o 2> build/stem_tc.ptxas.log &
 $NVCC $FLAGS -fmad=false -c csrc/geometry.cu -o build/geometry.o &
 $NVCC $FLAGS -c csrc/api.cu -o build/api.o &
+$NVCC $FLAGS -c csrc/wgrad_tc.cu -o build/wgrad_tc.o &
+$NVCC $FLAGS -c csrc/train_kernels.cu -o build/train_kernels.o &
+$NVCC $FLAGS -c csrc/train.cu -o build/train.o &
 wait
-$NVCC -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o
+$NVCC -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o build/wgrad_tc.o build/train_kernels.o build/train.o
 echo "built $(pwd)/libchessvision_b200.so"

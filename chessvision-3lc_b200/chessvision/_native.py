@@ -31,6 +31,12 @@ class _Outputs(C.Structure):
 
 OUTPUT_FIELDS = tuple(n for n, _ in _Outputs._fields_)
 
+
+class TrainConfig(C.Structure):
+    """cvb_train_config (include/chessvision_b200.h); defaults follow scripts/train/train_unet.py of the reference."""
+    _fields_ = [("batch", C.c_int32), ("loss_scale", C.c_float), ("momentum", C.c_float), ("alpha", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("max_grad_norm", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float)]
+
 # every symbol include/chessvision_b200.h declares: name -> (restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 SYMBOLS = {
@@ -53,6 +59,14 @@ SYMBOLS = {
     "cvb_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P]),
     "cvb_unet_stem": (_I, [_P, _P, _I, _P, _P]),
     "cvb_resnet_stem": (_I, [_P, _P, _I, _P, _P]),
+    "cvb_train_default_config": (_I, [C.POINTER(TrainConfig)]),
+    "cvb_train_create": (_I, [_P, C.POINTER(_Tensor), _I, C.POINTER(TrainConfig)]),
+    "cvb_train_forward_backward": (_I, [_P, _P, _P, _P, _P]),
+    "cvb_train_grads": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "cvb_train_optimizer_step": (_I, [_P, _F, _F, _P]),
+    "cvb_train_step": (_I, [_P, _P, _P, _F, _P, _P]),
+    "cvb_train_export": (_I, [_P, _I, C.POINTER(_Tensor), _I]),
+    "cvb_wgrad3x3_f16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "cvb_launch_count": (C.c_int64, [_P]),
     "cvb_profile": (_I, [_P, _I]),
     "cvb_profile_read": (_I, [_P, C.POINTER(C.c_float), _I]),
@@ -259,6 +273,79 @@ class Engine:
         out = torch.empty((n * 64, 16, 16, 64), dtype=torch.float16, device=self.device)
         self._ck(self.lib.cvb_resnet_stem(self.h, _ptr(board), n, _ptr(out), _stream()), "cvb_resnet_stem")
         return out
+
+    # ---- UNet training step (cvb_train_*)
+    def train_create(self, state_dict, batch=2, **overrides):
+        """model.train() state of UNet(3,1) from a state_dict; overrides: any field of TrainConfig."""
+        cfg = TrainConfig()
+        self._ck(self.lib.cvb_train_default_config(C.byref(cfg)), "cvb_train_default_config")
+        cfg.batch = batch
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown training option '{k}'")
+            setattr(cfg, k, v)
+        arr, keep = _state_dict_array(state_dict)
+        self._ck(self.lib.cvb_train_create(self.h, arr, len(arr), C.byref(cfg)), "cvb_train_create")
+        self.train_cfg = cfg
+        self._train_shapes = {k: tuple(v.shape) for k, v in state_dict.items() if torch.is_tensor(v) and v.is_floating_point()}
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        return cfg
+
+    def _check_batch(self, images, masks):
+        b = self.train_cfg.batch
+        assert images.is_cuda and images.dtype == torch.float32 and tuple(images.shape) == (b, 3, 256, 256) and images.is_contiguous()
+        assert masks.is_cuda and masks.dtype == torch.float32 and masks.numel() == b * 65536 and masks.is_contiguous()
+
+    def train_forward_backward(self, images, masks):
+        """images fp32 [B,3,256,256], masks fp32 [B,1,256,256]; returns the loss as a 1-element device tensor (no sync)."""
+        self._check_batch(images, masks)
+        self._ck(self.lib.cvb_train_forward_backward(self.h, _ptr(images), _ptr(masks), _ptr(self._loss), _stream()),
+                 "cvb_train_forward_backward")
+        return self._loss
+
+    def train_grads(self):
+        """The library's flat fp32 gradient buffer as a torch tensor aliasing the same device memory (for the all-reduce)."""
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.cvb_train_grads(self.h, C.byref(ptr), C.byref(cnt)), "cvb_train_grads")
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (cnt.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 3, "strides": None}
+
+        return torch.as_tensor(_Alias(), device=self.device)
+
+    def train_optimizer_step(self, lr, grad_scale=1.0):
+        self._ck(self.lib.cvb_train_optimizer_step(self.h, lr, grad_scale, _stream()), "cvb_train_optimizer_step")
+
+    def train_step(self, images, masks, lr):
+        self._check_batch(images, masks)
+        self._ck(self.lib.cvb_train_step(self.h, _ptr(images), _ptr(masks), lr, _ptr(self._loss), _stream()), "cvb_train_step")
+        return self._loss
+
+    def train_export(self, grads=False):
+        """Parameters + BatchNorm running statistics (or the gradients) as a CPU state_dict in torch layout."""
+        out, items = {}, []
+        for k, shape in self._train_shapes.items():
+            if grads and ("running_" in k):
+                continue
+            a = np.zeros(shape, np.float32)
+            out[k] = a
+            t = _Tensor()
+            t.name = k.encode()
+            t.data = a.ctypes.data
+            t.ndim = a.ndim
+            for i in range(4):
+                t.shape[i] = a.shape[i] if i < a.ndim else 1
+            items.append(t)
+        arr = (_Tensor * len(items))(*items)
+        self._ck(self.lib.cvb_train_export(self.h, 1 if grads else 0, arr, len(items)), "cvb_train_export")
+        return {k: torch.from_numpy(v) for k, v in out.items()}
+
+    def wgrad3x3_f16(self, dz, x, scale=1.0):
+        n, h, w, cout = dz.shape
+        cin = x.shape[3]
+        dw = torch.empty((cout, 9, cin), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.cvb_wgrad3x3_f16(self.h, _ptr(dz), _ptr(x), n, h, w, cout, cin, scale, _ptr(dw), _stream()), "cvb_wgrad3x3_f16")
+        return dw
 
     def launch_count(self) -> int:
         return int(self.lib.cvb_launch_count(self.h))

@@ -415,6 +415,7 @@ void cvb_destroy(cvb_ctx* ctx) {
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->trainer) cvb_trainer_free(ctx->trainer);
     delete ctx;
 }
 

@@ -159,7 +159,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void epilogue_consts(const ConvParams& p, int n_tile, float* s_bias, float* s_outw, int etid) {
     named_bar_sync(1, 128);   // nobody still reads the previous tile's constants
-    for (int i = etid; i < BLOCK_N; i += 128) s_bias[i] = __ldg(p.bias + n_tile * BLOCK_N + i);
+    // transposed convolution: the four (dy,dx) column blocks share one per-channel bias (index modulo Cout)
+    for (int i = etid; i < BLOCK_N; i += 128)
+        s_bias[i] = __ldg(p.bias + (EPI == EPI_CONVT ? (n_tile * BLOCK_N + i) % p.convt_cout : n_tile * BLOCK_N + i));
     if constexpr (EPI == EPI_OUTC) {
         if (etid < 64) s_outw[etid] = __ldg(p.outc_w + etid);
     }

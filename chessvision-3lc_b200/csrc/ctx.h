@@ -13,6 +13,7 @@
 #include "conv_tc.h"
 
 struct cvb_trainer;   // train.cu
+void cvb_trainer_free(cvb_trainer* t);
 
 using namespace cvb;
 

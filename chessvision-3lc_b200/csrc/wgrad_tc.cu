@@ -15,6 +15,7 @@
 // warps 4-7 epilogue (tcgen05.ld -> scale -> red.global.add.f32 into the fp32 gradient buffer).  Work item = (tile of
 // the weight matrix, slice of the pixel range); slices of one tile are combined by the atomics.
 #include "common.cuh"
+#include "conv_tc.h"
 #include "wgrad_tc.h"
 
 #include <string.h>

@@ -109,6 +109,45 @@ CVB_API int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, 
 CVB_API int cvb_unet_stem(cvb_ctx* ctx, const uint8_t* img, int N, void* out, void* stream);
 CVB_API int cvb_resnet_stem(cvb_ctx* ctx, const uint8_t* board, int N, void* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * UNet board-extractor training step (BASELINE.json configs[4]; reference scripts/train/train_unet.py:236-245,293-323,
+ * chessvision/pytorch_unet/utils/dice_score.py:5-30).  fp16 tensor-core operands, fp32 master weights / accumulation /
+ * optimizer state (what the reference's `--amp` autocast path computes), BatchNorm in training mode with local batch
+ * statistics.  Data-parallel use: forward_backward on every rank, all-reduce (sum) the flat gradient buffer over NCCL,
+ * then optimizer_step with grad_scale = 1/world_size.
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct cvb_train_config {
+    int32_t batch;        /* images per step on this GPU (fixed; scripts/bin/train_board_extractor.sh uses 2)           */
+    float loss_scale;     /* static factor applied to the fp16 activation gradients (GradScaler's role), default 4096   */
+    float momentum;       /* RMSprop momentum 0.999 (train_unet.py:240)                                                  */
+    float alpha;          /* RMSprop alpha 0.99, eps 1e-8 (torch defaults)                                               */
+    float eps;
+    float weight_decay;   /* 1e-8 (train_unet.py:239)                                                                    */
+    float max_grad_norm;  /* clip_grad_norm_ threshold 1.0 (train_unet.py:321)                                           */
+    float bn_momentum;    /* nn.BatchNorm2d defaults 0.1 / 1e-5                                                          */
+    float bn_eps;
+} cvb_train_config;
+
+CVB_API int cvb_train_default_config(cvb_train_config* cfg);
+/* UNet(3,1) in model.train() state from a state_dict (same tensors cvb_load_unet takes); cfg NULL = reference defaults. */
+CVB_API int cvb_train_create(cvb_ctx* ctx, const cvb_tensor* state_dict, int n_tensors, const cvb_train_config* cfg);
+/* masks_pred = model(images); loss = BCEWithLogits + dice_loss; loss.backward()  (train_unet.py:309-319).
+ * img fp32 [B,3,256,256] NCHW, mask fp32 [B,1,256,256] in {0,1}, loss: 1 float; all device pointers. */
+CVB_API int cvb_train_forward_backward(cvb_ctx* ctx, const float* img, const float* mask, float* loss, void* stream);
+/* The flat fp32 gradient buffer written by forward_backward (packed layout; only sums/norms are layout independent). */
+CVB_API int cvb_train_grads(cvb_ctx* ctx, float** grads, int64_t* count);
+/* clip_grad_norm_(params, max_grad_norm); optimizer.step()  (train_unet.py:321-322) on grads * grad_scale. */
+CVB_API int cvb_train_optimizer_step(cvb_ctx* ctx, float lr, float grad_scale, void* stream);
+/* Single-GPU convenience: forward_backward + optimizer_step(grad_scale 1). */
+CVB_API int cvb_train_step(cvb_ctx* ctx, const float* img, const float* mask, float lr, float* loss, void* stream);
+/* Copy parameters + BatchNorm running statistics (what = 0) or gradients (what = 1) back in torch state_dict layout:
+ * out[i].name / shape select the tensor, out[i].data must point to WRITABLE host memory. */
+CVB_API int cvb_train_export(cvb_ctx* ctx, int what, const cvb_tensor* out, int n_tensors);
+/* Building block exposed for parity tests: weight gradient of Conv2d(3x3, pad 1) on the tcgen05 MN-major kernel.
+ * dz fp16 [N,H,H,Cout], x fp16 [N,H,H,Cin] (dense NHWC) -> dw fp32 [Cout][9][Cin] = scale * sum_p dz[p] (x) x[p+tap]. */
+CVB_API int cvb_wgrad3x3_f16(cvb_ctx* ctx, const void* dz, const void* x, int N, int H, int W, int Cout, int Cin, float scale,
+                             float* dw, void* stream);
+
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 CVB_API int64_t cvb_launch_count(const cvb_ctx* ctx);
 
