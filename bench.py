@@ -149,8 +149,146 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def synthetic_training_batch(b: int, seed: int):
+    """configs[4] input: fp32 [b,3,256,256] images in [0,1] (smooth colour field + checkerboard inside a random quad) and
+    the quad's {0,1} mask [b,1,256,256] -- the shape and value range scripts/train/train_unet.py feeds the UNet."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.meshgrid(np.arange(256, dtype=np.float32), np.arange(256, dtype=np.float32), indexing="ij")
+    imgs = np.empty((b, 3, 256, 256), np.float32)
+    masks = np.empty((b, 1, 256, 256), np.float32)
+    for i in range(b):
+        cx, cy = 128 + 30 * (rng.random(2) - 0.5)
+        r = 60 + 40 * rng.random()
+        th = 0.6 * (rng.random() - 0.5)
+        u = (xx - cx) * np.cos(th) + (yy - cy) * np.sin(th)
+        v = -(xx - cx) * np.sin(th) + (yy - cy) * np.cos(th)
+        m = ((np.abs(u) < r) & (np.abs(v) < r * (0.8 + 0.2 * rng.random()))).astype(np.float32)
+        base = np.kron(rng.random((3, 8, 8)).astype(np.float32), np.ones((32, 32), np.float32))
+        checker = (np.floor(u / (r / 4)) + np.floor(v / (r / 4))) % 2
+        imgs[i] = np.clip(0.6 * base + 0.4 * m * checker + 0.05 * rng.random((3, 256, 256)).astype(np.float32), 0, 1)
+        masks[i, 0] = m
+    return imgs, masks
+
+
+def run_train_reference(args):
+    """--impl reference --workload train: the fp32 oracle of the reference's training step (oracle/train.py, pinned to
+    scripts/train/train_unet.py) on the host cores, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from oracle import train as otrain
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = max(1, min(args.train_batch, 2))
+    model = otrain.new_model(0)
+    opt = otrain.make_optimizer(model, 1e-6)
+    imgs, masks = synthetic_training_batch(b, SEED)
+    imgs, masks = torch.from_numpy(imgs), torch.from_numpy(masks)
+    for _ in range(min(args.warmup, 1)):
+        otrain.train_step(model, opt, imgs, masks)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        otrain.train_step(model, opt, imgs, masks)
+    dt = time.perf_counter() - t0
+    thr = b * args.steps / dt
+    cores = os.cpu_count() or 1
+    print(json.dumps({
+        "impl": "reference", "metric": "UNet training images/sec (fwd+bwd+clip+RMSprop)", "value": thr, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "configs[4]: UNet training step", "batch_per_step": b},
+        "cpu_baseline": {"value": thr, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of batch {b}, fp32 torch oracle of train_unet.py's step, {cores} threads"},
+        "e2e": {"value": thr, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_train(args):
+    """--workload train (BASELINE.json configs[4]): UNet training step, data-parallel, NCCL all-reduce of the flat fp32
+    gradient buffer between backward and the optimizer.  One step = fwd + loss + bwd + all-reduce + clip + RMSprop on
+    `--train-batch` images per GPU."""
+    import torch
+    import torch.distributed as dist
+    from chessvision import utils
+    from chessvision.training import UNetTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.train_batch
+    sd = utils.load_state_dict(str(ROOT / "weights" / "best_extractor.pth"))[0]
+    tr = UNetTrainer(sd, batch_size=B, learning_rate=1e-6, device=local_rank)
+    imgs, masks = synthetic_training_batch(B, SEED + rank)
+    h_img, h_mask = torch.from_numpy(imgs).pin_memory(), torch.from_numpy(masks).pin_memory()
+    d_img, d_mask = h_img.to(dev), h_mask.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        tr.step(d_img, d_mask)
+    barrier()
+    l0 = tr.engine.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            loss = tr.step(d_img, d_mask)
+        e1.record(stream)
+        barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = tr.engine.launch_count() - l0
+    clocks = clk.summary()
+    # end to end: pinned host batch -> H2D -> step -> loss D2H, every step
+    for _ in range(args.warmup):
+        float(tr.step(h_img.to(dev, non_blocking=True), h_mask.to(dev, non_blocking=True)).item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = float(tr.step(h_img.to(dev, non_blocking=True), h_mask.to(dev, non_blocking=True)).item())
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+    total = B * args.steps * world
+    value = total / (dev_ms / 1000.0)
+    peak_tf, _, peak_src = measured_peaks()
+    tflops = 3 * UNET_GFLOP * value / 1000.0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "UNet training images/sec (fwd+bwd+clip+RMSprop)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands, f32 master weights/accumulation", "data": "synthetic (quad masks + checkerboard images), trained start weights",
+            "config": {"workload": "configs[4]: UNet board-extractor training step, data-parallel", "batch_per_gpu": B,
+                       "l2": f"activations + gradients of one step ({B} x ~0.5 GB) exceed L2, no flush",
+                       "parallelism": f"dp{world}, NCCL all-reduce of 31.0 M fp32 gradients per step"},
+            "e2e": {"value": total / (e2e_ms / 1000.0), "unit": "images/s", "h2d_bytes_per_step": B * 4 * 256 * 256 * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps, "last_loss": last},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "whole step (conv_tc fwd + dgrad, wgrad_tc)", "achieved": tflops, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": tflops / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_gflop_per_image": 3 * UNET_GFLOP},
+            "clocks": clocks, "loss": float(loss.item())}), flush=True)
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "train"],
+                    help="pipeline = BASELINE.json's metric (configs[3]); train = UNet training step (configs[4])")
+    ap.add_argument("--train-batch", type=int, default=8, help="--workload train: images per GPU per step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
@@ -163,7 +301,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
+        return run_train_reference(args) if args.workload == "train" else run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist
