@@ -18,6 +18,7 @@
 #include "conv_tc.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace cvb {
@@ -483,6 +484,203 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 1, Cout = 64 "row streaming" variant for the two full-resolution UNet levels (inc.3, up4.conv0,
+// up4.conv3 + head).  With BLOCK_N = 64 one tcgen05.mma 128x64x16 reads 4 KB of A + 2 KB of B from shared memory for 32
+// tensor-clocks of work, so the kernels above are bound by shared-memory operand bandwidth at ~45 % tensor utilisation
+// (profiles/README.md).  Here the three VERTICAL taps of one horizontal offset become one MMA with N = 192:
+//     D[128 pixels of input row y][dy*64 + co] = A(row y, shifted by dx) . [W(dy=0,dx) | W(dy=1,dx) | W(dy=2,dx)]
+// so A is read once for three taps.  Column block dy is the contribution of input row y to OUTPUT row y + 1 - dy; the
+// TMEM accumulator is a ring of eight 64-column slots, slot(out row r) = (-r) & 7, so the three blocks of an input row
+// land on three consecutive slots and consecutive input rows slide the window down by one slot.  An output row is
+// complete after input row r + 1 has been issued; its slot is then drained by the epilogue warps while the MMA warp
+// carries on with the other slots.  Where the window wraps around the ring (2 of 8 rows) and on the very first K step
+// of a slot (accumulate = 0 for block dy = 0 only) the MMA is split into N = 64 / N = 128 pieces.
+// One CTA streams a strip of rs_rows output rows x 128 columns of one image; weights (9*Cin*64*2 B) stay resident.
+// rs_mode 0: one TMA box {64 ch, 128 px} per (row, dx).  rs_mode 1/2: one box {64 ch, 130 px} per row, horizontal tap
+// dx addressed 128*dx bytes further (descriptor base_offset 0 / (addr >> 7) & 7).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRsBarBytes = 512;
+
+template <int EPI>
+__global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constant__ ConvParams p) {
+    constexpr int kBBytes = 64 * 128;
+    const int S = p.vr_stages;
+    const int R = p.rs_rows;
+    const int mode = p.rs_mode;
+    const uint32_t a_bytes = mode == 0 ? 128u * 128u : 130u * 128u;   // bytes one TMA box delivers
+    const uint32_t stage_bytes = mode == 0 ? 16384u : 17408u;         // 1024-aligned stage pitch
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base_addr - raw_addr);
+    const uint32_t w_bytes = 9u * p.c_chunks * kBBytes;
+    const uint32_t stages_addr = base_addr + w_bytes;
+    uint8_t* s_out = base_ptr + w_bytes + S * stage_bytes;
+    const uint32_t out_bytes = EPI == EPI_OUTC ? 0u : static_cast<uint32_t>(p.out_bufs * kOutBufBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + out_bytes);
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * S;
+    const uint32_t bar_tfull = bar_full + 16 * S;     // 8 slots
+    const uint32_t bar_tempty = bar_tfull + 64;       // 8 slots
+    const uint32_t bar_w = bar_tempty + 64;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 17);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.a_map[mode == 0 ? 0 : 1]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 8; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        mbar_init(bar_w, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int strips_per_image = p.tiles_h * p.tiles_w;
+    const int total_strips = p.tiles_n * strips_per_image;
+    const int loads_per_row = mode == 0 ? 3 * p.c_chunks : p.c_chunks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_w, w_bytes);
+            // resident order: ((dx * c_chunks + kc) * 3 + dy), so the three vertical taps of one (dx, kc) are one N = 192 operand
+            for (int dxi = 0; dxi < 3; ++dxi)
+                for (int kc = 0; kc < p.c_chunks; ++kc)
+                    for (int dy = 0; dy < 3; ++dy)
+                        tma_load_2d(base_addr + ((dxi * p.c_chunks + kc) * 3 + dy) * kBBytes, &p.b_map, bar_w,
+                                    ((dy * 3 + dxi) * p.c_chunks + kc) * 64, 0);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_strips; t += gridDim.x) {
+            const int w0 = (t % p.tiles_w) * 128;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
+            const int n0 = t / strips_per_image;
+            for (int j = -1; j <= R; ++j) {
+                for (int l = 0; l < loads_per_row; ++l) {
+                    const int kc = mode == 0 ? l / 3 : l;
+                    const int dxi = mode == 0 ? l - 3 * kc : 0;
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_full + 8 * stage, a_bytes);
+                        tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[mode == 0 ? 0 : 1], bar_full + 8 * stage,
+                                    p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        mbar_wait(bar_w, 0);
+        tc_fence_after();
+        const uint32_t idesc0 = p.idesc & ~(0x3Fu << 17);
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t rho0 = 0;   // output rows this CTA has started before the current strip
+        for (int t = blockIdx.x; t < total_strips; t += gridDim.x, rho0 += R) {
+            for (int j = -1; j <= R; ++j) {
+                // input row j feeds output rows j + 1 - dy, dy in [dy_lo, dy_hi]
+                const int dy_lo = j + 2 - R > 0 ? j + 2 - R : 0;
+                const int dy_hi = j + 1 < 2 ? j + 1 : 2;
+                const uint32_t rho_new = rho0 + static_cast<uint32_t>(j + 1);
+                const uint32_t s_base = (0u - rho_new) & 7u;   // slot of block dy = (s_base + dy) & 7
+                if (dy_lo == 0) {   // block 0 starts output row rho_new: its slot must have been drained
+                    mbar_wait(bar_tempty + 8 * s_base, ((rho_new >> 3) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                for (int l = 0; l < loads_per_row; ++l) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = stages_addr + stage * stage_bytes;
+                        const int ndx = mode == 0 ? 1 : 3;
+                        for (int dd = 0; dd < ndx; ++dd) {
+                            const int kc = mode == 0 ? l / 3 : l;
+                            const int dxi = mode == 0 ? l - 3 * kc : dd;
+                            const uint32_t a_start = a_addr + (mode == 0 ? 0u : 128u * dd);
+                            uint64_t a_desc = umma_desc_sw128(a_start);
+                            if (mode == 2) a_desc |= static_cast<uint64_t>((a_start >> 7) & 7u) << 49;
+                            const uint64_t b_desc = umma_desc_sw128(base_addr + ((dxi * p.c_chunks + kc) * 3) * kBBytes);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const bool first = l == 0 && dd == 0 && k == 0;   // first K step of this input row
+                                int dy = dy_lo;
+                                while (dy <= dy_hi) {
+                                    const uint32_t slot = (s_base + dy) & 7u;
+                                    const bool fresh = first && dy == 0;   // overwrite: first contribution to a new output row
+                                    int nb = 1;
+                                    if (!fresh) {
+                                        while (dy + nb <= dy_hi && slot + nb < 8u) ++nb;
+                                    }
+                                    umma_f16(tmem_base + slot * 64u, a_desc + 2 * k, b_desc + ((dy * kBBytes) >> 4) + 2 * k,
+                                             idesc0 | (static_cast<uint32_t>(nb * 8) << 17), fresh ? 0u : 1u);
+                                    dy += nb;
+                                }
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * stage);
+                        // after the last K step of input row j, output row j - 1 is complete
+                        if (l == loads_per_row - 1 && j >= 1) umma_commit(bar_tfull + 8 * ((s_base + 2u) & 7u));
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        float* s_bias = reinterpret_cast<float*>(s_out + out_bytes + kRsBarBytes);
+        float* s_outw = s_bias + 256;
+        int store_count = 0;
+        epilogue_consts<64, EPI>(p, 0, s_bias, s_outw, threadIdx.x - 128);
+        uint32_t rho0 = 0;
+        for (int t = blockIdx.x; t < total_strips; t += gridDim.x, rho0 += R) {
+            const int w0 = (t % p.tiles_w) * 128;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
+            const int n = t / strips_per_image;
+            for (int r = 0; r < R; ++r) {
+                const uint32_t rho = rho0 + static_cast<uint32_t>(r);
+                const uint32_t slot = (0u - rho) & 7u;
+                mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
+                epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, s_out,
+                                       stages_addr + S * stage_bytes, store_count, threadIdx.x - 128);
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * slot);
+            }
+        }
+        if (threadIdx.x == 128) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------ host
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -589,7 +787,11 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
     p.bias = bias;
     L.epilogue = epilogue;
     L.n_max = Nmax;
-    if (use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
+    if (use_vr && conv_try_rs(L, ksize, stride, Ho, Wo, Cin)) {
+        rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 128, 1, 1);
+        if (!rc) rc = tmap_act(&p.a_map[1], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 130, 1, 1);
+        if (rc) return rc;
+    } else if (use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
         if (rc) return rc;
     }
@@ -689,6 +891,8 @@ cudaError_t conv_configure() {
     if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
     if ((e = configure_vr<128, EPI_STORE, false>()) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_OUTC, true>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -725,6 +929,44 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     return true;
 }
 
+// Decide whether the row-streaming kernel applies (3x3 s1, Cout = 64, rows of a multiple of 128 pixels) and size it.
+// CVB_NO_RS=1 disables it, CVB_RS_MODE=0|1|2 picks the activation staging (A/B measurements and tests).
+bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) {
+    ConvParams& p = L.p;
+    const char* off = getenv("CVB_NO_RS");
+    if (off && off[0] == '1') return false;
+    if (ksize != 3 || stride != 1 || Wo % 128 || L.block_n != 64 || p.n_tiles != 1) return false;
+    if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
+    const int R = Ho % 64 == 0 ? 64 : (Ho % 32 == 0 ? 32 : (Ho % 16 == 0 ? 16 : 0));
+    if (R == 0) return false;
+    const char* m = getenv("CVB_RS_MODE");
+    const int mode = m ? atoi(m) : 0;
+    if (mode < 0 || mode > 2) return false;
+    const int stage = mode == 0 ? 16384 : 17408;
+    const int w_bytes = 9 * (Cin / 64) * 64 * 128;
+    int out_bufs = L.epilogue == EPI_OUTC ? 0 : 2;
+    const int fixed = 1024 + kRsBarBytes + kEpiConstBytes;
+    int stages = (kVrMaxSmem - fixed - w_bytes - out_bufs * kOutBufBytes) / stage;
+    const int want = mode == 0 ? 6 : 3;
+    if (stages < want && out_bufs == 2) {
+        out_bufs = 1;
+        stages = (kVrMaxSmem - fixed - w_bytes - out_bufs * kOutBufBytes) / stage;
+    }
+    if (stages > 8) stages = 8;
+    if (stages < (mode == 0 ? 3 : 2)) return false;
+    p.vr_stages = stages;
+    p.w_stationary = 1;
+    p.rs_rows = R;
+    p.rs_mode = mode;
+    p.smem_bytes = w_bytes + stages * stage + out_bufs * kOutBufBytes + fixed;
+    p.out_bufs = out_bufs;
+    p.tn = 1; p.th = 1; p.tw = 128;
+    p.tiles_w = Wo / 128;
+    p.tiles_h = Ho / R;
+    L.variant = 2;
+    return true;
+}
+
 template <int BN, int EPI, bool WS>
 static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s) {
     conv3x3_vr_kernel<BN, EPI, WS><<<grid, 256, p.smem_bytes, s>>>(p);
@@ -739,6 +981,11 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     const long long total = 1LL * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = (int)(total < sm_count ? total : sm_count);
+    if (L.variant == 2) {
+        if (L.epilogue == EPI_OUTC) conv3x3_rs_kernel<EPI_OUTC><<<grid, 256, p.smem_bytes, stream>>>(p);
+        else conv3x3_rs_kernel<EPI_STORE><<<grid, 256, p.smem_bytes, stream>>>(p);
+        return cudaGetLastError();
+    }
     if (L.variant == 1) {
         const bool ws = p.w_stationary != 0;
         if (L.epilogue == EPI_OUTC) return launch_vr<64, EPI_OUTC, true>(p, grid, stream);

@@ -32,9 +32,11 @@ struct alignas(64) ConvParams {
     int N, H, W;   // output extent covered by the M tiles (N = images in this launch)
     int n_tiles;   // Cout_total / BLOCK_N
     uint32_t idesc;
-    int vr_stages;      // vertical-reuse variant: pipeline depth, weights resident in smem, dynamic smem size
+    int vr_stages;      // vertical-reuse / row-streaming variants: pipeline depth, weights resident in smem, dynamic smem size
     int w_stationary;
     int smem_bytes;
+    int rs_rows;        // row-streaming variant: output rows per strip
+    int rs_mode;        // ... activation staging: 0 = one box per (row, dx), 1/2 = one 130-pixel box per row
     // epilogue
     int relu;
     const float* bias;      // [Cout_total]
@@ -55,7 +57,7 @@ struct ConvLaunch {
     ConvParams p;
     int block_n;   // 64, 128 or 256
     int epilogue;  // ConvEpilogue
-    int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel
+    int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel, 2 row-streaming 3x3 kernel (Cout = 64)
     int n_max;     // images the activation / output views were built for
 };
 
@@ -70,6 +72,8 @@ int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int bl
 // Vertical-reuse 3x3 kernel: 4-D view with box {64, 8, 18, 1}; conv_try_vr switches a built launch over to it.
 int tmap_act_vr(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, int64_t sW, int64_t sH, int64_t sN);
 bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin);
+// Row-streaming 3x3 kernel (Cout = 64, W % 128 == 0): views with boxes {64, 128, 1, 1} and {64, 130, 1, 1}.
+bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin);
 
 // Host-side construction of a launch (api.cu / train.cu).  Return 0, -5 (shape not supported) or a tensor-map error.
 int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int in_c_stride, int in_c_off, int Cin, const __half* w,

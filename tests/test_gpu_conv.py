@@ -41,6 +41,12 @@ CASES = [
     (1, 64, 64, 256, 128, 3, 1, False, False),   # 256 -> 128, 4 K chunks
     (1, 128, 128, 64, 128, 3, 1, True, False),   # 64 -> 128 resident
     (7, 16, 8, 64, 64, 3, 1, True, True),        # a single 16x8 tile per image
+    # row-streaming kernel (3x3 s1, Cout 64, W%128==0): N=192 MMAs over a ring of TMEM slots (CVB_RS_MODE picks the staging)
+    (3, 128, 128, 64, 64, 3, 1, True, False),    # strips of 64 rows, one 128-pixel segment
+    (2, 256, 256, 128, 64, 3, 1, True, False),   # Cin 128 (up4.conv0): two K chunks, 144 KB of resident weights
+    (5, 64, 128, 64, 64, 3, 1, True, True),      # residual, one strip per image
+    (2, 48, 256, 64, 64, 3, 1, False, False),    # strips of 16 rows, two segments
+    (150, 16, 128, 64, 64, 3, 1, True, False),   # more strips than SMs, one 16-row strip each
 ]
 
 
