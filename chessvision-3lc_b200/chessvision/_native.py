@@ -67,6 +67,8 @@ SYMBOLS = {
     "cvb_train_step": (_I, [_P, _P, _P, _F, _P, _P]),
     "cvb_train_export": (_I, [_P, _I, C.POINTER(_Tensor), _I]),
     "cvb_wgrad3x3_f16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
+    "cvb_eval_metrics": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "cvb_quality_scores": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "cvb_launch_count": (C.c_int64, [_P]),
     "cvb_profile": (_I, [_P, _I]),
     "cvb_profile_read": (_I, [_P, C.POINTER(C.c_float), _I]),
@@ -346,6 +348,32 @@ class Engine:
         dw = torch.empty((cout, 9, cin), dtype=torch.float32, device=self.device)
         self._ck(self.lib.cvb_wgrad3x3_f16(self.h, _ptr(dz), _ptr(x), n, h, w, cout, cin, scale, _ptr(dw), _stream()), "cvb_wgrad3x3_f16")
         return dw
+
+    # ---- consumers of the outputs
+    def eval_metrics(self, probs, labels, labels_valid, true_labels, k=3, flip=False):
+        """probs f32[N,64,13], labels / labels_valid u8[N,64] (or None), true_labels u8[N,64] -> (topk_hits i32[N,k],
+        correct i32[N,2]) on the device."""
+        n = probs.shape[0]
+        assert probs.is_cuda and probs.dtype == torch.float32 and tuple(probs.shape[1:]) == (64, 13) and probs.is_contiguous()
+        assert true_labels.is_cuda and true_labels.dtype == torch.uint8 and tuple(true_labels.shape) == (n, 64) and true_labels.is_contiguous()
+        hits = torch.empty((n, k), dtype=torch.int32, device=self.device)
+        correct = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        self._ck(self.lib.cvb_eval_metrics(self.h, _ptr(probs), _ptr(labels), _ptr(labels_valid), _ptr(true_labels), n, int(flip), k,
+                                           _ptr(hits), _ptr(correct), _stream()), "cvb_eval_metrics")
+        return hits, correct
+
+    def quality_scores(self, values, quad=None, found=None):
+        """values f32[N,L] (logits), quad f32[N,4,2] or None, found u8[N] or None -> f64[N,4] =
+        (quadrangle_regularity, NaN, probability_distribution, probability_confidence)."""
+        n = values.shape[0]
+        v = values.reshape(n, -1)
+        assert v.is_cuda and v.dtype == torch.float32 and v.is_contiguous()
+        if quad is not None:
+            assert quad.is_cuda and quad.dtype == torch.float32 and quad.numel() == n * 8 and quad.is_contiguous()
+        scores = torch.empty((n, 4), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.cvb_quality_scores(self.h, _ptr(v), _ptr(quad), _ptr(found), n, v.shape[1], _ptr(scores), _stream()),
+                 "cvb_quality_scores")
+        return scores
 
     def launch_count(self) -> int:
         return int(self.lib.cvb_launch_count(self.h))

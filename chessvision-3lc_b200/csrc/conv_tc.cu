@@ -498,19 +498,87 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
 // carries on with the other slots.  Where the window wraps around the ring (2 of 8 rows) and on the very first K step
 // of a slot (accumulate = 0 for block dy = 0 only) the MMA is split into N = 64 / N = 128 pieces.
 // One CTA streams a strip of rs_rows output rows x 128 columns of one image; weights (9*Cin*64*2 B) stay resident.
-// rs_mode 0: one TMA box {64 ch, 128 px} per (row, dx).  rs_mode 1/2: one box {64 ch, 130 px} per row, horizontal tap
-// dx addressed 128*dx bytes further (descriptor base_offset 0 / (addr >> 7) & 7).
+// The MMA-issuing thread is the critical resource of this kernel (12 MMAs per row, each only 96 tensor-clocks long): the
+// TMEM runs and descriptor words of a row are computed once, the K loop is fully unrolled, and one elected thread runs
+// the whole role loop.  Two epilogue groups (warps 4-7 / 8-11) drain alternate output rows and write fp16 NHWC with
+// 256-bit global stores (one full 32-byte sector per lane and instruction), so the epilogue adds no shared-memory traffic.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kRsBarBytes = 512;
+constexpr int kRsThreads = 384;   // TMA warp, MMA warp, TMEM warp, one idle warp, two epilogue groups of four warps
 
-template <int EPI>
-__global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constant__ ConvParams p) {
-    constexpr int kBBytes = 64 * 128;
+// Contiguous runs of TMEM slots covered by column blocks dy in [lo, hi] of one input row (at most two: the ring wraps
+// after slot 7).  col = first TMEM column, boff = offset of the first block inside the resident N = 192 weight operand
+// (16-byte units), idesc = instruction descriptor with N = 64 * run length.
+struct RsRuns {
+    uint32_t col[2], boff[2], idesc[2];
+    int n;
+};
+__device__ __forceinline__ void rs_runs(uint32_t s_base, int lo, int hi, uint32_t idesc0, RsRuns& r) {
+    r.n = 0;
+    r.col[1] = r.boff[1] = r.idesc[1] = 0;
+    if (lo > hi) return;
+    const uint32_t s0 = (s_base + static_cast<uint32_t>(lo)) & 7u;
+    int n0 = hi - lo + 1;
+    const int room = 8 - static_cast<int>(s0);
+    const int n1 = n0 > room ? n0 - room : 0;
+    n0 -= n1;
+    r.col[0] = s0 * 64u;
+    r.boff[0] = static_cast<uint32_t>(lo) * (64u * 128u >> 4);
+    r.idesc[0] = idesc0 | (static_cast<uint32_t>(n0 * 8) << 17);
+    r.n = 1;
+    if (n1) {
+        r.col[1] = 0;
+        r.boff[1] = static_cast<uint32_t>(lo + n0) * (64u * 128u >> 4);
+        r.idesc[1] = idesc0 | (static_cast<uint32_t>(n1 * 8) << 17);
+        r.n = 2;
+    }
+}
+
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+// All K steps of one pipeline stage for an interior input row (its three column blocks land on slots s_base .. s_base+2
+// of the ring).  NA = slots before the ring wraps (3: no wrap; 2 or 1: the remaining 3 - NA blocks go to slot 0 on).
+// Straight-line code: every N and every operand offset is a compile-time constant.
+template <int NA, int NDX>
+__device__ __forceinline__ void rs_issue_row(uint32_t tmem_base, uint32_t s_base, uint64_t desc_hi, uint32_t a_lo, uint32_t b_lo,
+                                             uint32_t b_dx_stride, uint32_t idesc0, bool first) {
+    constexpr int NB = 3 - NA;
+    constexpr uint32_t kBlk = 64u * 128u >> 4;   // one 64-row weight block, 16-byte units
+    const uint32_t d_a = tmem_base + s_base * 64u;
+    const uint32_t i_a = idesc0 | (static_cast<uint32_t>(NA * 8) << 17);
+    const uint32_t i_b = idesc0 | (static_cast<uint32_t>(NB * 8) << 17);
+#pragma unroll
+    for (int dd = 0; dd < NDX; ++dd) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t a_desc = desc_hi | (a_lo + 8u * dd + 2u * k);
+            const uint32_t b_k = b_lo + dd * b_dx_stride + 2u * k;
+            if (dd == 0 && k == 0 && first) {
+                umma_f16(d_a, a_desc, desc_hi | b_k, idesc0 | (8u << 17), 0u);
+                if constexpr (NA > 1) umma_f16(d_a + 64u, a_desc, desc_hi | (b_k + kBlk), idesc0 | (static_cast<uint32_t>((NA - 1) * 8) << 17), 1u);
+            } else {
+                umma_f16(d_a, a_desc, desc_hi | b_k, i_a, 1u);
+            }
+            if constexpr (NB > 0) umma_f16(tmem_base, a_desc, desc_hi | (b_k + NA * kBlk), i_b, 1u);
+        }
+    }
+}
+
+// MODE 0: one TMA box {64 ch, 128 px} per (row, dx).  MODE 1: one box {64 ch, 130 px} per row, horizontal tap dx
+// addressed 128*dx bytes further (the 128-byte swizzle is a function of the shared-memory address, so a start address
+// that is a multiple of 128 B inside a 1024-byte group keeps the pattern the TMA wrote).
+template <int EPI, int MODE>
+__global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_constant__ ConvParams p) {
+    constexpr uint32_t kBBytes = 64 * 128;
+    constexpr uint32_t a_bytes = MODE == 0 ? 128u * 128u : 130u * 128u;   // bytes one TMA box delivers
+    constexpr uint32_t stage_bytes = MODE == 0 ? 16384u : 17408u;         // 1024-aligned stage pitch
+    constexpr int NDX = MODE == 0 ? 1 : 3;                                // horizontal taps served by one stage
     const int S = p.vr_stages;
     const int R = p.rs_rows;
-    const int mode = p.rs_mode;
-    const uint32_t a_bytes = mode == 0 ? 128u * 128u : 130u * 128u;   // bytes one TMA box delivers
-    const uint32_t stage_bytes = mode == 0 ? 16384u : 17408u;         // 1024-aligned stage pitch
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -518,22 +586,22 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constan
     uint8_t* base_ptr = smem_raw + (base_addr - raw_addr);
     const uint32_t w_bytes = 9u * p.c_chunks * kBBytes;
     const uint32_t stages_addr = base_addr + w_bytes;
-    uint8_t* s_out = base_ptr + w_bytes + S * stage_bytes;
-    const uint32_t out_bytes = EPI == EPI_OUTC ? 0u : static_cast<uint32_t>(p.out_bufs * kOutBufBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + out_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + w_bytes + S * stage_bytes);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * S;
     const uint32_t bar_tfull = bar_full + 16 * S;     // 8 slots
     const uint32_t bar_tempty = bar_tfull + 64;       // 8 slots
     const uint32_t bar_w = bar_tempty + 64;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 17);
+    float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kRsBarBytes);
+    float* s_outw = s_bias + 256;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.b_map);
-        tma_prefetch_desc(&p.a_map[mode == 0 ? 0 : 1]);
+        tma_prefetch_desc(&p.a_map[MODE == 0 ? 0 : 1]);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; ++i) {
@@ -542,12 +610,18 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constan
         }
         for (int i = 0; i < 8; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 128);
+            mbar_init(bar_tempty + 8 * i, 4);   // one arrival per epilogue warp of the group that drained the slot
         }
         mbar_init(bar_w, 1);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 3) {   // per-column constants (Cout = 64: one N tile)
+        for (int i = lane; i < 64; i += 32) {
+            s_bias[i] = __ldg(p.bias + i);
+            if constexpr (EPI == EPI_OUTC) s_outw[i] = __ldg(p.outc_w + i);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -555,7 +629,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constan
 
     const int strips_per_image = p.tiles_h * p.tiles_w;
     const int total_strips = p.tiles_n * strips_per_image;
-    const int loads_per_row = mode == 0 ? 3 * p.c_chunks : p.c_chunks;
+    const int loads_per_row = MODE == 0 ? 3 * p.c_chunks : p.c_chunks;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -566,33 +640,43 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constan
                     for (int dy = 0; dy < 3; ++dy)
                         tma_load_2d(base_addr + ((dxi * p.c_chunks + kc) * 3 + dy) * kBBytes, &p.b_map, bar_w,
                                     ((dy * 3 + dxi) * p.c_chunks + kc) * 64, 0);
-        }
-        __syncwarp();
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_strips; t += gridDim.x) {
-            const int w0 = (t % p.tiles_w) * 128;
-            const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
-            const int n0 = t / strips_per_image;
-            for (int j = -1; j <= R; ++j) {
-                for (int l = 0; l < loads_per_row; ++l) {
-                    const int kc = mode == 0 ? l / 3 : l;
-                    const int dxi = mode == 0 ? l - 3 * kc : 0;
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(bar_full + 8 * stage, a_bytes);
-                        tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[mode == 0 ? 0 : 1], bar_full + 8 * stage,
-                                    p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_strips; t += gridDim.x) {
+                const int w0 = (t % p.tiles_w) * 128;
+                const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
+                const int n0 = t / strips_per_image;
+                for (int j = -1; j <= R; ++j) {
+                    for (int l = 0; l < loads_per_row; ++l) {
+                        const int kc = MODE == 0 ? l / 3 : l;
+                        const int dxi = MODE == 0 ? l - 3 * kc : 0;
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        if (p.rs_debug & 4) {
+                            mbar_arrive(bar_full + 8 * stage);
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * stage, a_bytes);
+                            tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[MODE == 0 ? 0 : 1], bar_full + 8 * stage,
+                                        p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
+                        }
+                        if (++stage == S) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
+        // The role loop runs warp-uniformly (so descriptors and barrier addresses live in uniform registers) and only
+        // the tcgen05 instructions are predicated on the elected lane.  The issuing thread is the critical resource:
+        // the tensor pipe drains 12 queued MMAs in ~1150 clocks, so a row must not cost more than that to set up.
+        const bool leader = elect_one();
         mbar_wait(bar_w, 0);
         tc_fence_after();
         const uint32_t idesc0 = p.idesc & ~(0x3Fu << 17);
+        const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_sw128(0));
+        const uint32_t w_lo = desc_lo0 + ((base_addr & 0x3FFFFu) >> 4);
+        const uint32_t a_lo0 = desc_lo0 + ((stages_addr & 0x3FFFFu) >> 4);
+        const uint32_t b_dx_stride = static_cast<uint32_t>(p.c_chunks) * 3u * (kBBytes >> 4);   // one horizontal tap further
         int stage = 0;
         uint32_t phase = 0;
         uint32_t rho0 = 0;   // output rows this CTA has started before the current strip
@@ -603,37 +687,42 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constan
                 const int dy_hi = j + 1 < 2 ? j + 1 : 2;
                 const uint32_t rho_new = rho0 + static_cast<uint32_t>(j + 1);
                 const uint32_t s_base = (0u - rho_new) & 7u;   // slot of block dy = (s_base + dy) & 7
-                if (dy_lo == 0) {   // block 0 starts output row rho_new: its slot must have been drained
+                const bool interior = dy_lo == 0 && dy_hi == 2;
+                if (dy_lo == 0 && !(p.rs_debug & 8)) {   // block 0 starts output row rho_new: its slot must have been drained
                     mbar_wait(bar_tempty + 8 * s_base, ((rho_new >> 3) & 1u) ^ 1u);
                     tc_fence_after();
                 }
                 for (int l = 0; l < loads_per_row; ++l) {
-                    mbar_wait(bar_full + 8 * stage, phase);
+                    if (!(p.rs_debug & 8)) mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_addr = stages_addr + stage * stage_bytes;
-                        const int ndx = mode == 0 ? 1 : 3;
-                        for (int dd = 0; dd < ndx; ++dd) {
-                            const int kc = mode == 0 ? l / 3 : l;
-                            const int dxi = mode == 0 ? l - 3 * kc : dd;
-                            const uint32_t a_start = a_addr + (mode == 0 ? 0u : 128u * dd);
-                            uint64_t a_desc = umma_desc_sw128(a_start);
-                            if (mode == 2) a_desc |= static_cast<uint64_t>((a_start >> 7) & 7u) << 49;
-                            const uint64_t b_desc = umma_desc_sw128(base_addr + ((dxi * p.c_chunks + kc) * 3) * kBBytes);
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const bool first = l == 0 && dd == 0 && k == 0;   // first K step of this input row
-                                int dy = dy_lo;
-                                while (dy <= dy_hi) {
-                                    const uint32_t slot = (s_base + dy) & 7u;
-                                    const bool fresh = first && dy == 0;   // overwrite: first contribution to a new output row
-                                    int nb = 1;
-                                    if (!fresh) {
-                                        while (dy + nb <= dy_hi && slot + nb < 8u) ++nb;
+                    const int kc = MODE == 0 ? l / 3 : l;
+                    const int dx0 = MODE == 0 ? l - 3 * kc : 0;
+                    const uint32_t a_lo = a_lo0 + stage * (stage_bytes >> 4);
+                    const uint32_t b_lo = w_lo + static_cast<uint32_t>(kc * 3) * (kBBytes >> 4) + dx0 * b_dx_stride;
+                    const bool first = l == 0 && dy_lo == 0;   // overwrite block 0 on the first K step of a new output row
+                    if (leader) {
+                        if (interior) {
+                            if (s_base <= 5u) rs_issue_row<3, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                            else if (s_base == 6u) rs_issue_row<2, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                            else rs_issue_row<1, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                        } else {   // first / last two input rows of a strip: a partial window
+                            RsRuns all, rest;
+                            rs_runs(s_base, dy_lo, dy_hi, idesc0, all);
+                            rs_runs(s_base, 1, dy_hi, idesc0, rest);
+                            bool fresh = first;
+                            for (int dd = 0; dd < NDX; ++dd) {
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t a_desc = desc_hi | (a_lo + 8u * dd + 2u * k);
+                                    const uint32_t b_k = b_lo + dd * b_dx_stride + 2u * k;
+                                    if (fresh) {
+                                        umma_f16(tmem_base + s_base * 64u, a_desc, desc_hi | b_k, idesc0 | (8u << 17), 0u);
+                                        if (rest.n > 0) umma_f16(tmem_base + rest.col[0], a_desc, desc_hi | (b_k + rest.boff[0]), rest.idesc[0], 1u);
+                                        if (rest.n > 1) umma_f16(tmem_base + rest.col[1], a_desc, desc_hi | (b_k + rest.boff[1]), rest.idesc[1], 1u);
+                                        fresh = false;
+                                    } else {
+                                        umma_f16(tmem_base + all.col[0], a_desc, desc_hi | (b_k + all.boff[0]), all.idesc[0], 1u);
+                                        if (all.n > 1) umma_f16(tmem_base + all.col[1], a_desc, desc_hi | (b_k + all.boff[1]), all.idesc[1], 1u);
                                     }
-                                    umma_f16(tmem_base + slot * 64u, a_desc + 2 * k, b_desc + ((dy * kBBytes) >> 4) + 2 * k,
-                                             idesc0 | (static_cast<uint32_t>(nb * 8) << 17), fresh ? 0u : 1u);
-                                    dy += nb;
                                 }
                             }
                         }
@@ -641,36 +730,64 @@ __global__ void __launch_bounds__(256, 1) conv3x3_rs_kernel(const __grid_constan
                         // after the last K step of input row j, output row j - 1 is complete
                         if (l == loads_per_row - 1 && j >= 1) umma_commit(bar_tfull + 8 * ((s_base + 2u) & 7u));
                     }
-                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp >= 4) {
+        // two epilogue groups: group g drains the output rows with (rho & 1) == g, so two rows are in flight
+        const int group = (warp - 4) >> 2;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        float* s_bias = reinterpret_cast<float*>(s_out + out_bytes + kRsBarBytes);
-        float* s_outw = s_bias + 256;
-        int store_count = 0;
-        epilogue_consts<64, EPI>(p, 0, s_bias, s_outw, threadIdx.x - 128);
         uint32_t rho0 = 0;
         for (int t = blockIdx.x; t < total_strips; t += gridDim.x, rho0 += R) {
             const int w0 = (t % p.tiles_w) * 128;
             const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
             const int n = t / strips_per_image;
-            for (int r = 0; r < R; ++r) {
+            for (int r = static_cast<int>((rho0 ^ group) & 1u); r < R; r += 2) {
                 const uint32_t rho = rho0 + static_cast<uint32_t>(r);
                 const uint32_t slot = (0u - rho) & 7u;
-                mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
+                if (p.rs_debug & 16) {
+                    while (!mbar_try_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u)) __nanosleep(200);
+                } else {
+                    mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
+                }
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
-                epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, s_out,
-                                       stages_addr + S * stage_bytes, store_count, threadIdx.x - 128);
-                tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * slot);
+                if constexpr (EPI == EPI_OUTC) {
+                    int unused = 0;
+                    epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+                } else {
+                    if (p.rs_debug & 2) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+                        continue;
+                    }
+                    uint32_t va[32], vb[32], o[32];
+                    tmem_ld_32x32(taddr, va);
+                    tmem_ld_32x32(taddr + 32, vb);
+                    const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0 + row;
+                    const __half* res = (p.res != nullptr && n < p.N) ? p.res + pix * p.res_c_stride : nullptr;
+                    tmem_ld_wait(va);
+                    pack_chunk(va, s_bias, res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                    tmem_ld_wait(vb);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // the accumulator is in registers: release the slot early
+                    pack_chunk(vb, s_bias + 32, res ? res + 32 : nullptr, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                    if (n < p.N && !(p.rs_debug & 1)) {
+                        __half* dst = p.out + pix * p.out_c_stride + p.out_c_off;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) st_global_v8(dst + 16 * q, o + 8 * q);
+                    }
+                }
             }
         }
-        if (threadIdx.x == 128) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -891,8 +1008,10 @@ cudaError_t conv_configure() {
     if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
     if ((e = configure_vr<128, EPI_STORE, false>()) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_OUTC, true>()) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -930,7 +1049,7 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
 }
 
 // Decide whether the row-streaming kernel applies (3x3 s1, Cout = 64, rows of a multiple of 128 pixels) and size it.
-// CVB_NO_RS=1 disables it, CVB_RS_MODE=0|1|2 picks the activation staging (A/B measurements and tests).
+// CVB_NO_RS=1 disables it, CVB_RS_MODE=0|1 picks the activation staging (A/B measurements and tests); default 1.
 bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) {
     ConvParams& p = L.p;
     const char* off = getenv("CVB_NO_RS");
@@ -940,26 +1059,22 @@ bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     const int R = Ho % 64 == 0 ? 64 : (Ho % 32 == 0 ? 32 : (Ho % 16 == 0 ? 16 : 0));
     if (R == 0) return false;
     const char* m = getenv("CVB_RS_MODE");
-    const int mode = m ? atoi(m) : 0;
-    if (mode < 0 || mode > 2) return false;
+    const int mode = m ? atoi(m) : 1;
+    if (mode < 0 || mode > 1) return false;
     const int stage = mode == 0 ? 16384 : 17408;
     const int w_bytes = 9 * (Cin / 64) * 64 * 128;
-    int out_bufs = L.epilogue == EPI_OUTC ? 0 : 2;
     const int fixed = 1024 + kRsBarBytes + kEpiConstBytes;
-    int stages = (kVrMaxSmem - fixed - w_bytes - out_bufs * kOutBufBytes) / stage;
-    const int want = mode == 0 ? 6 : 3;
-    if (stages < want && out_bufs == 2) {
-        out_bufs = 1;
-        stages = (kVrMaxSmem - fixed - w_bytes - out_bufs * kOutBufBytes) / stage;
-    }
+    int stages = (kVrMaxSmem - fixed - w_bytes) / stage;
     if (stages > 8) stages = 8;
     if (stages < (mode == 0 ? 3 : 2)) return false;
     p.vr_stages = stages;
     p.w_stationary = 1;
     p.rs_rows = R;
     p.rs_mode = mode;
-    p.smem_bytes = w_bytes + stages * stage + out_bufs * kOutBufBytes + fixed;
-    p.out_bufs = out_bufs;
+    const char* dbg = getenv("CVB_RS_DEBUG");
+    p.rs_debug = dbg ? atoi(dbg) : 0;
+    p.smem_bytes = w_bytes + stages * stage + fixed;
+    p.out_bufs = 0;
     p.tn = 1; p.th = 1; p.tw = 128;
     p.tiles_w = Wo / 128;
     p.tiles_h = Ho / R;
@@ -982,8 +1097,13 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     if (total <= 0) return cudaSuccess;
     const int grid = (int)(total < sm_count ? total : sm_count);
     if (L.variant == 2) {
-        if (L.epilogue == EPI_OUTC) conv3x3_rs_kernel<EPI_OUTC><<<grid, 256, p.smem_bytes, stream>>>(p);
-        else conv3x3_rs_kernel<EPI_STORE><<<grid, 256, p.smem_bytes, stream>>>(p);
+        if (L.epilogue == EPI_OUTC) {
+            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_OUTC, 0><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            else conv3x3_rs_kernel<EPI_OUTC, 1><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+        } else {
+            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_STORE, 0><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            else conv3x3_rs_kernel<EPI_STORE, 1><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+        }
         return cudaGetLastError();
     }
     if (L.variant == 1) {

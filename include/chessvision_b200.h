@@ -148,6 +148,23 @@ CVB_API int cvb_train_export(cvb_ctx* ctx, int what, const cvb_tensor* out, int 
 CVB_API int cvb_wgrad3x3_f16(cvb_ctx* ctx, const void* dz, const void* x, int N, int H, int W, int Cout, int Cin, float scale,
                              float* dw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Consumers of the per-board outputs, computed on the device buffers the pipeline wrote.
+ * ------------------------------------------------------------------------------------------------------------------- */
+/* scripts/eval/evaluate.py:37-52,109-140 for N boards.  probs f32 [N,64,13]; labels / labels_valid u8 [N,64] (either may
+ * be NULL); true_labels u8 [N,64] = class index of the ground-truth FEN in FEN order a8..h1 (evaluate.py:61-86, 12 = empty);
+ * topk_hits i32 [N,k]: squares whose true class is among the i+1 most probable (compute_model_topk_accuracy * 64, ties
+ * ranked like np.argsort read from the end); correct i32 [N,2] (may be NULL): squares on which original_fen / fen agree
+ * with the truth (compute_position_accuracy.num_correct); flip = the orientation the labels were produced with. */
+CVB_API int cvb_eval_metrics(cvb_ctx* ctx, const float* probs, const uint8_t* labels, const uint8_t* labels_valid,
+                             const uint8_t* true_labels, int N, int flip, int k, int32_t* topk_hits, int32_t* correct, void* stream);
+/* scripts/process_new_raw/process_pipeline.py:357-378,416-467 for N boards.  values f32 [N,L] (the reference passes
+ * BoardExtractionResult.probabilities, L = 65536); quad f32 [N,4,2] (may be NULL) with found u8 [N] (may be NULL);
+ * scores f64 [N,4] = {quadrangle_regularity, NaN (mask_completeness is not computed), probability_distribution,
+ * probability_confidence}. */
+CVB_API int cvb_quality_scores(cvb_ctx* ctx, const float* values, const float* quad, const uint8_t* found, int N, int L,
+                               double* scores, void* stream);
+
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 CVB_API int64_t cvb_launch_count(const cvb_ctx* ctx);
 

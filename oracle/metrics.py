@@ -1,0 +1,112 @@
+"""ORACLE (test infrastructure, never on the product path): CPU restatement of the reference's per-board consumers of the
+image->FEN outputs — SURVEY.md §8(f) rows n1 and n4.
+
+n1  evaluation metrics        scripts/eval/evaluate.py:37-140,406-440 (``compute_position_accuracy``, ``board_to_labels``,
+                              ``compute_model_topk_accuracy``, ``get_label_indices``, ``get_validated_indices``)
+n4  extraction quality scores scripts/process_new_raw/process_pipeline.py:357-467 (``probability_distribution``,
+                              ``mask_completeness``, ``quadrangle_regularity``, ``probability_confidence``)
+
+python-chess (``chess==1.11.2``, not installed) is only used by the reference to parse the piece-placement field of a
+FEN; ``fen_to_labels`` restates that.  Pinned by ``tests/test_oracle_metrics.py``: the reference's own known answers
+(tests/test_metrics.py:16-174), the golden vectors ``tests/golden/metrics_vectors.npz`` written by
+``oracle/make_golden_metrics.py`` from the UNMODIFIED reference functions, and — where /root/reference exists — the live
+reference functions on random inputs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LABEL_NAMES = ["B", "K", "N", "P", "Q", "R", "b", "k", "n", "p", "q", "r", "f"]  # constants.py:23
+LABEL_INDICES = {s: i for i, s in enumerate(LABEL_NAMES)}
+
+
+def fen_to_labels(fen: str) -> list[str]:
+    """``board_to_labels(chess.BaseBoard(fen))`` (evaluate.py:61-86): 64 piece symbols in FEN order a8..h8, a7..h1,
+    "f" for an empty square.  Only the piece-placement field is read (anything after the first blank is ignored)."""
+    rows = fen.split()[0].split("/")
+    assert len(rows) == 8, f"expected 8 ranks in '{fen}'"
+    labels: list[str] = []
+    for row in rows:
+        n = 0
+        for ch in row:
+            if ch.isdigit():
+                labels.extend("f" * int(ch))
+                n += int(ch)
+            else:
+                assert ch in LABEL_INDICES and ch != "f", f"invalid piece '{ch}' in '{fen}'"
+                labels.append(ch)
+                n += 1
+        assert n == 8, f"rank '{row}' of '{fen}' does not have 8 squares"
+    return labels
+
+
+def fen_to_indices(fen: str) -> list[int]:
+    """``get_validated_indices`` (evaluate.py:430-440)."""
+    return [LABEL_INDICES[s] for s in fen_to_labels(fen)]
+
+
+def position_correct(predicted_fen: str, true_fen: str) -> int:
+    """``compute_position_accuracy(...).num_correct`` (evaluate.py:37-52): squares whose piece (or emptiness) agrees."""
+    return sum(a == b for a, b in zip(fen_to_labels(predicted_fen), fen_to_labels(true_fen)))
+
+
+def topk_hits(probabilities: np.ndarray, true_fen: str, k: int = 3) -> list[int]:
+    """``compute_model_topk_accuracy`` (evaluate.py:109-140) before the division by 64: hits[i] = squares whose true label
+    is among the i+1 most probable classes.  Ranking is ``np.argsort(axis=1)`` read from the end: for 13 elements numpy's
+    sort is a stable insertion sort, so among equal probabilities the HIGHER class index ranks first."""
+    true = fen_to_indices(true_fen)
+    hits = [0] * k
+    for sq in range(64):
+        order = sorted(range(probabilities.shape[1]), key=lambda c: (probabilities[sq, c], c))  # ascending, stable
+        for i in range(k):
+            if order[-(i + 1)] == true[sq]:
+                for j in range(i, k):
+                    hits[j] += 1
+                break
+    return hits
+
+
+def label_indices(probabilities: np.ndarray, true_fen: str) -> tuple[list[int], list[int]]:
+    """``get_label_indices`` (evaluate.py:406-427): first maximum wins."""
+    return np.argmax(probabilities, axis=1).tolist(), fen_to_indices(true_fen)
+
+
+# ------------------------------------------------------------------------------------------------------------ n4
+def probability_distribution(mask: np.ndarray) -> float:
+    """process_pipeline.py:357-378: 1 - entropy(10-bin histogram over [0,1]) / log2(10).  ``np.histogram`` semantics:
+    values outside [0,1] are dropped, the last bin is closed on the right, bin = floor(v * 10) computed in float64."""
+    v = np.asarray(mask, dtype=np.float64).ravel()
+    v = v[(v >= 0.0) & (v <= 1.0)]
+    b = np.minimum((v * 10.0).astype(np.int64), 9)
+    # np.histogram corrects the rare cases where v*10 rounds across a bin edge (edges are linspace(0,1,11))
+    edges = np.linspace(0.0, 1.0, 11)
+    b -= (v < edges[b]).astype(np.int64)
+    b += ((v >= edges[np.minimum(b + 1, 10)]) & (b != 9)).astype(np.int64)
+    hist = np.bincount(b, minlength=10).astype(np.float64)
+    hist = hist / np.sum(hist)
+    entropy = -np.sum(hist * np.log2(hist + 1e-10))
+    return float(1.0 - entropy / (-np.log2(1 / 10)))
+
+
+def probability_confidence(probabilities: np.ndarray) -> float:
+    """process_pipeline.py:459-467: mean |p - 0.5| * 2 over the top quarter of the values (largest p)."""
+    flat = np.asarray(probabilities).ravel()
+    k = int(flat.size * 0.25)
+    top = np.sort(flat)[-k:]
+    return float(np.mean(np.abs(top - 0.5)) * 2)
+
+
+def quadrangle_regularity(quadrangle: np.ndarray | None) -> float:
+    """process_pipeline.py:416-456: 1 - (cv(side lengths) + std(corner angles)/(pi/2)) / 2."""
+    if quadrangle is None:
+        return 0.0
+    q = np.asarray(quadrangle).copy().squeeze(1)
+    sides = [np.sqrt(((q[i] - q[(i + 1) % 4]) ** 2).sum()) for i in range(4)]
+    angles = []
+    for i in range(4):
+        v1, v2 = q[(i - 1) % 4] - q[i], q[(i + 1) % 4] - q[i]
+        norm = np.linalg.norm(v1) * np.linalg.norm(v2)
+        angles.append(np.arccos(np.dot(v1, v2) / norm) if norm > 0 else 0)
+    side_var = np.std(sides) / np.mean(sides) if np.mean(sides) > 0 else 1.0
+    angle_var = np.std(angles) / (np.pi / 2)
+    return float(1.0 - (side_var * 0.5 + angle_var * 0.5))
