@@ -242,6 +242,12 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             }
         }
     } else if (warp == 1) {
+        // warp-uniform role loop, tcgen05 instructions predicated on one lane elected once; descriptor words are
+        // base + stage * pitch (uniform registers), so a stage costs a handful of instructions besides its four MMAs
+        const bool leader = elect_one();
+        const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t a_lo0 = static_cast<uint32_t>(umma_desc_sw128(0)) + ((tiles_addr & 0x3FFFFu) >> 4);
+        const uint32_t idesc = p.idesc;
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
@@ -254,22 +260,20 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             for (int kb = 0; kb < k_steps; ++kb) {
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t a_addr = tiles_addr + stage * Cfg::kStageBytes;
-                    const uint64_t a_desc = umma_desc_sw128(a_addr);
-                    const uint64_t b_desc = umma_desc_sw128(a_addr + Cfg::kABytes);
+                if (leader) {
+                    const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
+                    const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+                    // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+                    umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, p.idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 1; k < 4; ++k) umma_f16(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, 1u);
                     umma_commit(bar_empty + 8 * stage);
                     if (kb == k_steps - 1) umma_commit(bar_tfull + 8 * acc);
                 }
-                __syncwarp();
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -407,10 +411,18 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             }
         }
     } else if (warp == 1) {
+        const bool leader = elect_one();   // warp-uniform loop, tcgen05 instructions predicated on one lane (see conv_tc_kernel)
         if (W_STAT) {
             mbar_wait(bar_w, 0);
             tc_fence_after();
         }
+        const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_sw128(0));
+        const uint32_t a_lo0 = desc_lo0 + ((stages_addr & 0x3FFFFu) >> 4);
+        const uint32_t w_lo0 = desc_lo0 + ((base_addr & 0x3FFFFu) >> 4);
+        // tap dy: the A tile 1024 B (one 8-row swizzle group) further, the weight tile 3*c_chunks (or 1) tiles further
+        const uint32_t b_step = (W_STAT ? 3u * p.c_chunks * kBBytes : static_cast<uint32_t>(kBBytes)) >> 4;
+        const uint32_t idesc = p.idesc;
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
@@ -424,27 +436,24 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
                 for (int dxi = 0; dxi < 3; ++dxi) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t a_addr = stages_addr + stage * kStageBytes;
-                        const uint64_t a_desc0 = umma_desc_sw128(a_addr);
-                        const uint64_t b_desc0 = umma_desc_sw128(W_STAT ? base_addr + (dxi * p.c_chunks + kc) * kBBytes : a_addr + kABytes);
-                        // tap dy: the A tile 1024 B (one 8-row swizzle group) further, the weight tile 3*c_chunks (or 1) tiles further
-                        const uint32_t b_step = (W_STAT ? 3u * p.c_chunks * kBBytes : static_cast<uint32_t>(kBBytes)) >> 4;
+                    if (leader) {
+                        const uint32_t a_lo = a_lo0 + stage * (kStageBytes >> 4);
+                        const uint32_t b_lo = W_STAT ? w_lo0 + (dxi * p.c_chunks + kc) * (kBBytes >> 4) : a_lo + (kABytes >> 4);
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                umma_f16(d_tmem, a_desc0 + dy * 64 + 2 * k, b_desc0 + dy * b_step + 2 * k, p.idesc,
+                                umma_f16(d_tmem, desc_hi | (a_lo + dy * 64 + 2 * k), desc_hi | (b_lo + dy * b_step + 2 * k), idesc,
                                          (kc | dxi | dy | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(bar_empty + 8 * stage);
                         if (kc == p.c_chunks - 1 && dxi == 2) umma_commit(bar_tfull + 8 * acc);
                     }
-                    __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp >= 4) {
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -568,6 +577,31 @@ __device__ __forceinline__ void rs_issue_row(uint32_t tmem_base, uint32_t s_base
     }
 }
 
+// Same for the first / last two input rows of a strip, whose window is partial (4 of rs_rows + 2 rows: kept out of line
+// so that its bookkeeping is not hoisted into the hot loop).
+template <int NDX>
+__device__ __noinline__ void rs_issue_partial(uint32_t tmem_base, uint32_t s_base, int dy_lo, int dy_hi, uint64_t desc_hi, uint32_t a_lo,
+                                              uint32_t b_lo, uint32_t b_dx_stride, uint32_t idesc0, bool fresh) {
+    RsRuns all, rest;
+    rs_runs(s_base, dy_lo, dy_hi, idesc0, all);
+    rs_runs(s_base, 1, dy_hi, idesc0, rest);
+    for (int dd = 0; dd < NDX; ++dd) {
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t a_desc = desc_hi | (a_lo + 8u * dd + 2u * k);
+            const uint32_t b_k = b_lo + dd * b_dx_stride + 2u * k;
+            if (fresh) {
+                umma_f16(tmem_base + s_base * 64u, a_desc, desc_hi | b_k, idesc0 | (8u << 17), 0u);
+                if (rest.n > 0) umma_f16(tmem_base + rest.col[0], a_desc, desc_hi | (b_k + rest.boff[0]), rest.idesc[0], 1u);
+                if (rest.n > 1) umma_f16(tmem_base + rest.col[1], a_desc, desc_hi | (b_k + rest.boff[1]), rest.idesc[1], 1u);
+                fresh = false;
+            } else {
+                umma_f16(tmem_base + all.col[0], a_desc, desc_hi | (b_k + all.boff[0]), all.idesc[0], 1u);
+                if (all.n > 1) umma_f16(tmem_base + all.col[1], a_desc, desc_hi | (b_k + all.boff[1]), all.idesc[1], 1u);
+            }
+        }
+    }
+}
+
 // MODE 0: one TMA box {64 ch, 128 px} per (row, dx).  MODE 1: one box {64 ch, 130 px} per row, horizontal tap dx
 // addressed 128*dx bytes further (the 128-byte swizzle is a function of the shared-memory address, so a start address
 // that is a multiple of 128 B inside a 1024-byte group keeps the pattern the TMA wrote).
@@ -651,13 +685,9 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                         const int kc = MODE == 0 ? l / 3 : l;
                         const int dxi = MODE == 0 ? l - 3 * kc : 0;
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        if (p.rs_debug & 4) {
-                            mbar_arrive(bar_full + 8 * stage);
-                        } else {
-                            mbar_expect_tx(bar_full + 8 * stage, a_bytes);
-                            tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[MODE == 0 ? 0 : 1], bar_full + 8 * stage,
-                                        p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
-                        }
+                        mbar_expect_tx(bar_full + 8 * stage, a_bytes);
+                        tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[MODE == 0 ? 0 : 1], bar_full + 8 * stage,
+                                    p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -688,12 +718,12 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                 const uint32_t rho_new = rho0 + static_cast<uint32_t>(j + 1);
                 const uint32_t s_base = (0u - rho_new) & 7u;   // slot of block dy = (s_base + dy) & 7
                 const bool interior = dy_lo == 0 && dy_hi == 2;
-                if (dy_lo == 0 && !(p.rs_debug & 8)) {   // block 0 starts output row rho_new: its slot must have been drained
+                if (dy_lo == 0) {   // block 0 starts output row rho_new: its slot must have been drained
                     mbar_wait(bar_tempty + 8 * s_base, ((rho_new >> 3) & 1u) ^ 1u);
                     tc_fence_after();
                 }
                 for (int l = 0; l < loads_per_row; ++l) {
-                    if (!(p.rs_debug & 8)) mbar_wait(bar_full + 8 * stage, phase);
+                    mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     const int kc = MODE == 0 ? l / 3 : l;
                     const int dx0 = MODE == 0 ? l - 3 * kc : 0;
@@ -706,25 +736,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                             else if (s_base == 6u) rs_issue_row<2, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
                             else rs_issue_row<1, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
                         } else {   // first / last two input rows of a strip: a partial window
-                            RsRuns all, rest;
-                            rs_runs(s_base, dy_lo, dy_hi, idesc0, all);
-                            rs_runs(s_base, 1, dy_hi, idesc0, rest);
-                            bool fresh = first;
-                            for (int dd = 0; dd < NDX; ++dd) {
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t a_desc = desc_hi | (a_lo + 8u * dd + 2u * k);
-                                    const uint32_t b_k = b_lo + dd * b_dx_stride + 2u * k;
-                                    if (fresh) {
-                                        umma_f16(tmem_base + s_base * 64u, a_desc, desc_hi | b_k, idesc0 | (8u << 17), 0u);
-                                        if (rest.n > 0) umma_f16(tmem_base + rest.col[0], a_desc, desc_hi | (b_k + rest.boff[0]), rest.idesc[0], 1u);
-                                        if (rest.n > 1) umma_f16(tmem_base + rest.col[1], a_desc, desc_hi | (b_k + rest.boff[1]), rest.idesc[1], 1u);
-                                        fresh = false;
-                                    } else {
-                                        umma_f16(tmem_base + all.col[0], a_desc, desc_hi | (b_k + all.boff[0]), all.idesc[0], 1u);
-                                        if (all.n > 1) umma_f16(tmem_base + all.col[1], a_desc, desc_hi | (b_k + all.boff[1]), all.idesc[1], 1u);
-                                    }
-                                }
-                            }
+                            rs_issue_partial<NDX>(tmem_base, s_base, dy_lo, dy_hi, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
                         }
                         umma_commit(bar_empty + 8 * stage);
                         // after the last K step of input row j, output row j - 1 is complete
@@ -748,11 +760,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
             for (int r = static_cast<int>((rho0 ^ group) & 1u); r < R; r += 2) {
                 const uint32_t rho = rho0 + static_cast<uint32_t>(r);
                 const uint32_t slot = (0u - rho) & 7u;
-                if (p.rs_debug & 16) {
-                    while (!mbar_try_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u)) __nanosleep(200);
-                } else {
-                    mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
-                }
+                mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
                 if constexpr (EPI == EPI_OUTC) {
@@ -762,12 +770,6 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
                 } else {
-                    if (p.rs_debug & 2) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
-                        continue;
-                    }
                     uint32_t va[32], vb[32], o[32];
                     tmem_ld_32x32(taddr, va);
                     tmem_ld_32x32(taddr + 32, vb);
@@ -780,7 +782,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // the accumulator is in registers: release the slot early
                     pack_chunk(vb, s_bias + 32, res ? res + 32 : nullptr, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
-                    if (n < p.N && !(p.rs_debug & 1)) {
+                    if (n < p.N) {
                         __half* dst = p.out + pix * p.out_c_stride + p.out_c_off;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) st_global_v8(dst + 16 * q, o + 8 * q);
@@ -1071,8 +1073,6 @@ bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     p.w_stationary = 1;
     p.rs_rows = R;
     p.rs_mode = mode;
-    const char* dbg = getenv("CVB_RS_DEBUG");
-    p.rs_debug = dbg ? atoi(dbg) : 0;
     p.smem_bytes = w_bytes + stages * stage + fixed;
     p.out_bufs = 0;
     p.tn = 1; p.th = 1; p.tw = 128;

@@ -37,7 +37,6 @@ struct alignas(64) ConvParams {
     int smem_bytes;
     int rs_rows;        // row-streaming variant: output rows per strip
     int rs_mode;        // ... activation staging: 0 = one box per (row, dx), 1 = one 130-pixel box per row
-    int rs_debug;       // CVB_RS_DEBUG bit mask for timing experiments (results invalid): 1 no stores, 2 no TMEM loads, 4 no TMA loads
     // epilogue
     int relu;
     const float* bias;      // [Cout_total]

@@ -52,8 +52,11 @@ def position_correct(predicted_fen: str, true_fen: str) -> int:
 
 def topk_hits(probabilities: np.ndarray, true_fen: str, k: int = 3) -> list[int]:
     """``compute_model_topk_accuracy`` (evaluate.py:109-140) before the division by 64: hits[i] = squares whose true label
-    is among the i+1 most probable classes.  Ranking is ``np.argsort(axis=1)`` read from the end: for 13 elements numpy's
-    sort is a stable insertion sort, so among equal probabilities the HIGHER class index ranks first."""
+    is among the i+1 most probable classes.  Ranking is ``np.argsort(axis=1)`` read from the end.  Among EQUAL
+    probabilities the reference's order is numpy-implementation-defined (its default quicksort is vectorised per CPU
+    and not stable: [probe] numpy 2.3 on this container's AVX-512 cores does not return the stable order), so ties are
+    unpinned; here and in the CUDA kernel they are defined as the stable ascending order read from the end, i.e. the
+    HIGHER class index ranks first."""
     true = fen_to_indices(true_fen)
     hits = [0] * k
     for sq in range(64):
@@ -73,19 +76,13 @@ def label_indices(probabilities: np.ndarray, true_fen: str) -> tuple[list[int], 
 
 # ------------------------------------------------------------------------------------------------------------ n4
 def probability_distribution(mask: np.ndarray) -> float:
-    """process_pipeline.py:357-378: 1 - entropy(10-bin histogram over [0,1]) / log2(10).  ``np.histogram`` semantics:
-    values outside [0,1] are dropped, the last bin is closed on the right, bin = floor(v * 10) computed in float64."""
-    v = np.asarray(mask, dtype=np.float64).ravel()
-    v = v[(v >= 0.0) & (v <= 1.0)]
-    b = np.minimum((v * 10.0).astype(np.int64), 9)
-    # np.histogram corrects the rare cases where v*10 rounds across a bin edge (edges are linspace(0,1,11))
-    edges = np.linspace(0.0, 1.0, 11)
-    b -= (v < edges[b]).astype(np.int64)
-    b += ((v >= edges[np.minimum(b + 1, 10)]) & (b != 9)).astype(np.int64)
-    hist = np.bincount(b, minlength=10).astype(np.float64)
+    """process_pipeline.py:357-378: 1 - entropy(10-bin histogram over [0,1]) / log2(10).  ``np.histogram`` keeps the
+    input dtype: for float32 input the bin index is int(v * 10) in float32, corrected against the float32 edges
+    ``linspace(0, 1, 11)``; values outside [0,1] are dropped and the last bin is closed on the right."""
+    hist, _ = np.histogram(np.asarray(mask).flatten(), bins=10, range=(0, 1))
     hist = hist / np.sum(hist)
     entropy = -np.sum(hist * np.log2(hist + 1e-10))
-    return float(1.0 - entropy / (-np.log2(1 / 10)))
+    return float(1.0 - (entropy / -np.log2(1 / 10)))
 
 
 def probability_confidence(probabilities: np.ndarray) -> float:

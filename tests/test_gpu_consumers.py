@@ -1,0 +1,88 @@
+"""GPU parity of the output consumers (csrc/consumers.cu; SURVEY.md §8(f) n1 evaluation metrics, n4 quality scores)
+against ``oracle/metrics.py`` and the golden vectors frozen from the unmodified reference functions
+(``tests/golden/metrics_vectors.npz``).  Integer results bit-exact; floating-point scores within the stated tolerance."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import metrics as om
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vec():
+    return np.load(GOLDEN / "metrics_vectors.npz")
+
+
+def _truth(fens):
+    return torch.tensor([om.fen_to_indices(str(f)) for f in fens], dtype=torch.uint8).cuda()
+
+
+def test_topk_and_position_accuracy_golden(engine, vec):
+    probs = torch.from_numpy(vec["probs"]).cuda()
+    pred = _truth(vec["pred_fens"])
+    hits, correct = engine.eval_metrics(probs, pred, pred, _truth(vec["fens"]), k=5)
+    assert np.array_equal(hits.cpu().numpy(), vec["topk_hits"])
+    assert np.array_equal(correct.cpu().numpy()[:, 0], vec["correct"]) and np.array_equal(correct.cpu().numpy()[:, 1], vec["correct"])
+
+
+def test_topk_ties_and_flip_against_the_oracle(engine):
+    rng = np.random.default_rng(3)
+    fens = ["rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR", "8/8/8/8/8/8/8/8", "2b3k1/pp3pp1/8/1n1p3p/1b1P1B1P/1P3PP1/P4KN1/3B4"]
+    probs = np.round(rng.dirichlet(np.ones(13), size=(3, 64)) * 6).astype(np.float32) / 6    # many exact ties
+    labels = rng.integers(0, 13, (3, 64)).astype(np.uint8)
+    for flip in (False, True):
+        hits, correct = engine.eval_metrics(torch.from_numpy(probs).cuda(), torch.from_numpy(labels).cuda(), None, _truth(fens), k=13, flip=flip)
+        for i, fen in enumerate(fens):
+            assert hits[i].cpu().tolist() == om.topk_hits(probs[i], fen, 13)
+            true = om.fen_to_indices(fen)
+            seen = labels[i][::-1] if flip else labels[i]
+            assert int(correct[i, 0]) == int(sum(int(a) == b for a, b in zip(seen, true))) and int(correct[i, 1]) == 0
+
+
+def test_reference_known_answers_through_the_python_mirror(engine):
+    """reference tests/test_metrics.py:49-105 through chessvision.evaluation (same names as scripts/eval/evaluate.py)."""
+    from chessvision import constants, evaluation as ev
+    LI = {s: i for i, s in enumerate(constants.LABEL_NAMES)}
+    p = np.zeros((64, 13), np.float32)
+    p[:32, LI["f"]] = 1.0
+    p[32:48, LI["p"]], p[32:48, LI["f"]] = 1.0, 0.9
+    p[48:, LI["P"]], p[48:, LI["p"]], p[48:, LI["f"]] = 1.0, 0.9, 0.8
+    r = ev.compute_model_topk_accuracy(p, "8/8/8/8/8/8/8/8", k=3)
+    assert isinstance(r, ev.TopKAccuracyResult) and r.k == 3 and len(r.accuracies) == 3
+    assert (r.top_1, r.top_2, r.top_3) == (0.5, 0.75, 1.0)
+    r1 = ev.compute_model_topk_accuracy(p, "8/8/8/8/8/8/8/8", k=1)
+    assert r1.top_1 == 0.5 and r1.top_2 == 0.0
+    acc = ev.compute_position_accuracy("8/8/8/8/4Q3/8/8/8", "8/8/8/8/4q3/8/8/8")
+    assert acc.num_correct == 63 and acc.accuracy == 63 / 64 and acc.total_squares == 64
+    assert ev.board_to_labels("8/8/8/8/4Q3/8/8/8")[36] == "Q"
+
+
+def test_quality_scores_golden(engine, vec):
+    arrays = torch.from_numpy(vec["arrays"]).cuda()
+    scores = engine.quality_scores(arrays).cpu().numpy()
+    # histogram counts are exact, the entropy is evaluated in float64 on both sides: 1e-12; the confidence is a float32
+    # pairwise sum in numpy and a float64 sum here: 2e-6 relative
+    assert np.allclose(scores[:, 2], vec["distribution"], rtol=0, atol=1e-12), (scores[:, 2], vec["distribution"])
+    assert np.allclose(scores[:, 3], vec["confidence"], rtol=2e-6, atol=0), (scores[:, 3], vec["confidence"])
+    assert np.isnan(scores[:, 1]).all()
+    quads = torch.from_numpy(vec["quads"].reshape(-1, 4, 2)).cuda()
+    dummy = torch.zeros((quads.shape[0], 16), dtype=torch.float32, device="cuda")
+    reg = engine.quality_scores(dummy, quads).cpu().numpy()[:, 0]
+    want = vec["regularity"]
+    ok = np.isclose(reg, want, rtol=0, atol=2e-6) | (np.isnan(reg) & np.isnan(want))   # float32 arithmetic, acosf within 2 ulp
+    assert ok.all(), (reg, want)
+
+
+def test_quality_scores_on_pipeline_logits(engine):
+    """The shape the reference feeds (process_pipeline.py:288-291): the 256x256 logits of real boards."""
+    rng = np.random.default_rng(8)
+    logits = (rng.normal(size=(5, 256, 256)) * 6).astype(np.float32)
+    logits[1] = np.clip(logits[1], 0, 1)            # everything inside the histogram range, many values on 0 and 1
+    logits[2, :128] = 0.5                           # a large tie group straddling the top-quarter threshold
+    scores = engine.quality_scores(torch.from_numpy(logits).cuda()).cpu().numpy()
+    for i in range(5):
+        assert abs(scores[i, 2] - om.probability_distribution(logits[i])) <= 1e-12
+        assert abs(scores[i, 3] - om.probability_confidence(logits[i])) <= 2e-6 * abs(scores[i, 3])

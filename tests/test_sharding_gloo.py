@@ -66,7 +66,7 @@ def test_sharded_equals_unsharded_gloo(world, n):
     procs = [ctx.Process(target=worker, args=(r, world, port, n, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=120) for _ in range(world)]
+    results = [q.get(timeout=300) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
