@@ -38,8 +38,21 @@ struct ConvCfg {
 
 constexpr int kOutBufBytes = 128 * 128;   // one staged store group: 128 pixels x 64 channels fp16
 
-// 32 accumulator columns of one pixel -> bias (+ residual) (+ ReLU) -> 16 packed fp16 pairs.
-__device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float* s_bias, const __half* res, bool relu, uint32_t (&o)[16]) {
+// 64 channels (128 B) of one pixel of the residual tensor -> 32 registers, as four 256-bit loads (every request moves whole
+// 32-byte sectors).  Issued well before the accumulator is ready so that the L2 latency is off the epilogue's critical path.
+__device__ __forceinline__ void res_load64(const __half* res, uint32_t (&r)[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[8 * i]), "=r"(r[8 * i + 1]), "=r"(r[8 * i + 2]), "=r"(r[8 * i + 3]), "=r"(r[8 * i + 4]), "=r"(r[8 * i + 5]),
+                       "=r"(r[8 * i + 6]), "=r"(r[8 * i + 7])
+                     : "l"(res + 16 * i));
+}
+
+// 32 accumulator columns of one pixel -> bias (+ residual: 16 preloaded fp16 pairs) (+ ReLU) -> 16 packed fp16 pairs.
+template <int RES_OFF>
+__device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float* s_bias, const uint32_t (&res)[32], bool has_res, bool relu,
+                                           uint32_t (&o)[16]) {
     const float4* b4 = reinterpret_cast<const float4*>(s_bias);
     float f[32];
 #pragma unroll
@@ -50,18 +63,13 @@ __device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float*
         f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b.z;
         f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b.w;
     }
-    if (res != nullptr) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(res);
+    if (has_res) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint4 r = __ldg(r4 + i);
-            const __half2* rh2 = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 rf = __half22float2(rh2[j]);
-                f[8 * i + 2 * j] += rf.x;
-                f[8 * i + 2 * j + 1] += rf.y;
-            }
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t rj = res[RES_OFF + j];
+            const float2 rf = __half22float2(*reinterpret_cast<const __half2*>(&rj));
+            f[2 * j] += rf.x;
+            f[2 * j + 1] += rf.y;
         }
     }
 #pragma unroll
@@ -80,7 +88,7 @@ __device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float*
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int row, int n0, int h0, int w0, int n, int h, int w,
                                               bool valid, int n_tile, const float* s_bias, const float* s_outw, uint8_t* s_out,
-                                              uint32_t s_out_addr, int& store_count, int etid) {
+                                              uint32_t s_out_addr, int& store_count, int etid, const uint32_t (&res0)[32]) {
     constexpr int NC = BLOCK_N / 32;
     const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
     uint32_t va[32], vb[32];
@@ -119,17 +127,28 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
         }
     } else {
         const bool relu = p.relu != 0;
+        const bool has_res = EPI == EPI_STORE && p.res != nullptr && valid;
+        const __half* res_px = has_res ? p.res + pix * p.res_c_stride + n_tile * BLOCK_N : nullptr;
+        uint32_t rcur[32], rnext[32];
+        if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rcur[i] = res0[i];
+        }
 #pragma unroll
         for (int c = 0; c < NC; c += 2) {
             const int col0 = n_tile * BLOCK_N + c * 32;   // first of the 64 columns of this store group
-            const __half* res = (EPI == EPI_STORE && p.res != nullptr && valid) ? p.res + pix * p.res_c_stride + col0 : nullptr;
+            if (c + 2 < NC && has_res) res_load64(res_px + (c + 2) * 32, rnext);   // one group ahead
             uint32_t o[32];
             tmem_ld_wait(va);
             tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-            pack_chunk(va, s_bias + c * 32, res, relu, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+            pack_chunk<0>(va, s_bias + c * 32, rcur, has_res, relu, reinterpret_cast<uint32_t(&)[16]>(o[0]));
             tmem_ld_wait(vb);
             if (c + 2 < NC) tmem_ld_32x32(taddr + (c + 2) * 32, va);
-            pack_chunk(vb, s_bias + c * 32 + 32, res ? res + 32 : nullptr, relu, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+            pack_chunk<16>(vb, s_bias + c * 32 + 32, rcur, has_res, relu, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+            if (c + 2 < NC && has_res) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) rcur[i] = rnext[i];
+            }
             // staging buffer: free once the store issued `out_bufs` groups ago has read it
             const int buf = p.out_bufs == 2 ? (store_count & 1) : 0;
             if (etid == 0) {
@@ -297,11 +316,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             const int h = ((m_tile / p.tiles_w) % p.tiles_h) * p.th + rh;
             const int n = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn + rn;
             const bool valid = n < p.N;
+            uint32_t res0[32];   // first 64 residual channels of this pixel, requested before the accumulator is waited for
+            if (EPI == EPI_STORE && p.res != nullptr && valid)
+                res_load64(p.res + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.res_c_stride + n_tile * BLOCK_N, res0);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
             epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n - rn, h - rh, w - rw, n, h, w, valid, n_tile, s_bias, s_outw, s_out,
-                                        tiles_addr + S * Cfg::kStageBytes, store_count, threadIdx.x - 128);
+                                        tiles_addr + S * Cfg::kStageBytes, store_count, threadIdx.x - 128, res0);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
@@ -474,11 +496,14 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             const int w = (m_tile % p.tiles_w) * 8 + rw;
             const int h = ((m_tile / p.tiles_w) % p.tiles_h) * 16 + rh;
             const int n = m_tile / (p.tiles_w * p.tiles_h);
+            uint32_t res0[32];
+            if (EPI == EPI_STORE && p.res != nullptr && n < p.N)
+                res_load64(p.res + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.res_c_stride + n_tile * BLOCK_N, res0);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
             epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n, h - rh, w - rw, n, h, w, n < p.N, n_tile, s_bias, s_outw, s_out,
-                                        stages_addr + S * kStageBytes, store_count, threadIdx.x - 128);
+                                        stages_addr + S * kStageBytes, store_count, threadIdx.x - 128, res0);
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * acc);
         }
@@ -760,12 +785,16 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
             for (int r = static_cast<int>((rho0 ^ group) & 1u); r < R; r += 2) {
                 const uint32_t rho = rho0 + static_cast<uint32_t>(r);
                 const uint32_t slot = (0u - rho) & 7u;
+                const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0 + row;
+                const bool has_res = EPI == EPI_STORE && p.res != nullptr && n < p.N;
+                uint32_t res0[32];
+                if (has_res) res_load64(p.res + pix * p.res_c_stride, res0);
                 mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
                 if constexpr (EPI == EPI_OUTC) {
                     int unused = 0;
-                    epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0);
+                    epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res0);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
@@ -773,15 +802,13 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                     uint32_t va[32], vb[32], o[32];
                     tmem_ld_32x32(taddr, va);
                     tmem_ld_32x32(taddr + 32, vb);
-                    const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0 + row;
-                    const __half* res = (p.res != nullptr && n < p.N) ? p.res + pix * p.res_c_stride : nullptr;
                     tmem_ld_wait(va);
-                    pack_chunk(va, s_bias, res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                    pack_chunk<0>(va, s_bias, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
                     tmem_ld_wait(vb);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // the accumulator is in registers: release the slot early
-                    pack_chunk(vb, s_bias + 32, res ? res + 32 : nullptr, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                    pack_chunk<16>(vb, s_bias + 32, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
                     if (n < p.N) {
                         __half* dst = p.out + pix * p.out_c_stride + p.out_c_off;
 #pragma unroll
