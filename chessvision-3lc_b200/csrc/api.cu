@@ -203,7 +203,10 @@ int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logi
         else CK(aux(launch_unet_stem_tc(img, ctx->stem_wsw, ctx->stem_b, &ctx->stem_omap, n, ctx->sm_count, s)));
     }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[0], n, s)) return -2; }                       // inc.3      t0 -> cat0[0:64)
-    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat0, ctx->p1, n, 256, 256, 64, 128, s))); }
+    if (P[0].p.pool_out == nullptr) {   // the row-streaming kernel pools in its epilogue (conv_try_rs), the others do not
+        StageTimer t(ctx, 1, s);
+        CK(aux(launch_maxpool2(ctx->cat0, ctx->p1, n, 256, 256, 64, 128, s)));
+    }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[1], n, s) || run_conv(ctx, P[2], n, s)) return -2; }   // down1
     { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat1, ctx->p2, n, 128, 128, 128, 256, s))); }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[3], n, s) || run_conv(ctx, P[4], n, s)) return -2; }   // down2
@@ -459,6 +462,10 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     int rc = 0;
     // encoder
     rc |= build_conv(ctx, P[0], ctx->t0, B, 256, 256, 64, 0, 64, W[0], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[0], ctx->cat0, 128, 0, 1, nullptr, 0);
+    if (P[0].variant == 2 && getenv("CVB_NO_POOL_FUSE") == nullptr) {   // row-streaming kernel: MaxPool2d(2) of inc's output fused into its epilogue
+        P[0].p.pool_out = ctx->p1;
+        P[0].p.pool_c_stride = 64;
+    }
     rc |= build_conv(ctx, P[1], ctx->p1, B, 128, 128, 64, 0, 64, W[1], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[1], ctx->t1, 128, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[2], ctx->t1, B, 128, 128, 128, 0, 128, W[2], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[2], ctx->cat1, 256, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[3], ctx->p2, B, 64, 64, 128, 0, 128, W[3], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[3], ctx->t2, 256, 0, 1, nullptr, 0);

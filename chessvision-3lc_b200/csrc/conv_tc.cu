@@ -773,7 +773,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // two epilogue groups: group g drains the output rows with (rho & 1) == g, so two rows are in flight
+        // two epilogue groups: group g drains the output row PAIRS with ((rho >> 1) & 1) == g, so two rows are in flight
+        // and a thread sees both rows of a 2x2 max-pool window (the fused MaxPool2d of unet_parts.py:34)
         const int group = (warp - 4) >> 2;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
@@ -782,37 +783,64 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
             const int w0 = (t % p.tiles_w) * 128;
             const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
             const int n = t / strips_per_image;
-            for (int r = static_cast<int>((rho0 ^ group) & 1u); r < R; r += 2) {
-                const uint32_t rho = rho0 + static_cast<uint32_t>(r);
-                const uint32_t slot = (0u - rho) & 7u;
-                const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0 + row;
-                const bool has_res = EPI == EPI_STORE && p.res != nullptr && n < p.N;
-                uint32_t res0[32];
-                if (has_res) res_load64(p.res + pix * p.res_c_stride, res0);
-                mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
-                if constexpr (EPI == EPI_OUTC) {
-                    int unused = 0;
-                    epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res0);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
-                } else {
-                    uint32_t va[32], vb[32], o[32];
-                    tmem_ld_32x32(taddr, va);
-                    tmem_ld_32x32(taddr + 32, vb);
-                    tmem_ld_wait(va);
-                    pack_chunk<0>(va, s_bias, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
-                    tmem_ld_wait(vb);
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // the accumulator is in registers: release the slot early
-                    pack_chunk<16>(vb, s_bias + 32, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
-                    if (n < p.N) {
-                        __half* dst = p.out + pix * p.out_c_stride + p.out_c_off;
+            for (int r2 = 2 * group; r2 < R; r2 += 4) {
+                uint32_t o_prev[32];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) st_global_v8(dst + 16 * q, o + 8 * q);
+                for (int half = 0; half < 2; ++half) {
+                    const int r = r2 + half;
+                    const uint32_t rho = rho0 + static_cast<uint32_t>(r);
+                    const uint32_t slot = (0u - rho) & 7u;
+                    const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0 + row;
+                    const bool has_res = EPI == EPI_STORE && p.res != nullptr && n < p.N;
+                    uint32_t res0[32];
+                    if (has_res) res_load64(p.res + pix * p.res_c_stride, res0);
+                    mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
+                    if constexpr (EPI == EPI_OUTC) {
+                        int unused = 0;
+                        epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res0);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
+                    } else {
+                        uint32_t va[32], vb[32], o[32];
+                        tmem_ld_32x32(taddr, va);
+                        tmem_ld_32x32(taddr + 32, vb);
+                        tmem_ld_wait(va);
+                        pack_chunk<0>(va, s_bias, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                        tmem_ld_wait(vb);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // the accumulator is in registers: release the slot early
+                        pack_chunk<16>(vb, s_bias + 32, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                        if (n < p.N) {
+                            __half* dst = p.out + pix * p.out_c_stride + p.out_c_off;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) st_global_v8(dst + 16 * q, o + 8 * q);
+                        }
+                        if (p.pool_out != nullptr) {
+                            if (half == 0) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) o_prev[i] = o[i];
+                            } else {
+                                // vertical max with the row above, horizontal max with the neighbouring pixel (lane ^ 1)
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&o[i]), *reinterpret_cast<const __half2*>(&o_prev[i]));
+                                    uint32_t mu = *reinterpret_cast<const uint32_t*>(&m);
+                                    const uint32_t nb = __shfl_xor_sync(0xffffffffu, mu, 1);
+                                    const __half2 mm = __hmax2(m, *reinterpret_cast<const __half2*>(&nb));
+                                    o[i] = *reinterpret_cast<const uint32_t*>(&mm);
+                                }
+                                if (n < p.N && (lane & 1) == 0) {
+                                    const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + ((h0 + r) >> 1)) * (p.W >> 1) + ((w0 + row) >> 1);
+                                    __half* pdst = p.pool_out + ppix * p.pool_c_stride;
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) st_global_v8(pdst + 16 * q, o + 8 * q);
+                                }
+                            }
+                        }
                     }
                 }
             }

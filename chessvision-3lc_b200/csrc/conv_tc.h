@@ -44,6 +44,8 @@ struct alignas(64) ConvParams {
     int out_c_stride;       // channels per pixel of the output buffer
     int out_c_off;          // first output channel
     const __half* res;      // optional residual, NHWC fp16 (same pixel grid as out)
+    __half* pool_out;       // row-streaming kernel only: also write MaxPool2d(2) of the output, NHWC fp16 [N,H/2,W/2,pool_c_stride]
+    int pool_c_stride;
     int res_c_stride;
     int convt_cout;         // EPI_CONVT: Cout per (dy,dx) block
     const float* outc_w;    // EPI_OUTC: [64]
