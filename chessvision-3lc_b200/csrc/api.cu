@@ -208,11 +208,11 @@ int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logi
         CK(aux(launch_maxpool2(ctx->cat0, ctx->p1, n, 256, 256, 64, 128, s)));
     }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[1], n, s) || run_conv(ctx, P[2], n, s)) return -2; }   // down1
-    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat1, ctx->p2, n, 128, 128, 128, 256, s))); }
+    if (P[2].p.pool_out == nullptr) { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat1, ctx->p2, n, 128, 128, 128, 256, s))); }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[3], n, s) || run_conv(ctx, P[4], n, s)) return -2; }   // down2
-    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat2, ctx->p3, n, 64, 64, 256, 512, s))); }
+    if (P[4].p.pool_out == nullptr) { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat2, ctx->p3, n, 64, 64, 256, 512, s))); }
     { StageTimer t(ctx, 0, s); if (run_conv(ctx, P[5], n, s) || run_conv(ctx, P[6], n, s)) return -2; }   // down3
-    { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat3, ctx->p4, n, 32, 32, 512, 1024, s))); }
+    if (P[6].p.pool_out == nullptr) { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat3, ctx->p4, n, 32, 32, 512, 1024, s))); }
     {
         StageTimer t(ctx, 0, s);
         for (int i = 7; i <= 19; ++i)                                                             // down4, up1..up4.conv0
@@ -462,16 +462,24 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     int rc = 0;
     // encoder
     rc |= build_conv(ctx, P[0], ctx->t0, B, 256, 256, 64, 0, 64, W[0], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[0], ctx->cat0, 128, 0, 1, nullptr, 0);
-    if (P[0].variant == 2 && getenv("CVB_NO_POOL_FUSE") == nullptr) {   // row-streaming kernel: MaxPool2d(2) of inc's output fused into its epilogue
-        P[0].p.pool_out = ctx->p1;
-        P[0].p.pool_c_stride = 64;
-    }
     rc |= build_conv(ctx, P[1], ctx->p1, B, 128, 128, 64, 0, 64, W[1], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[1], ctx->t1, 128, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[2], ctx->t1, B, 128, 128, 128, 0, 128, W[2], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[2], ctx->cat1, 256, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[3], ctx->p2, B, 64, 64, 128, 0, 128, W[3], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[3], ctx->t2, 256, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[4], ctx->t2, B, 64, 64, 256, 0, 256, W[4], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[4], ctx->cat2, 512, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[5], ctx->p3, B, 32, 32, 256, 0, 256, W[5], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[5], ctx->t3, 512, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[6], ctx->t3, B, 32, 32, 512, 0, 512, W[6], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[6], ctx->cat3, 1024, 0, 1, nullptr, 0);
+    if (getenv("CVB_NO_POOL_FUSE") == nullptr) {
+        // MaxPool2d(2) (unet_parts.py:34) of each encoder level fused into the epilogue of the conv that produces it: the
+        // row-streaming kernel pools over row pairs, the tile kernels inside a warp (tile rows 8 or 16 lanes apart)
+        struct { int conv; __half* out; int c; } pools[4] = {{0, ctx->p1, 64}, {2, ctx->p2, 128}, {4, ctx->p3, 256}, {6, ctx->p4, 512}};
+        for (auto& q : pools) {
+            ConvLaunch& L = P[q.conv];
+            if (L.variant == 2 || (L.p.tn == 1 && (L.p.tw == 8 || L.p.tw == 16) && L.p.th % 2 == 0)) {
+                L.p.pool_out = q.out;
+                L.p.pool_c_stride = q.c;
+            }
+        }
+    }
     rc |= build_conv(ctx, P[7], ctx->p4, B, 16, 16, 512, 0, 512, W[7], 3, 1, EPI_STORE);      rc |= set_store(ctx, P[7], ctx->t4, 1024, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[8], ctx->t4, B, 16, 16, 1024, 0, 1024, W[8], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[8], ctx->x5, 1024, 0, 1, nullptr, 0);
     // decoder: convT writes the upper channel half of the concat buffer (torch.cat([skip, up]), unet_parts.py:67)

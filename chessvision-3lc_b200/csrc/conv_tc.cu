@@ -38,6 +38,12 @@ struct ConvCfg {
 
 constexpr int kOutBufBytes = 128 * 128;   // one staged store group: 128 pixels x 64 channels fp16
 
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 // 64 channels (128 B) of one pixel of the residual tensor -> 32 registers, as four 256-bit loads (every request moves whole
 // 32-byte sectors).  Issued well before the accumulator is ready so that the L2 latency is off the epilogue's critical path.
 __device__ __forceinline__ void res_load64(const __half* res, uint32_t (&r)[32]) {
@@ -148,6 +154,25 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             if (c + 2 < NC && has_res) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) rcur[i] = rnext[i];
+            }
+            if (EPI == EPI_STORE && p.pool_out != nullptr) {
+                // fused MaxPool2d(2): the 2x2 window lives in one warp (rows of the tile are tw = 8 or 16 lanes apart)
+                uint32_t m[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint32_t up = __shfl_xor_sync(0xffffffffu, o[i], p.tw);
+                    const __half2 v2 = __hmax2(*reinterpret_cast<const __half2*>(&o[i]), *reinterpret_cast<const __half2*>(&up));
+                    const uint32_t vu = *reinterpret_cast<const uint32_t*>(&v2);
+                    const uint32_t side = __shfl_xor_sync(0xffffffffu, vu, 1);
+                    const __half2 h2 = __hmax2(v2, *reinterpret_cast<const __half2*>(&side));
+                    m[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                if (valid && ((h | w) & 1) == 0) {
+                    const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1);
+                    __half* pdst = p.pool_out + ppix * p.pool_c_stride + col0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st_global_v8(pdst + 16 * q, m + 8 * q);
+                }
             }
             // staging buffer: free once the store issued `out_bufs` groups ago has read it
             const int buf = p.out_bufs == 2 ? (store_count & 1) : 0;
@@ -568,11 +593,6 @@ __device__ __forceinline__ void rs_runs(uint32_t s_base, int lo, int hi, uint32_
     }
 }
 
-__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t* v) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-                 : "memory");
-}
 
 // All K steps of one pipeline stage for an interior input row (its three column blocks land on slots s_base .. s_base+2
 // of the ring).  NA = slots before the ring wraps (3: no wrap; 2 or 1: the remaining 3 - NA blocks go to slot 0 on).
