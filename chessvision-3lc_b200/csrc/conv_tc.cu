@@ -722,9 +722,9 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_strips; t += gridDim.x) {
-                const int w0 = (t % p.tiles_w) * 128;
+                const int w0 = (t % p.tiles_w) * p.tw;
                 const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
-                const int n0 = t / strips_per_image;
+                const int n0 = (t / strips_per_image) * p.tn;
                 for (int j = -1; j <= R; ++j) {
                     for (int l = 0; l < loads_per_row; ++l) {
                         const int kc = MODE == 0 ? l / 3 : l;
@@ -800,9 +800,10 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
         const int row = quarter * 32 + lane;
         uint32_t rho0 = 0;
         for (int t = blockIdx.x; t < total_strips; t += gridDim.x, rho0 += R) {
-            const int w0 = (t % p.tiles_w) * 128;
+            // a streamed row is tn images x tw pixels (1 x 128 for the wide UNet levels, 8 x 16 for 16x16 squares)
+            const int w0 = (t % p.tiles_w) * p.tw + row % p.tw;
             const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
-            const int n = t / strips_per_image;
+            const int n = (t / strips_per_image) * p.tn + row / p.tw;
             for (int r2 = 2 * group; r2 < R; r2 += 4) {
                 uint32_t o_prev[32];
 #pragma unroll
@@ -810,7 +811,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                     const int r = r2 + half;
                     const uint32_t rho = rho0 + static_cast<uint32_t>(r);
                     const uint32_t slot = (0u - rho) & 7u;
-                    const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0 + row;
+                    const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0;
                     const bool has_res = EPI == EPI_STORE && p.res != nullptr && n < p.N;
                     uint32_t res0[32];
                     if (has_res) res_load64(p.res + pix * p.res_c_stride, res0);
@@ -819,7 +820,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
                     if constexpr (EPI == EPI_OUTC) {
                         int unused = 0;
-                        epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0 + row, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res0);
+                        epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res0);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
@@ -854,7 +855,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                                     o[i] = *reinterpret_cast<const uint32_t*>(&mm);
                                 }
                                 if (n < p.N && (lane & 1) == 0) {
-                                    const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + ((h0 + r) >> 1)) * (p.W >> 1) + ((w0 + row) >> 1);
+                                    const size_t ppix = (static_cast<size_t>(n) * (p.H >> 1) + ((h0 + r) >> 1)) * (p.W >> 1) + (w0 >> 1);
                                     __half* pdst = p.pool_out + ppix * p.pool_c_stride;
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) st_global_v8(pdst + 16 * q, o + 8 * q);
@@ -982,8 +983,8 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
     L.epilogue = epilogue;
     L.n_max = Nmax;
     if (use_vr && conv_try_rs(L, ksize, stride, Ho, Wo, Cin)) {
-        rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 128, 1, 1);
-        if (!rc) rc = tmap_act(&p.a_map[1], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 130, 1, 1);
+        rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, 1, p.tn);
+        if (!rc && p.rs_mode == 1) rc = tmap_act(&p.a_map[1], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 130, 1, 1);
         if (rc) return rc;
     } else if (use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
@@ -1131,12 +1132,15 @@ bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     ConvParams& p = L.p;
     const char* off = getenv("CVB_NO_RS");
     if (off && off[0] == '1') return false;
-    if (ksize != 3 || stride != 1 || Wo % 128 || L.block_n != 64 || p.n_tiles != 1) return false;
+    if (ksize != 3 || stride != 1 || L.block_n != 64 || p.n_tiles != 1) return false;
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
-    const int R = Ho % 64 == 0 ? 64 : (Ho % 32 == 0 ? 32 : (Ho % 16 == 0 ? 16 : 0));
+    // a streamed row of 128 pixels is either one 128-pixel segment of a wide image or the same row of eight 16x16 images
+    const bool squares = Wo == 16 && Ho == 16;
+    if (!squares && Wo % 128) return false;
+    const int R = squares ? 16 : (Ho % 64 == 0 ? 64 : (Ho % 32 == 0 ? 32 : (Ho % 16 == 0 ? 16 : 0)));
     if (R == 0) return false;
     const char* m = getenv("CVB_RS_MODE");
-    const int mode = m ? atoi(m) : 1;
+    const int mode = squares ? 0 : (m ? atoi(m) : 1);   // the 130-pixel box of mode 1 needs contiguous pixels: wide images only
     if (mode < 0 || mode > 1) return false;
     const int stage = mode == 0 ? 16384 : 17408;
     const int w_bytes = 9 * (Cin / 64) * 64 * 128;
@@ -1150,8 +1154,8 @@ bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     p.rs_mode = mode;
     p.smem_bytes = w_bytes + stages * stage + fixed;
     p.out_bufs = 0;
-    p.tn = 1; p.th = 1; p.tw = 128;
-    p.tiles_w = Wo / 128;
+    p.tn = squares ? 8 : 1; p.th = 1; p.tw = squares ? 16 : 128;
+    p.tiles_w = Wo / p.tw;
     p.tiles_h = Ho / R;
     L.variant = 2;
     return true;

@@ -22,7 +22,7 @@ def check(out, ref):
 
 CASES = [
     # N, H, W, Cin, Cout, k, stride, relu, residual
-    (2, 16, 16, 64, 64, 3, 1, True, False),      # BLOCK_N 64, tile 8x16
+    (2, 16, 16, 64, 64, 3, 1, True, False),      # BLOCK_N 64; row-streaming kernel, two of eight squares present
     (1, 32, 32, 64, 128, 3, 1, True, False),     # BLOCK_N 128
     (3, 16, 16, 128, 256, 3, 1, False, False),   # BLOCK_N 256, 2 K chunks per tap
     (1, 16, 16, 256, 512, 3, 1, True, False),    # 2 N tiles
@@ -47,6 +47,10 @@ CASES = [
     (5, 64, 128, 64, 64, 3, 1, True, True),      # residual, one strip per image
     (2, 48, 256, 64, 64, 3, 1, False, False),    # strips of 16 rows, two segments
     (150, 16, 128, 64, 64, 3, 1, True, False),   # more strips than SMs, one 16-row strip each
+    # ... in its 16x16 form (ResNet layer1): a streamed row is the same image row of eight squares
+    (64, 16, 16, 64, 64, 3, 1, True, True),      # one board of squares, residual (BasicBlock conv2)
+    (203, 16, 16, 64, 64, 3, 1, True, False),    # ragged: 203 = 25 * 8 + 3 squares
+    (1500, 16, 16, 64, 64, 3, 1, False, True),   # more strips than SMs
 ]
 
 
