@@ -69,6 +69,9 @@ SYMBOLS = {
     "cvb_wgrad3x3_f16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "cvb_eval_metrics": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "cvb_quality_scores": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    "cvb_jpeg_info": (_I, [_P, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "cvb_jpeg_coefficients": (_I, [_P, C.c_int64, _P, _P]),
+    "cvb_decode_jpeg": (_I, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I, _I, _I, _P, _P]),
     "cvb_launch_count": (C.c_int64, [_P]),
     "cvb_profile": (_I, [_P, _I]),
     "cvb_profile_read": (_I, [_P, C.POINTER(C.c_float), _I]),
@@ -375,6 +378,19 @@ class Engine:
                  "cvb_quality_scores")
         return scores
 
+    # ---- JPEG decode front-end
+    def decode_jpeg(self, streams):
+        """list of ``bytes`` (JPEG files of identical dimensions) -> u8[N,H,W,3] BGR on the device, bit-identical to
+        ``cv2.imdecode(buf, cv2.IMREAD_COLOR)``."""
+        n = len(streams)
+        h, w = jpeg_info(streams[0])
+        bufs = [np.frombuffer(b, dtype=np.uint8) for b in streams]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_int64 * n)(*[b.size for b in bufs])
+        img = torch.empty((n, h, w, 3), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_decode_jpeg(self.h, ptrs, sizes, n, h, w, _ptr(img), _stream()), "cvb_decode_jpeg")
+        return img
+
     def launch_count(self) -> int:
         return int(self.lib.cvb_launch_count(self.h))
 
@@ -386,6 +402,30 @@ class Engine:
         self._ck(self.lib.cvb_profile_read(self.h, buf, 7), "cvb_profile_read")
         names = ("unet_conv_tc", "unet_aux", "mask_to_quad", "warp", "resnet_stem", "resnet_conv_tc", "head")
         return dict(zip(names, [float(v) for v in buf]))
+
+
+def jpeg_info(stream: bytes):
+    """(height, width) of a JPEG stream; raises NativeError for streams outside the supported subset."""
+    lib = load_library()
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    h, w = C.c_int32(), C.c_int32()
+    rc = lib.cvb_jpeg_info(C.c_void_p(buf.ctypes.data), buf.size, C.byref(h), C.byref(w))
+    if rc != 0:
+        raise NativeError(f"cvb_jpeg_info failed ({rc}): not a baseline 4:2:0 JPEG with dimensions that are multiples of 16")
+    return h.value, w.value
+
+
+def jpeg_coefficients(stream: bytes):
+    """Host-side entropy decoding alone: (int16 [H*W*3/2] coefficients, uint16 [3,64] quantisation tables)."""
+    lib = load_library()
+    h, w = jpeg_info(stream)
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    coef = np.empty(h * w * 3 // 2, np.int16)
+    qt = np.empty((3, 64), np.uint16)
+    rc = lib.cvb_jpeg_coefficients(C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(coef.ctypes.data), C.c_void_p(qt.ctypes.data))
+    if rc != 0:
+        raise NativeError(f"cvb_jpeg_coefficients failed ({rc})")
+    return coef, qt
 
 
 def fen_strings(fen_tensor):

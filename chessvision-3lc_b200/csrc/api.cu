@@ -419,6 +419,7 @@ void cvb_destroy(cvb_ctx* ctx) {
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->trainer) cvb_trainer_free(ctx->trainer);
+    if (ctx->jpeg) cvb_jpeg_free(ctx->jpeg);
     delete ctx;
 }
 

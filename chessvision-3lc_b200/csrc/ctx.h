@@ -14,6 +14,8 @@
 
 struct cvb_trainer;   // train.cu
 void cvb_trainer_free(cvb_trainer* t);
+struct cvb_jpeg_state;   // jpeg.cu: staging buffers of the JPEG decode front-end
+void cvb_jpeg_free(cvb_jpeg_state* s);
 
 using namespace cvb;
 
@@ -85,6 +87,7 @@ struct cvb_ctx {
 
     // ---- UNet training step (train.cu); owned, destroyed with the context
     cvb_trainer* trainer = nullptr;
+    cvb_jpeg_state* jpeg = nullptr;
 
     // ---- profiling
     bool profile = false;

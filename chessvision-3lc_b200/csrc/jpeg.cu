@@ -1,0 +1,520 @@
+// JPEG decode front-end of the image->FEN path.
+//
+// Replaces cv2.imread / cv2.imdecode(buf, IMREAD_COLOR) in front of ChessVision.process_image
+// (scripts/eval/evaluate.py:147, app/computeroot/cv_endpoint.py:151-153), i.e. OpenCV's bundled libjpeg-turbo with its
+// defaults (JDCT_ISLOW, fancy chroma upsampling, separate colour conversion, BGR output) — bit for bit.
+//
+// Split by what is sequential and what is not:
+//   host   marker parsing + Huffman decoding (jdhuff.c): inherently serial per image, one image per host thread; the
+//          result is the quantised coefficients, int16 [blocks][64] in natural order (1.5 * H * W * 2 bytes per image)
+//   device k_jpeg_idct   dequantisation + 8x8 inverse DCT (jidctint.c jpeg_idct_islow, 32-bit integer arithmetic,
+//                        CONST_BITS 13 / PASS1_BITS 2) + masked range limit -> Y, Cb, Cr planes
+//          k_jpeg_color  h2v2 fancy upsampling of Cb/Cr (jdsample.c: 3/4 near + 1/4 far per axis, rounding 8 / 7
+//                        alternating by column, edges replicated) + YCbCr->RGB with libjpeg's 16-bit fixed-point
+//                        constants (jdcolor.c) -> u8 [N,H,W,3] BGR, the layout every other kernel of the path reads
+// Both kernels are HBM-bound byte/integer work (3 B read + 3 B written per pixel in total).
+// Supported subset (what the reference's data needs; anything else is error -6, never a silent fallback): baseline SOF0,
+// 8-bit, 3 components, 4:2:0, dimensions multiples of 16, restart intervals, EXIF orientation absent or 1.
+#include "ctx.h"
+
+#include <string.h>
+
+#include <atomic>
+#include <thread>
+
+namespace cvb {
+namespace {
+
+const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct HuffTable {
+    bool present = false;
+    int32_t maxcode[18];   // largest code of each length (-1: none)
+    int32_t valoff[17];    // symbol index of the first code of each length minus that code
+    uint8_t symbols[256];
+    uint16_t look[256];    // 8-bit lookahead: (length << 8) | symbol, 0 = longer than 8 bits
+};
+
+struct JpegHeader {
+    int h = 0, w = 0, restart = 0;
+    size_t scan = 0;
+    uint16_t qt[3][64];      // natural order
+    HuffTable dc[4], ac[4];
+    uint16_t qsrc[4][64];
+    bool qpresent[4] = {false, false, false, false};
+    int comp_q[3], comp_dc[3], comp_ac[3], comp_id[3];
+};
+
+void build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, int n) {
+    t.present = true;
+    memcpy(t.symbols, symbols, n);
+    memset(t.look, 0, sizeof t.look);
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        t.valoff[len] = k - code;
+        for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+            if (len <= 8) {
+                const int lo = code << (8 - len);
+                for (int f = 0; f < (1 << (8 - len)); ++f) t.look[lo + f] = static_cast<uint16_t>((len << 8) | symbols[k]);
+            }
+        }
+        t.maxcode[len] = counts[len - 1] ? code - 1 : -1;
+        code <<= 1;
+    }
+    t.maxcode[17] = 0x7fffffff;
+}
+
+int exif_orientation(const uint8_t* t, size_t n) {
+    if (n < 8) return 0;
+    const bool le = t[0] == 'I';
+    auto u16 = [&](size_t o) { return le ? t[o] | (t[o + 1] << 8) : (t[o] << 8) | t[o + 1]; };
+    auto u32 = [&](size_t o) { return le ? u16(o) | (u16(o + 2) << 16) : (u16(o) << 16) | u16(o + 2); };
+    const size_t ifd = static_cast<size_t>(u32(4));
+    if (ifd + 2 > n) return 0;
+    const int cnt = u16(ifd);
+    for (int k = 0; k < cnt; ++k) {
+        const size_t e = ifd + 2 + 12 * static_cast<size_t>(k);
+        if (e + 12 <= n && u16(e) == 0x0112) return u16(e + 8);
+    }
+    return 0;
+}
+
+// 0 ok, -6 unsupported / corrupt (msg says why)
+int parse_header(const uint8_t* d, size_t n, JpegHeader& H, const char** msg) {
+    auto bad = [&](const char* m) { *msg = m; return -6; };
+    if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return bad("not a JPEG stream");
+    size_t i = 2;
+    bool sof = false;
+    while (i + 4 <= n) {
+        if (d[i] != 0xFF) return bad("corrupt JPEG: marker expected");
+        const int m = d[i + 1];
+        if (m == 0xFF) { ++i; continue; }
+        const size_t len = (static_cast<size_t>(d[i + 2]) << 8) | d[i + 3];
+        if (len < 2 || i + 2 + len > n) return bad("corrupt JPEG: segment exceeds the buffer");
+        const uint8_t* s = d + i + 4;
+        const size_t sl = len - 2;
+        if (m == 0xDB) {
+            for (size_t j = 0; j + 65 <= sl; j += 65) {
+                if (s[j] >> 4) return bad("16-bit quantisation tables are not supported");
+                const int tq = s[j] & 3;
+                for (int k = 0; k < 64; ++k) H.qsrc[tq][kZigzag[k]] = s[j + 1 + k];
+                H.qpresent[tq] = true;
+            }
+        } else if (m == 0xC4) {
+            size_t j = 0;
+            while (j + 17 <= sl) {
+                const int tc = s[j] >> 4, th = s[j] & 3;
+                int cnt = 0;
+                for (int k = 0; k < 16; ++k) cnt += s[j + 1 + k];
+                if (cnt > 256 || j + 17 + cnt > sl) return bad("corrupt JPEG: Huffman table");
+                build_table(tc ? H.ac[th] : H.dc[th], s + j + 1, s + j + 17, cnt);
+                j += 17 + cnt;
+            }
+        } else if (m == 0xC0) {
+            if (sl < 15 || s[0] != 8 || s[5] != 3) return bad("only 8-bit three-component baseline JPEGs are supported");
+            H.h = (s[1] << 8) | s[2];
+            H.w = (s[3] << 8) | s[4];
+            for (int k = 0; k < 3; ++k) {
+                H.comp_id[k] = s[6 + 3 * k];
+                const int hv = s[7 + 3 * k];
+                if (hv != (k == 0 ? 0x22 : 0x11)) return bad("only 4:2:0 chroma subsampling is supported");
+                H.comp_q[k] = s[8 + 3 * k] & 3;
+            }
+            if (H.h % 16 || H.w % 16 || H.h <= 0 || H.w <= 0) return bad("image dimensions must be multiples of 16");
+            sof = true;
+        } else if ((m >= 0xC1 && m <= 0xCF) && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return bad("only baseline (SOF0) JPEGs are supported");
+        } else if (m == 0xDD) {
+            H.restart = (s[0] << 8) | s[1];
+        } else if (m == 0xE1 && sl > 6 && memcmp(s, "Exif\0\0", 6) == 0) {
+            const int o = exif_orientation(s + 6, sl - 6);
+            if (o != 0 && o != 1) return bad("EXIF orientation other than 1 is not supported");
+        } else if (m == 0xDA) {
+            if (!sof || sl < 10 || s[0] != 3) return bad("corrupt JPEG: scan header");
+            for (int k = 0; k < 3; ++k) {
+                int c = -1;
+                for (int q = 0; q < 3; ++q)
+                    if (H.comp_id[q] == s[1 + 2 * k]) c = q;
+                if (c != k) return bad("interleaved scan with components in frame order expected");
+                H.comp_dc[c] = s[2 + 2 * k] >> 4;
+                H.comp_ac[c] = s[2 + 2 * k] & 3;
+                if (!H.dc[H.comp_dc[c] & 3].present || !H.ac[H.comp_ac[c]].present || !H.qpresent[H.comp_q[c]])
+                    return bad("corrupt JPEG: missing table");
+                memcpy(H.qt[c], H.qsrc[H.comp_q[c]], sizeof H.qt[c]);
+            }
+            H.scan = i + 2 + len;
+            return 0;
+        }
+        i += 2 + len;
+    }
+    return bad("corrupt JPEG: no scan");
+}
+
+struct BitReader {
+    const uint8_t* d;
+    size_t n, p;
+    uint64_t acc = 0;
+    int bits = 0;
+    void fill() {
+        while (bits <= 56) {
+            uint32_t b = 0;
+            if (p < n) {
+                b = d[p];
+                if (b == 0xFF) {
+                    const uint32_t nx = p + 1 < n ? d[p + 1] : 0xD9;
+                    if (nx == 0) p += 2;
+                    else b = 0;   // a marker: feed zeros (jdhuff.c does the same until the MCU ends)
+                } else {
+                    ++p;
+                }
+            }
+            acc = (acc << 8) | b;
+            bits += 8;
+        }
+    }
+    inline uint32_t peek(int k) {
+        if (bits < k) fill();
+        return static_cast<uint32_t>(acc >> (bits - k)) & ((1u << k) - 1);
+    }
+    inline void skip(int k) { bits -= k; }
+    inline uint32_t get(int k) {
+        if (k == 0) return 0;
+        const uint32_t v = peek(k);
+        bits -= k;
+        return v;
+    }
+    void restart() {
+        acc = 0;
+        bits = 0;
+        while (p + 1 < n && !(d[p] == 0xFF && d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7)) ++p;
+        p += 2;
+    }
+};
+
+inline int decode_symbol(BitReader& br, const HuffTable& t) {
+    const uint32_t look = t.look[br.peek(8)];
+    if (look) {
+        br.skip(look >> 8);
+        return look & 255;
+    }
+    int code = static_cast<int>(br.get(8));
+    for (int len = 9; len <= 16; ++len) {
+        code = (code << 1) | static_cast<int>(br.get(1));
+        if (code <= t.maxcode[len]) return t.symbols[(t.valoff[len] + code) & 255];
+    }
+    return -1;
+}
+
+inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
+// coef: int16 [Y blocks (H/8 x W/8) | Cb blocks | Cr blocks][64], zero-initialised by the caller.  0 ok / -6 corrupt.
+int decode_scan(const uint8_t* d, size_t n, const JpegHeader& H, int16_t* coef) {
+    const int mh = H.h / 16, mw = H.w / 16;
+    int16_t* plane[3] = {coef, coef + static_cast<size_t>(4) * mh * mw * 64, coef + static_cast<size_t>(5) * mh * mw * 64};
+    BitReader br{d, n, H.scan};
+    int pred[3] = {0, 0, 0};
+    for (int mcu = 0; mcu < mh * mw; ++mcu) {
+        if (H.restart && mcu && mcu % H.restart == 0) {
+            br.restart();
+            pred[0] = pred[1] = pred[2] = 0;
+        }
+        const int my = mcu / mw, mx = mcu - my * mw;
+        for (int b = 0; b < 6; ++b) {
+            const int c = b < 4 ? 0 : b - 3;
+            int16_t* blk = c == 0 ? plane[0] + (static_cast<size_t>(2 * my + (b >> 1)) * (2 * mw) + 2 * mx + (b & 1)) * 64
+                                  : plane[c] + (static_cast<size_t>(my) * mw + mx) * 64;
+            const HuffTable& dct = H.dc[H.comp_dc[c] & 3];
+            const HuffTable& act = H.ac[H.comp_ac[c]];
+            int s = decode_symbol(br, dct);
+            if (s < 0 || s > 15) return -6;
+            if (s) pred[c] += extend(static_cast<int>(br.get(s)), s);
+            blk[0] = static_cast<int16_t>(pred[c]);
+            for (int k = 1; k < 64;) {
+                const int rs = decode_symbol(br, act);
+                if (rs < 0) return -6;
+                const int r = rs >> 4;
+                s = rs & 15;
+                if (s == 0) {
+                    if (r != 15) break;
+                    k += 16;
+                    continue;
+                }
+                k += r;
+                if (k > 63) return -6;
+                blk[kZigzag[k]] = static_cast<int16_t>(extend(static_cast<int>(br.get(s)), s));
+                ++k;
+            }
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------- device
+constexpr int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633;
+constexpr int F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
+
+// one 1-D pass of jpeg_idct_islow on 8 values (32-bit integers like the C code); DESCALE by `shift`
+__device__ __forceinline__ void idct8(const int (&v)[8], int shift, int (&o)[8]) {
+    int z2 = v[2], z3 = v[6];
+    int z1 = (z2 + z3) * F_0_541;
+    int tmp2 = z1 + z3 * (-F_1_847);
+    int tmp3 = z1 + z2 * F_0_765;
+    z2 = v[0];
+    z3 = v[4];
+    int tmp0 = (z2 + z3) * 8192;
+    int tmp1 = (z2 - z3) * 8192;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = v[7];
+    tmp1 = v[5];
+    tmp2 = v[3];
+    tmp3 = v[1];
+    z1 = tmp0 + tmp3;
+    z2 = tmp1 + tmp2;
+    z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * F_1_175;
+    tmp0 *= F_0_298;
+    tmp1 *= F_2_053;
+    tmp2 *= F_3_072;
+    tmp3 *= F_1_501;
+    z1 *= -F_0_899;
+    z2 *= -F_2_562;
+    z3 = z3 * (-F_1_961) + z5;
+    z4 = z4 * (-F_0_390) + z5;
+    tmp0 += z1 + z3;
+    tmp1 += z2 + z4;
+    tmp2 += z2 + z3;
+    tmp3 += z1 + z4;
+    const int r = 1 << (shift - 1);
+    o[0] = (tmp10 + tmp3 + r) >> shift;
+    o[7] = (tmp10 - tmp3 + r) >> shift;
+    o[1] = (tmp11 + tmp2 + r) >> shift;
+    o[6] = (tmp11 - tmp2 + r) >> shift;
+    o[2] = (tmp12 + tmp1 + r) >> shift;
+    o[5] = (tmp12 - tmp1 + r) >> shift;
+    o[3] = (tmp13 + tmp0 + r) >> shift;
+    o[4] = (tmp13 - tmp0 + r) >> shift;
+}
+
+__device__ __forceinline__ uint32_t range_limit_masked(int x) {   // range_limit[x & RANGE_MASK], table centred on 128
+    const int i = x & 1023;
+    return i < 128 ? i + 128 : (i < 512 ? 255 : (i < 896 ? 0 : i - 896));
+}
+
+// 8 threads per 8x8 block (32 blocks per CTA of 256 threads): thread t transforms column t, then row t.
+// coef int16 [N][blocks_per_image][64]; qt u16 [N][3][64]; planes u8 [N][H*W (Y) | H*W/4 (Cb) | H*W/4 (Cr)]
+__global__ void __launch_bounds__(256) k_jpeg_idct(const int16_t* __restrict__ coef, const uint16_t* __restrict__ qt,
+                                                   uint8_t* __restrict__ planes, int H, int W, long long total_blocks) {
+    __shared__ int ws[32][8][9];
+    const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const long long gb = static_cast<long long>(blockIdx.x) * 32 + lb;
+    const int per_image = (H / 8) * (W / 8) * 3 / 2;
+    const bool live = gb < total_blocks;
+    int n = 0, b = 0, comp = 0, bw = W / 8;
+    size_t plane_off = 0;
+    if (live) {
+        n = static_cast<int>(gb / per_image);
+        b = static_cast<int>(gb - static_cast<long long>(n) * per_image);
+        const int ny = (H / 8) * (W / 8);
+        if (b >= ny) {
+            comp = 1 + (b - ny) / (ny / 4);
+            b = (b - ny) % (ny / 4);
+            bw = W / 16;
+            plane_off = static_cast<size_t>(H) * W + static_cast<size_t>(comp - 1) * (H / 2) * (W / 2);
+        }
+        const int16_t* src = coef + gb * 64;
+        const uint16_t* q = qt + (static_cast<size_t>(n) * 3 + comp) * 64;
+        int v[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v[r] = static_cast<int>(__ldg(src + r * 8 + t)) * static_cast<int>(__ldg(q + r * 8 + t));
+        idct8(v, 13 - 2, o);   // pass 1: column t
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ws[lb][r][t] = o[r];
+    }
+    __syncwarp();
+    if (live) {
+        int v[8], o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = ws[lb][t][c];
+        idct8(v, 13 + 2 + 3, o);   // pass 2: row t
+        uint2 px;
+        px.x = range_limit_masked(o[0]) | (range_limit_masked(o[1]) << 8) | (range_limit_masked(o[2]) << 16) | (range_limit_masked(o[3]) << 24);
+        px.y = range_limit_masked(o[4]) | (range_limit_masked(o[5]) << 8) | (range_limit_masked(o[6]) << 16) | (range_limit_masked(o[7]) << 24);
+        const int by = b / bw, bx = b - by * bw;
+        uint8_t* dst = planes + static_cast<size_t>(n) * (static_cast<size_t>(H) * W * 3 / 2) + plane_off +
+                       (static_cast<size_t>(by) * 8 + t) * (bw * 8) + bx * 8;
+        *reinterpret_cast<uint2*>(dst) = px;
+    }
+}
+
+// one thread per pair of horizontally adjacent output pixels (2c, 2c+1) of row y
+__global__ void __launch_bounds__(256) k_jpeg_color(const uint8_t* __restrict__ planes, uint8_t* __restrict__ img, int H, int W,
+                                                    long long total_pairs) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total_pairs) return;
+    const int cw = W / 2, ch = H / 2;
+    const int c = static_cast<int>(i % cw);
+    const long long r = i / cw;
+    const int y = static_cast<int>(r % H);
+    const long long n = r / H;
+    const uint8_t* base = planes + n * (static_cast<long long>(H) * W * 3 / 2);
+    const uint8_t* Y = base + static_cast<long long>(y) * W + 2 * c;
+    const int cy = y >> 1;
+    int oy = (y & 1) ? cy + 1 : cy - 1;   // the further chroma row; edge rows are replicated (jdmainct.c context rows)
+    oy = oy < 0 ? 0 : (oy >= ch ? ch - 1 : oy);
+    const int cl = c > 0 ? c - 1 : 0, cr = c + 1 < cw ? c + 1 : cw - 1;
+    int up[2][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const uint8_t* P = base + static_cast<long long>(H) * W + static_cast<long long>(k) * ch * cw;
+        const uint8_t* near = P + static_cast<long long>(cy) * cw;
+        const uint8_t* far = P + static_cast<long long>(oy) * cw;
+        const int cur = 3 * near[c] + far[c], last = 3 * near[cl] + far[cl], next = 3 * near[cr] + far[cr];
+        up[k][0] = (3 * cur + last + 8) >> 4;
+        up[k][1] = (3 * cur + next + 7) >> 4;
+    }
+    uint8_t out[6];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int yy = Y[k], xb = up[0][k] - 128, xr = up[1][k] - 128;
+        int rr = yy + ((91881 * xr + 32768) >> 16);
+        int bb = yy + ((116130 * xb + 32768) >> 16);
+        int gg = yy + ((-22554 * xb + 32768 - 46802 * xr) >> 16);
+        rr = rr < 0 ? 0 : (rr > 255 ? 255 : rr);
+        gg = gg < 0 ? 0 : (gg > 255 ? 255 : gg);
+        bb = bb < 0 ? 0 : (bb > 255 ? 255 : bb);
+        out[3 * k] = static_cast<uint8_t>(bb);
+        out[3 * k + 1] = static_cast<uint8_t>(gg);
+        out[3 * k + 2] = static_cast<uint8_t>(rr);
+    }
+    uint16_t* dst = reinterpret_cast<uint16_t*>(img + (r * W + 2 * c) * 3);   // 6-byte aligned at an even pixel: 2-byte stores
+    dst[0] = static_cast<uint16_t>(out[0] | (out[1] << 8));
+    dst[1] = static_cast<uint16_t>(out[2] | (out[3] << 8));
+    dst[2] = static_cast<uint16_t>(out[4] | (out[5] << 8));
+}
+
+}  // namespace
+}  // namespace cvb
+
+// Lazily sized staging (pinned host + device) for chunks of images; owned by the context.
+struct cvb_jpeg_state {
+    int16_t* h_coef = nullptr;
+    uint16_t* h_qt = nullptr;
+    int16_t* d_coef = nullptr;
+    uint16_t* d_qt = nullptr;
+    uint8_t* d_planes = nullptr;
+    size_t cap_pixels = 0;   // chunk * H * W the buffers were sized for
+    int chunk = 0;
+    cudaEvent_t done = nullptr;
+};
+
+void cvb_jpeg_free(cvb_jpeg_state* s) {
+    if (!s) return;
+    if (s->h_coef) cudaFreeHost(s->h_coef);
+    if (s->h_qt) cudaFreeHost(s->h_qt);
+    if (s->d_coef) cudaFree(s->d_coef);
+    if (s->d_qt) cudaFree(s->d_qt);
+    if (s->d_planes) cudaFree(s->d_planes);
+    if (s->done) cudaEventDestroy(s->done);
+    delete s;
+}
+
+extern "C" {
+
+int cvb_jpeg_info(const uint8_t* data, int64_t nbytes, int32_t* h, int32_t* w) {
+    if (!data || nbytes < 4) return -1;
+    cvb::JpegHeader H;
+    const char* msg = "";
+    const int rc = cvb::parse_header(data, static_cast<size_t>(nbytes), H, &msg);
+    if (rc) return rc;
+    if (h) *h = H.h;
+    if (w) *w = H.w;
+    return 0;
+}
+
+int cvb_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* coef, uint16_t* qt) {
+    if (!data || !coef || nbytes < 4) return -1;
+    cvb::JpegHeader H;
+    const char* msg = "";
+    int rc = cvb::parse_header(data, static_cast<size_t>(nbytes), H, &msg);
+    if (rc) return rc;
+    memset(coef, 0, static_cast<size_t>(H.h) * H.w * 3 / 2 * sizeof(int16_t));
+    if (qt) memcpy(qt, H.qt, sizeof H.qt);
+    return cvb::decode_scan(data, static_cast<size_t>(nbytes), H, coef);
+}
+
+int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nbytes, int N, int H, int W, uint8_t* img, void* stream) {
+    if (!ctx || !data || !nbytes || !img || N < 0 || H <= 0 || W <= 0 || H % 16 || W % 16) return fail(ctx, -1, "cvb_decode_jpeg: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    if (N == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t px = static_cast<size_t>(H) * W;
+    const size_t coef_per_image = px * 3 / 2;          // int16 values
+    const int chunk = N < 64 ? N : 64;
+    if (!ctx->jpeg) ctx->jpeg = new cvb_jpeg_state();
+    cvb_jpeg_state* J = ctx->jpeg;
+    if (J->cap_pixels < static_cast<size_t>(chunk) * px) {
+        if (J->h_coef) cudaFreeHost(J->h_coef);
+        if (J->d_coef) cudaFree(J->d_coef);
+        if (J->d_planes) cudaFree(J->d_planes);
+        J->h_coef = nullptr; J->d_coef = nullptr; J->d_planes = nullptr;
+        J->cap_pixels = 0;
+        CK(cudaMallocHost(&J->h_coef, chunk * coef_per_image * sizeof(int16_t)));
+        if (!J->h_qt) CK(cudaMallocHost(&J->h_qt, static_cast<size_t>(64) * 3 * 64 * sizeof(uint16_t)));   // tables: always 64 images
+        CK(cudaMalloc(&J->d_coef, chunk * coef_per_image * sizeof(int16_t)));
+        if (!J->d_qt) CK(cudaMalloc(&J->d_qt, static_cast<size_t>(64) * 3 * 64 * sizeof(uint16_t)));
+        CK(cudaMalloc(&J->d_planes, chunk * coef_per_image));
+        J->cap_pixels = static_cast<size_t>(chunk) * px;
+        J->chunk = chunk;
+        if (!J->done) CK(cudaEventCreateWithFlags(&J->done, cudaEventDisableTiming));
+    }
+    const int cap = static_cast<int>(J->cap_pixels / px) < 64 ? static_cast<int>(J->cap_pixels / px) : 64;
+    for (int off = 0; off < N; off += cap) {
+        const int n = N - off < cap ? N - off : cap;
+        if (off) CK(cudaEventSynchronize(J->done));   // the previous chunk's H2D copy must have left the pinned buffer
+        std::atomic<int> next{0}, err{0};
+        const char* err_msg = "";
+        auto work = [&]() {
+            for (;;) {
+                const int i = next.fetch_add(1);
+                if (i >= n) return;
+                cvb::JpegHeader hd;
+                const char* msg = "";
+                int rc = cvb::parse_header(data[off + i], static_cast<size_t>(nbytes[off + i]), hd, &msg);
+                if (!rc && (hd.h != H || hd.w != W)) { rc = -6; msg = "image dimensions differ from the batch's H x W"; }
+                if (!rc) {
+                    memset(J->h_coef + i * coef_per_image, 0, coef_per_image * sizeof(int16_t));
+                    memcpy(J->h_qt + static_cast<size_t>(i) * 192, hd.qt, sizeof hd.qt);
+                    rc = cvb::decode_scan(data[off + i], static_cast<size_t>(nbytes[off + i]), hd, J->h_coef + i * coef_per_image);
+                    if (rc) msg = "corrupt JPEG: entropy-coded data";
+                }
+                if (rc) { err.store(rc); err_msg = msg; }
+            }
+        };
+        unsigned hw = std::thread::hardware_concurrency();
+        int nthreads = static_cast<int>(hw ? hw : 4);
+        if (nthreads > n) nthreads = n;
+        if (nthreads > 32) nthreads = 32;
+        std::vector<std::thread> pool;
+        for (int k = 1; k < nthreads; ++k) pool.emplace_back(work);
+        work();
+        for (auto& th : pool) th.join();
+        if (err.load()) return fail(ctx, err.load(), "cvb_decode_jpeg: %s", err_msg);
+        CK(cudaMemcpyAsync(J->d_coef, J->h_coef, n * coef_per_image * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(J->d_qt, J->h_qt, static_cast<size_t>(n) * 192 * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(J->done, s));
+        const long long blocks = static_cast<long long>(n) * (H / 8) * (W / 8) * 3 / 2;
+        cvb::k_jpeg_idct<<<static_cast<unsigned>((blocks + 31) / 32), 256, 0, s>>>(J->d_coef, J->d_qt, J->d_planes, H, W, blocks);
+        CK(cudaGetLastError());
+        const long long pairs = static_cast<long long>(n) * H * (W / 2);
+        cvb::k_jpeg_color<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, s>>>(J->d_planes, img + static_cast<size_t>(off) * px * 3, H, W, pairs);
+        CK(cudaGetLastError());
+        ctx->launches += 2;
+    }
+    CK(cudaEventSynchronize(J->done));   // the caller may reuse / free its JPEG buffers and ours is pinned staging
+    return 0;
+}
+
+}  // extern "C"

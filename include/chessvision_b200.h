@@ -165,6 +165,23 @@ CVB_API int cvb_eval_metrics(cvb_ctx* ctx, const float* probs, const uint8_t* la
 CVB_API int cvb_quality_scores(cvb_ctx* ctx, const float* values, const float* quad, const uint8_t* found, int N, int L,
                                double* scores, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * JPEG decode front-end: cv2.imread / cv2.imdecode(buf, IMREAD_COLOR) in front of process_image
+ * (scripts/eval/evaluate.py:147, app/computeroot/cv_endpoint.py:151-153), bit-identical to OpenCV's libjpeg-turbo
+ * defaults (islow IDCT, fancy upsampling, BGR).  Huffman decoding runs on the host (one image per thread), the inverse
+ * DCT, chroma upsampling and colour conversion on the device.  Supported: baseline, 8-bit, 4:2:0, dimensions multiples
+ * of 16, restart intervals, EXIF orientation absent or 1; anything else returns -6 with the reason in cvb_last_error.
+ * ------------------------------------------------------------------------------------------------------------------- */
+/* Host only: dimensions of one JPEG stream (0 ok, -6 unsupported / corrupt). */
+CVB_API int cvb_jpeg_info(const uint8_t* data, int64_t nbytes, int32_t* h, int32_t* w);
+/* Host only: the entropy-decoding half alone (tests): quantised coefficients int16 [Y blocks (H/8 x W/8, row-major) | Cb
+ * blocks | Cr blocks][64] in natural order (H*W*3/2 values) and the three quantisation tables u16 [3][64] (may be NULL). */
+CVB_API int cvb_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* coef, uint16_t* qt);
+/* data[i] / nbytes[i]: N JPEG streams in HOST memory, all H x W; img: DEVICE u8 [N,H,W,3] BGR.  The host buffers may be
+ * released on return; the device work is enqueued on `stream`.  Staging buffers are sized on first use. */
+CVB_API int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nbytes, int N, int H, int W, uint8_t* img,
+                            void* stream);
+
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 CVB_API int64_t cvb_launch_count(const cvb_ctx* ctx);
 
