@@ -284,10 +284,78 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_decode(args):
+    """--workload decode: the JPEG front-end on the reference's data/test files, cycled to `--boards`
+    images per step.  `value` = files -> pixels in HBM through the public call (host Huffman threads + H2D of the
+    coefficients + CUDA inverse DCT / upsampling / colour conversion; the device work of chunk i overlaps the host work
+    of chunk i+1), so value and e2e coincide and the host half (`host_ms_per_step`) is what bounds it.  The two kernels'
+    own durations are in the ncu launch list under profiles/ (they are not separable from the host half by events
+    around the public call), so `roofline.achieved` is left null here."""
+    import cv2
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from chessvision import _native
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.cuda.set_device(local_rank)
+    eng = _native.Engine(local_rank, max_batch=4)
+    files = sorted((ROOT / "tests" / "golden" / "data_test").glob("*/*"))
+    base = [f.read_bytes() for f in files]
+    n = args.boards
+    streams = [base[i % len(base)] for i in range(n)]
+    for _ in range(args.warmup):
+        img = eng.decode_jpeg(streams)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count()
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            img = eng.decode_jpeg(streams)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1000.0 / args.steps
+    launches = eng.launch_count() - l0
+    ref = cv2.imdecode(np.frombuffer(streams[0], np.uint8), cv2.IMREAD_COLOR)
+    assert np.array_equal(img[0].cpu().numpy(), ref), "decode differs from cv2.imdecode"
+    # the host half alone (entropy decoding, same thread count as the library uses)
+    threads = min(os.cpu_count() or 4, 32)
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(_native.jpeg_coefficients, streams[: 4 * threads]))
+        host_ms = (time.perf_counter() - t0) * 1000.0 * n / (4 * threads)
+    # CPU baseline: cv2.imdecode (what the reference calls) on all host cores
+    cv2.setNumThreads(1)
+    sample = (streams * (1 + 8192 // len(streams)))[:8192]              # bounded sample: ~8k decodes, a few seconds of CPU work
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda b: cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR), sample[:threads]))
+        t0 = time.perf_counter()
+        list(ex.map(lambda b: cv2.imdecode(np.frombuffer(b, np.uint8), cv2.IMREAD_COLOR), sample, chunksize=16))
+        cpu_s = time.perf_counter() - t0
+    _, hbm, src = measured_peaks()
+    px = 512 * 512
+    print(json.dumps({
+        "metric": "JPEG decode images/sec (files -> u8 BGR in HBM)", "value": n / (ms / 1000.0), "unit": "images/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 / u8", "data": "the reference's 38 data/test JPEGs (512x512, 4:2:0), cycled",
+        "config": {"workload": "8(f) n2: JPEG decode front-end", "images_per_step": n, "host_threads": threads,
+                   "l2": f"coefficients + pixels of one step ({n} x 1.5 MB) exceed L2, no flush"},
+        "e2e": {"value": n / (ms / 1000.0), "unit": "images/s", "h2d_bytes_per_step": int(n * px * 3), "d2h_bytes_per_step": 0,
+                "host_ms_per_step": host_ms},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_jpeg_idct + k_jpeg_color", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
+                     "traffic": None, "peak_source": src, "algorithmic_bytes_per_image": 9 * px,
+                     "note": "idct: 3 B/px coefficients in + 1.5 out; colour: 1.5 in + 3 out; per-launch durations: profiles/ ncu launch list"},
+        "cpu_baseline": {"value": len(sample) / cpu_s, "unit": "images/s", "cores": threads, "kind": "reference",
+                         "sample": f"cv2.imdecode of {len(sample)} of the same files on {threads} threads ({cpu_s:.1f} s)"},
+        "clocks": clk.summary()}), flush=True)
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "train"],
-                    help="pipeline = BASELINE.json's metric (configs[3]); train = UNet training step (configs[4])")
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "train", "decode"],
+                    help="pipeline = BASELINE.json's metric (configs[3]); train = UNet training step (configs[4]); decode = JPEG front-end")
     ap.add_argument("--train-batch", type=int, default=8, help="--workload train: images per GPU per step")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -302,6 +370,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_train_reference(args) if args.workload == "train" else run_reference(args)
+    if args.workload == "decode":
+        return run_decode(args)
     if args.workload == "train":
         return run_train(args)
 

@@ -35,6 +35,9 @@ struct HuffTable {
     int32_t valoff[17];    // symbol index of the first code of each length minus that code
     uint8_t symbols[256];
     uint16_t look[256];    // 8-bit lookahead: (length << 8) | symbol, 0 = longer than 8 bits
+    // AC tables: 10-bit lookahead that resolves code AND value bits at once when both fit:
+    // (coefficient << 16) | (run << 8) | total bits, 0 = take the general path
+    int32_t fast_ac[1024];
 };
 
 struct JpegHeader {
@@ -64,6 +67,16 @@ void build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, in
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
+    for (int i = 0; i < 1024; ++i) {
+        t.fast_ac[i] = 0;
+        const uint32_t e = t.look[i >> 2];
+        if (!e) continue;
+        const int len = e >> 8, sym = e & 255, run = sym >> 4, mag = sym & 15;
+        if (mag == 0 || len + mag > 10) continue;
+        int v = (i >> (10 - len - mag)) & ((1 << mag) - 1);
+        if (v < (1 << (mag - 1))) v += 1 - (1 << mag);
+        t.fast_ac[i] = (v * 65536) | (run << 8) | (len + mag);
+    }
 }
 
 int exif_orientation(const uint8_t* t, size_t n) {
@@ -157,7 +170,17 @@ struct BitReader {
     size_t n, p;
     uint64_t acc = 0;
     int bits = 0;
-    void fill() {
+    // top up to more than 56 bits; afterwards a Huffman code (<= 16 bits) plus its value bits (<= 15) need no further check
+    inline void refill() {
+        if (bits <= 32 && p + 4 <= n) {   // four bytes at once when none of them is 0xFF
+            const uint32_t w = (static_cast<uint32_t>(d[p]) << 24) | (static_cast<uint32_t>(d[p + 1]) << 16) | (static_cast<uint32_t>(d[p + 2]) << 8) | d[p + 3];
+            if ((((w & 0x7F7F7F7Fu) + 0x01010101u) & w & 0x80808080u) == 0) {   // no byte equals 0xFF
+                acc = (acc << 32) | w;
+                bits += 32;
+                p += 4;
+                return;
+            }
+        }
         while (bits <= 56) {
             uint32_t b = 0;
             if (p < n) {
@@ -174,13 +197,9 @@ struct BitReader {
             bits += 8;
         }
     }
-    inline uint32_t peek(int k) {
-        if (bits < k) fill();
-        return static_cast<uint32_t>(acc >> (bits - k)) & ((1u << k) - 1);
-    }
+    inline uint32_t peek(int k) const { return static_cast<uint32_t>(acc >> (bits - k)) & ((1u << k) - 1); }
     inline void skip(int k) { bits -= k; }
     inline uint32_t get(int k) {
-        if (k == 0) return 0;
         const uint32_t v = peek(k);
         bits -= k;
         return v;
@@ -193,16 +212,20 @@ struct BitReader {
     }
 };
 
+// caller guarantees at least 32 buffered bits
 inline int decode_symbol(BitReader& br, const HuffTable& t) {
     const uint32_t look = t.look[br.peek(8)];
     if (look) {
         br.skip(look >> 8);
         return look & 255;
     }
-    int code = static_cast<int>(br.get(8));
+    int code = static_cast<int>(br.peek(9));
     for (int len = 9; len <= 16; ++len) {
-        code = (code << 1) | static_cast<int>(br.get(1));
-        if (code <= t.maxcode[len]) return t.symbols[(t.valoff[len] + code) & 255];
+        if (code <= t.maxcode[len]) {
+            br.skip(len);
+            return t.symbols[(t.valoff[len] + code) & 255];
+        }
+        code = static_cast<int>(br.peek(len + 1));
     }
     return -1;
 }
@@ -227,11 +250,22 @@ int decode_scan(const uint8_t* d, size_t n, const JpegHeader& H, int16_t* coef) 
                                   : plane[c] + (static_cast<size_t>(my) * mw + mx) * 64;
             const HuffTable& dct = H.dc[H.comp_dc[c] & 3];
             const HuffTable& act = H.ac[H.comp_ac[c]];
+            br.refill();
             int s = decode_symbol(br, dct);
             if (s < 0 || s > 15) return -6;
             if (s) pred[c] += extend(static_cast<int>(br.get(s)), s);
             blk[0] = static_cast<int16_t>(pred[c]);
             for (int k = 1; k < 64;) {
+                if (br.bits < 32) br.refill();
+                const int32_t f = act.fast_ac[br.peek(10)];
+                if (f) {
+                    k += (f >> 8) & 15;
+                    if (k > 63) return -6;
+                    br.skip(f & 255);
+                    blk[kZigzag[k]] = static_cast<int16_t>(f >> 16);
+                    ++k;
+                    continue;
+                }
                 const int rs = decode_symbol(br, act);
                 if (rs < 0) return -6;
                 const int r = rs >> 4;

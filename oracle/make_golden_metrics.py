@@ -80,10 +80,17 @@ def install_standins():
 
 
 def load_reference():
+    """Import the two reference scripts unmodified.  sys.path is restored afterwards: a process that keeps /root/reference
+    at its front would hand it to spawned children, which then import the reference's ``chessvision`` instead of ours."""
+    import importlib
     install_standins()
+    saved = list(sys.path)
     sys.path.insert(0, REF)
-    from scripts.eval import evaluate as ref_eval
-    from scripts.process_new_raw import process_pipeline as ref_pipe
+    try:
+        ref_eval = importlib.import_module("scripts.eval.evaluate")
+        ref_pipe = importlib.import_module("scripts.process_new_raw.process_pipeline")
+    finally:
+        sys.path[:] = saved
     assert ref_eval.__file__.startswith(REF) and ref_pipe.__file__.startswith(REF)
     return ref_eval, ref_pipe
 

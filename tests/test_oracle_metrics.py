@@ -74,8 +74,7 @@ def test_golden_vectors_from_the_reference(vec):
 @pytest.mark.reference
 @pytest.mark.skipif(not (REFERENCE / "scripts" / "eval" / "evaluate.py").exists(), reason="reference checkout not present")
 def test_against_the_live_reference():
-    sys.path.insert(0, str(GOLDEN.parent.parent / "oracle"))
-    import make_golden_metrics as gen
+    from oracle import make_golden_metrics as gen
     ref_eval, ref_pipe = gen.load_reference()
     rng = np.random.default_rng(5)
     fens, *_ = gen.make_cases(seed=99)
