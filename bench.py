@@ -453,16 +453,20 @@ def main():
     value = boards_total / (dev_ms / 1000.0)
     e2e_value = boards_total / (e2e_ms / 1000.0)
 
-    # ---- roofline of the dominant kernel: conv_tc_kernel over the UNet layers (20 launches per chunk)
+    # ---- roofline of the dominant kernel class: the tcgen05 implicit-GEMM convs of the UNet (21 launches per chunk).
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of those 21 launches from the ncu --set full capture of one
+    # 128-board pass (profiles/r01/ncu_full_summary.md: 17.52 GB), per launch, scaled to this run's chunk; the
+    # algorithmic bytes (every layer's input and output once, fp16 NHWC) are 868 MB per launch at chunk 128.
     peak_tf, peak_hbm, peak_src = measured_peaks()
     unet_tc_ms = stages["unet_conv_tc"]
     tc_flops = (UNET_GFLOP - UNET_STEM_GFLOP) * 1e9 * B * args.steps
     achieved = tc_flops / (unet_tc_ms / 1000.0) / 1e12 if unet_tc_ms > 0 else 0.0
     chunks = (B + args.chunk - 1) // args.chunk
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (UNet layers, tcgen05 implicit GEMM)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
-                "launches": 20 * chunks * args.steps, "avg_launch_ms": unet_tc_ms / max(1, 20 * chunks * args.steps),
-                "algorithmic_gflop_per_board": UNET_GFLOP - UNET_STEM_GFLOP}
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel / conv3x3_vr_kernel / conv3x3_rs_kernel (UNet layers, tcgen05 implicit GEMM)", "achieved": achieved, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": 834.3e6 * args.chunk / 128,
+                "traffic_unit": "bytes per launch (ncu capture profiles/r01, not re-measured in this run)", "peak_source": peak_src,
+                "launches": 21 * chunks * args.steps, "avg_launch_ms": unet_tc_ms / max(1, 21 * chunks * args.steps),
+                "algorithmic_gflop_per_board": UNET_GFLOP - UNET_STEM_GFLOP, "algorithmic_bytes_per_launch": 868.0e6 * args.chunk / 128}
     stage_share = {k: v / max(1e-9, sum(stages.values())) for k, v in stages.items()}
     # second named metric of BASELINE.json: warp + 64-square crop against the measured HBM copy bandwidth
     # (algorithmic bytes per board: 786,432 read + 262,144 written); stage = k_homography + k_warp_board
