@@ -432,26 +432,29 @@ __global__ void __launch_bounds__(256) k_jpeg_color(const uint8_t* __restrict__ 
 }  // namespace
 }  // namespace cvb
 
-// Lazily sized staging (pinned host + device) for chunks of images; owned by the context.
+// Lazily sized staging for chunks of images; owned by the context.  Two pinned host buffers so that the host decodes
+// chunk i+1 while chunk i is on its way to the device; the device side is ordered by the stream.
+constexpr int kJpegChunk = 128;
 struct cvb_jpeg_state {
-    int16_t* h_coef = nullptr;
-    uint16_t* h_qt = nullptr;
+    int16_t* h_coef[2] = {nullptr, nullptr};
+    uint16_t* h_qt[2] = {nullptr, nullptr};
     int16_t* d_coef = nullptr;
     uint16_t* d_qt = nullptr;
     uint8_t* d_planes = nullptr;
-    size_t cap_pixels = 0;   // chunk * H * W the buffers were sized for
-    int chunk = 0;
-    cudaEvent_t done = nullptr;
+    size_t cap_pixels = 0;   // images * H * W the coefficient / plane buffers were sized for
+    cudaEvent_t done[2] = {nullptr, nullptr};
 };
 
 void cvb_jpeg_free(cvb_jpeg_state* s) {
     if (!s) return;
-    if (s->h_coef) cudaFreeHost(s->h_coef);
-    if (s->h_qt) cudaFreeHost(s->h_qt);
+    for (int i = 0; i < 2; ++i) {
+        if (s->h_coef[i]) cudaFreeHost(s->h_coef[i]);
+        if (s->h_qt[i]) cudaFreeHost(s->h_qt[i]);
+        if (s->done[i]) cudaEventDestroy(s->done[i]);
+    }
     if (s->d_coef) cudaFree(s->d_coef);
     if (s->d_qt) cudaFree(s->d_qt);
     if (s->d_planes) cudaFree(s->d_planes);
-    if (s->done) cudaEventDestroy(s->done);
     delete s;
 }
 
@@ -486,28 +489,36 @@ int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nby
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t px = static_cast<size_t>(H) * W;
     const size_t coef_per_image = px * 3 / 2;          // int16 values
-    const int chunk = N < 64 ? N : 64;
+    const int chunk = N < kJpegChunk ? N : kJpegChunk;
     if (!ctx->jpeg) ctx->jpeg = new cvb_jpeg_state();
     cvb_jpeg_state* J = ctx->jpeg;
     if (J->cap_pixels < static_cast<size_t>(chunk) * px) {
-        if (J->h_coef) cudaFreeHost(J->h_coef);
+        for (int i = 0; i < 2; ++i) {
+            if (J->h_coef[i]) cudaFreeHost(J->h_coef[i]);
+            J->h_coef[i] = nullptr;
+        }
         if (J->d_coef) cudaFree(J->d_coef);
         if (J->d_planes) cudaFree(J->d_planes);
-        J->h_coef = nullptr; J->d_coef = nullptr; J->d_planes = nullptr;
+        J->d_coef = nullptr; J->d_planes = nullptr;
         J->cap_pixels = 0;
-        CK(cudaMallocHost(&J->h_coef, chunk * coef_per_image * sizeof(int16_t)));
-        if (!J->h_qt) CK(cudaMallocHost(&J->h_qt, static_cast<size_t>(64) * 3 * 64 * sizeof(uint16_t)));   // tables: always 64 images
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMallocHost(&J->h_coef[i], chunk * coef_per_image * sizeof(int16_t)));
+            if (!J->h_qt[i]) CK(cudaMallocHost(&J->h_qt[i], static_cast<size_t>(kJpegChunk) * 192 * sizeof(uint16_t)));
+            if (!J->done[i]) CK(cudaEventCreateWithFlags(&J->done[i], cudaEventDisableTiming));
+        }
         CK(cudaMalloc(&J->d_coef, chunk * coef_per_image * sizeof(int16_t)));
-        if (!J->d_qt) CK(cudaMalloc(&J->d_qt, static_cast<size_t>(64) * 3 * 64 * sizeof(uint16_t)));
+        if (!J->d_qt) CK(cudaMalloc(&J->d_qt, static_cast<size_t>(kJpegChunk) * 192 * sizeof(uint16_t)));
         CK(cudaMalloc(&J->d_planes, chunk * coef_per_image));
         J->cap_pixels = static_cast<size_t>(chunk) * px;
-        J->chunk = chunk;
-        if (!J->done) CK(cudaEventCreateWithFlags(&J->done, cudaEventDisableTiming));
     }
-    const int cap = static_cast<int>(J->cap_pixels / px) < 64 ? static_cast<int>(J->cap_pixels / px) : 64;
-    for (int off = 0; off < N; off += cap) {
+    const int cap = static_cast<int>(J->cap_pixels / px) < kJpegChunk ? static_cast<int>(J->cap_pixels / px) : kJpegChunk;
+    int used[2] = {0, 0};
+    for (int off = 0, it = 0; off < N; off += cap, ++it) {
         const int n = N - off < cap ? N - off : cap;
-        if (off) CK(cudaEventSynchronize(J->done));   // the previous chunk's H2D copy must have left the pinned buffer
+        const int hb = it & 1;
+        if (used[hb]) CK(cudaEventSynchronize(J->done[hb]));   // the H2D copy issued two chunks ago must have left this buffer
+        int16_t* h_coef = J->h_coef[hb];
+        uint16_t* h_qt = J->h_qt[hb];
         std::atomic<int> next{0}, err{0};
         const char* err_msg = "";
         auto work = [&]() {
@@ -519,9 +530,9 @@ int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nby
                 int rc = cvb::parse_header(data[off + i], static_cast<size_t>(nbytes[off + i]), hd, &msg);
                 if (!rc && (hd.h != H || hd.w != W)) { rc = -6; msg = "image dimensions differ from the batch's H x W"; }
                 if (!rc) {
-                    memset(J->h_coef + i * coef_per_image, 0, coef_per_image * sizeof(int16_t));
-                    memcpy(J->h_qt + static_cast<size_t>(i) * 192, hd.qt, sizeof hd.qt);
-                    rc = cvb::decode_scan(data[off + i], static_cast<size_t>(nbytes[off + i]), hd, J->h_coef + i * coef_per_image);
+                    memset(h_coef + i * coef_per_image, 0, coef_per_image * sizeof(int16_t));
+                    memcpy(h_qt + static_cast<size_t>(i) * 192, hd.qt, sizeof hd.qt);
+                    rc = cvb::decode_scan(data[off + i], static_cast<size_t>(nbytes[off + i]), hd, h_coef + i * coef_per_image);
                     if (rc) msg = "corrupt JPEG: entropy-coded data";
                 }
                 if (rc) { err.store(rc); err_msg = msg; }
@@ -536,9 +547,10 @@ int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nby
         work();
         for (auto& th : pool) th.join();
         if (err.load()) return fail(ctx, err.load(), "cvb_decode_jpeg: %s", err_msg);
-        CK(cudaMemcpyAsync(J->d_coef, J->h_coef, n * coef_per_image * sizeof(int16_t), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(J->d_qt, J->h_qt, static_cast<size_t>(n) * 192 * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
-        CK(cudaEventRecord(J->done, s));
+        CK(cudaMemcpyAsync(J->d_coef, h_coef, n * coef_per_image * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(J->d_qt, h_qt, static_cast<size_t>(n) * 192 * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        CK(cudaEventRecord(J->done[hb], s));
+        used[hb] = 1;
         const long long blocks = static_cast<long long>(n) * (H / 8) * (W / 8) * 3 / 2;
         cvb::k_jpeg_idct<<<static_cast<unsigned>((blocks + 31) / 32), 256, 0, s>>>(J->d_coef, J->d_qt, J->d_planes, H, W, blocks);
         CK(cudaGetLastError());
@@ -547,7 +559,8 @@ int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nby
         CK(cudaGetLastError());
         ctx->launches += 2;
     }
-    CK(cudaEventSynchronize(J->done));   // the caller may reuse / free its JPEG buffers and ours is pinned staging
+    for (int i = 0; i < 2; ++i)
+        if (used[i]) CK(cudaEventSynchronize(J->done[i]));   // the pinned staging is ours, but the caller may free its streams' memory
     return 0;
 }
 
