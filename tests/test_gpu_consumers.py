@@ -86,3 +86,33 @@ def test_quality_scores_on_pipeline_logits(engine):
     for i in range(5):
         assert abs(scores[i, 2] - om.probability_distribution(logits[i])) <= 1e-12
         assert abs(scores[i, 3] - om.probability_confidence(logits[i])) <= 2e-6 * abs(scores[i, 3])
+
+
+def test_data_test_accuracy_from_device_outputs_equals_the_oracle():
+    """The reference's evaluation flow (scripts/eval/evaluate.py:227-330) end to end on the device — decode, image->FEN,
+    metrics — against the oracle's metrics on the REFERENCE's outputs for the same 38 files (golden vectors)."""
+    import json
+    from conftest import WEIGHTS
+    from chessvision import ChessVision, decode, evaluation
+    man = json.load(open(GOLDEN / "manifest.json"))["images"]
+    arr = np.load(GOLDEN / "reference_outputs.npz")
+    cv = ChessVision(board_extractor_weights=str(WEIGHTS / "best_extractor.pth"), classifier_weights=str(WEIGHTS / "best_classifier.pth"),
+                     classifier_model_id="resnet18", lazy_load=False, max_batch=64)
+    eng = cv._engine
+    files = [GOLDEN / "data_test" / e["file"] for e in man]
+    fens = [e["ground_truth_fen"].split()[0] for e in man]
+    out = eng.image_to_fen(decode.imread_batch(files, engine=eng), eng.alloc_outputs(len(files)))
+    hits, correct = evaluation.evaluate_batch(out["probs"], out["labels"], out["labels_valid"], fens, k=3, engine=eng)
+    found = out["found"].cpu().numpy().astype(bool)
+    top1 = top3 = tot = 0
+    for i, e in enumerate(man):
+        assert found[i] == e["found"]
+        if not e["found"]:
+            continue
+        want = om.topk_hits(arr[f"probs_{i}"].astype(np.float32), fens[i], 3)
+        assert int(hits[i, 0]) == want[0], e["file"]                      # labels are bit-identical, so top-1 is too
+        assert abs(int(hits[i, 1]) - want[1]) <= 1 and abs(int(hits[i, 2]) - want[2]) <= 1, e["file"]   # near-ties of 2nd/3rd rank
+        assert int(correct[i, 0]) == om.position_correct(e["original_fen"], fens[i])
+        assert int(correct[i, 1]) == om.position_correct(e["fen"], fens[i])
+        top1 += int(hits[i, 0]); top3 += int(hits[i, 2]); tot += 64
+    print(f"data/test from device outputs: top-1 {top1 / tot:.4f}, top-3 {top3 / tot:.4f} over {tot // 64} boards")
