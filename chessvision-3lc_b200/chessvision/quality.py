@@ -1,7 +1,7 @@
 """Extraction quality scores of the reference's enrichment pipeline —
 ``scripts/process_new_raw/process_pipeline.py:357-378,416-467`` with the same names, computed by ``cvb_quality_scores`` on
-the device.  ``mask_completeness`` (``:380-414``, needs the filled largest external contour) is not
-built; calling it raises.  No CPU fallback.
+the device; ``mask_completeness`` is defined for 256x256 arrays (the shape the reference passes).
+No CPU fallback.
 """
 from __future__ import annotations
 
@@ -16,7 +16,8 @@ def _engine():
 
 def quality_scores_batch(values, quad=None, found=None, engine=None) -> np.ndarray:
     """values f32[N,...] device tensor (the reference passes ``BoardExtractionResult.probabilities``), quad f32[N,4,2]
-    -> f64[N,4] = (quadrangle_regularity, NaN, probability_distribution, probability_confidence)."""
+    -> f64[N,4] = (quadrangle_regularity, mask_completeness (NaN unless the arrays are 256x256), probability_distribution,
+    probability_confidence)."""
     eng = engine or _engine()
     return eng.quality_scores(values, quad, found).cpu().numpy()
 
@@ -48,5 +49,7 @@ def quadrangle_regularity(quadrangle: np.ndarray | None) -> float:
 
 
 def mask_completeness(mask: np.ndarray) -> float:
-    """process_pipeline.py:380-414 — not part of the B200 path yet."""
-    raise NotImplementedError("mask_completeness is not built on the B200 path (see DESIGN.md)")
+    """process_pipeline.py:380-414 for a 256x256 array."""
+    if np.asarray(mask).shape != (256, 256):
+        raise NotImplementedError("mask_completeness on the B200 path takes the 256x256 array the reference passes")
+    return float(_one(mask)[1])

@@ -158,10 +158,10 @@ CVB_API int cvb_wgrad3x3_f16(cvb_ctx* ctx, const void* dz, const void* x, int N,
  * with the truth (compute_position_accuracy.num_correct); flip = the orientation the labels were produced with. */
 CVB_API int cvb_eval_metrics(cvb_ctx* ctx, const float* probs, const uint8_t* labels, const uint8_t* labels_valid,
                              const uint8_t* true_labels, int N, int flip, int k, int32_t* topk_hits, int32_t* correct, void* stream);
-/* scripts/process_new_raw/process_pipeline.py:357-378,416-467 for N boards.  values f32 [N,L] (the reference passes
+/* scripts/process_new_raw/process_pipeline.py:357-467 for N boards.  values f32 [N,L] (the reference passes
  * BoardExtractionResult.probabilities, L = 65536); quad f32 [N,4,2] (may be NULL) with found u8 [N] (may be NULL);
- * scores f64 [N,4] = {quadrangle_regularity, NaN (mask_completeness is not computed), probability_distribution,
- * probability_confidence}. */
+ * scores f64 [N,4] = {quadrangle_regularity, mask_completeness (process_pipeline.py:380-414; defined for L = 256*256,
+ * NaN otherwise), probability_distribution, probability_confidence}. */
 CVB_API int cvb_quality_scores(cvb_ctx* ctx, const float* values, const float* quad, const uint8_t* found, int N, int L,
                                double* scores, void* stream);
 

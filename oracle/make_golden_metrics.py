@@ -132,6 +132,33 @@ def make_cases(seed=20261017):
     return fens, probs, pred_fens, arrays, quads
 
 
+def completeness_cases(seed=7):
+    """256x256 masks for mask_completeness: holes, nested components, specks, thin lines, border contact, ties, empty, full."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    out = []
+    m = np.zeros((256, 256), np.float32); cv2.circle(m, (128, 128), 90, 1, -1); cv2.circle(m, (128, 128), 50, 0, -1); cv2.circle(m, (128, 128), 20, 1, -1)
+    m[rng.random(m.shape) > 0.985] = 1
+    out.append(m)                                                      # ring with a nested blob + specks
+    out.append((rng.random((256, 256)) > 0.6).astype(np.float32))      # dense noise: hundreds of components
+    out.append((rng.random((256, 256)) > 0.3).astype(np.float32))      # one percolating component with many holes
+    m = np.zeros((256, 256), np.float32)
+    for _ in range(12):
+        p = rng.integers(0, 256, 4); cv2.line(m, (int(p[0]), int(p[1])), (int(p[2]), int(p[3])), 1, 1)
+    out.append(m)                                                      # one-pixel-wide lines (doubly traversed borders)
+    m = np.zeros((256, 256), np.float32); m[:, :40] = 1; m[200:, :] = 1; m[60:120, 100:160] = 1; m[80:100, 120:140] = 0
+    out.append(m)                                                      # components touching the image border
+    m = np.zeros((256, 256), np.float32); m[10:40, 10:40] = 1; m[100:130, 50:80] = 1; m[200:230, 200:230] = 1
+    out.append(m)                                                      # three components of equal area: the tie rule
+    m = np.zeros((256, 256), np.float32); m[5, 5] = m[9, 200] = m[250, 3] = 1
+    out.append(m)                                                      # isolated pixels only (all areas 0)
+    out.append(np.zeros((256, 256), np.float32))                       # empty
+    out.append(np.ones((256, 256), np.float32))                        # full
+    m = np.zeros((256, 256), np.float32); m[0, :] = m[-1, :] = m[:, 0] = m[:, -1] = 1; m[100:150, 100:150] = 1
+    out.append(m)                                                      # a frame around everything: the inner blob is nested in its hole
+    return out
+
+
 def main():
     ref_eval, ref_pipe = load_reference()
     from oracle import metrics as om
@@ -147,6 +174,12 @@ def main():
         assert om.fen_to_labels(fen) == ref_eval.board_to_labels(sys.modules["chess"].BaseBoard(fen))
         assert om.label_indices(p, fen) == ref_eval.get_label_indices(p, fen)
         assert om.fen_to_indices(fen) == ref_eval.get_validated_indices(fen)
+    import cv2
+    ref_pipe.cv2 = cv2                                    # the stand-in loader may have mocked nothing here: cv2 is installed
+    comp_arrays = arrays + completeness_cases()
+    comp = np.array([ref_pipe.mask_completeness(a) for a in comp_arrays])
+    for i, a in enumerate(comp_arrays):
+        assert om.mask_completeness(a) == comp[i], (i, om.mask_completeness(a), comp[i])
     dist = np.array([ref_pipe.probability_distribution(a) for a in arrays])
     conf = np.array([ref_pipe.probability_confidence(a) for a in arrays])
     reg = np.array([ref_pipe.quadrangle_regularity(q) for q in quads])
@@ -159,7 +192,8 @@ def main():
     out = os.path.join(ROOT, "tests", "golden", "metrics_vectors.npz")
     np.savez_compressed(out, fens=np.array(fens), pred_fens=np.array(pred_fens), probs=np.stack(probs), topk_hits=hits,
                         correct=correct, arrays=np.stack(arrays).astype(np.float16 if False else np.float32), distribution=dist,
-                        confidence=conf, quads=np.stack(quads), regularity=reg)
+                        confidence=conf, quads=np.stack(quads), regularity=reg,
+                        completeness_masks=np.packbits(np.stack(comp_arrays[len(arrays):]) > 0.5, axis=-1), completeness=comp)
     print("wrote", out, os.path.getsize(out), "bytes;", len(fens), "positions,", len(arrays), "arrays,", len(quads), "quadrangles")
 
 

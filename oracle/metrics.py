@@ -85,6 +85,62 @@ def probability_distribution(mask: np.ndarray) -> float:
     return float(1.0 - (entropy / -np.log2(1 / 10)))
 
 
+def external_components(binary: np.ndarray):
+    """What ``cv2.findContours(binary, RETR_EXTERNAL, ...)`` returns, in ITS order, as (outer border points, first pixel):
+    the outer borders of the 8-connected components that are not enclosed by a hole of another component (Suzuki-Abe
+    border following; an outer border is top-level if the last border met on its row is the frame, or — transitively — a
+    top-level outer border), listed in REVERSE discovery order [pinned against live cv2 in tests/test_oracle_metrics.py]."""
+    from . import geometry as og
+    h, w = binary.shape
+    lab = np.zeros((h + 2, w + 2), np.int32)
+    lab[1:-1, 1:-1] = binary != 0
+    kind, out, nbd = {}, [], 1
+    for y in range(1, h + 1):
+        last = 0
+        row = lab[y]
+        for x in range(1, w + 1):
+            p, prev = int(row[x]), int(row[x - 1])
+            start = None
+            if prev == 0 and p == 1:
+                start = (x, False)
+            elif p == 0 and prev >= 1:
+                start = (x - 1, True)
+                if prev > 1:
+                    last = prev
+            if start is not None:
+                nbd += 1
+                pts, _ = og._follow(lab, start[0], y, nbd, start[1])
+                if start[1]:
+                    kind[nbd] = (True, False)
+                else:
+                    ext = True if last == 0 else (False if kind[last][0] else kind[last][1])
+                    kind[nbd] = (False, ext)
+                    if ext:
+                        out.append((pts, (start[0] - 1, y - 1)))
+            v = int(row[x])
+            if v != 0 and v != 1:
+                last = abs(v)
+    return out[::-1]
+
+
+def mask_completeness(mask: np.ndarray) -> float:
+    """process_pipeline.py:380-414: (#pixels > 0.5) / (#pixels of the filled largest external contour).  ``max(contours,
+    key=cv2.contourArea)`` keeps the first of equal areas; ``drawContours(..., thickness=-1)`` of an outer border paints the
+    component and everything it encloses (= the complement of the background that stays 4-connected to the frame when
+    only that component blocks)."""
+    from scipy import ndimage
+    from . import geometry as og
+    binary = np.asarray(mask) > 0.5
+    ext = external_components(binary.astype(np.uint8))
+    if not ext:
+        return 0.0
+    areas = [og.contour_area(p) for p, _ in ext]
+    sx, sy = ext[int(np.argmax(areas))][1]
+    lab8, _ = ndimage.label(binary, structure=np.ones((3, 3)))
+    filled = ndimage.binary_fill_holes(lab8 == lab8[sy, sx])
+    return float(binary.sum()) / float(filled.sum())
+
+
 def probability_confidence(probabilities: np.ndarray) -> float:
     """process_pipeline.py:459-467: mean |p - 0.5| * 2 over the top quarter of the values (largest p)."""
     flat = np.asarray(probabilities).ravel()

@@ -67,7 +67,9 @@ def test_quality_scores_golden(engine, vec):
     # pairwise sum in numpy and a float64 sum here: 2e-6 relative
     assert np.allclose(scores[:, 2], vec["distribution"], rtol=0, atol=1e-12), (scores[:, 2], vec["distribution"])
     assert np.allclose(scores[:, 3], vec["confidence"], rtol=2e-6, atol=0), (scores[:, 3], vec["confidence"])
-    assert np.isnan(scores[:, 1]).all()
+    masks = np.concatenate([vec["arrays"], np.unpackbits(vec["completeness_masks"], axis=-1).astype(np.float32)])
+    comp = engine.quality_scores(torch.from_numpy(masks).cuda()).cpu().numpy()[:, 1]
+    assert np.array_equal(comp, vec["completeness"]), (comp, vec["completeness"])     # a ratio of two pixel counts: exact
     quads = torch.from_numpy(vec["quads"].reshape(-1, 4, 2)).cuda()
     dummy = torch.zeros((quads.shape[0], 16), dtype=torch.float32, device="cuda")
     reg = engine.quality_scores(dummy, quads).cpu().numpy()[:, 0]
@@ -84,6 +86,7 @@ def test_quality_scores_on_pipeline_logits(engine):
     logits[2, :128] = 0.5                           # a large tie group straddling the top-quarter threshold
     scores = engine.quality_scores(torch.from_numpy(logits).cuda()).cpu().numpy()
     for i in range(5):
+        assert scores[i, 1] == om.mask_completeness(logits[i])
         assert abs(scores[i, 2] - om.probability_distribution(logits[i])) <= 1e-12
         assert abs(scores[i, 3] - om.probability_confidence(logits[i])) <= 2e-6 * abs(scores[i, 3])
 
@@ -116,3 +119,30 @@ def test_data_test_accuracy_from_device_outputs_equals_the_oracle():
         assert int(correct[i, 1]) == om.position_correct(e["fen"], fens[i])
         top1 += int(hits[i, 0]); top3 += int(hits[i, 2]); tot += 64
     print(f"data/test from device outputs: top-1 {top1 / tot:.4f}, top-3 {top3 / tot:.4f} over {tot // 64} boards")
+
+
+def test_mask_completeness_random_masks(engine):
+    """Bit-exact against the oracle (itself equal to the reference function + live cv2) on masks built to break contour
+    code: noise at every density, blobs with holes and islands, single-pixel bridges, everything on the image border."""
+    from scipy import ndimage
+    rng = np.random.default_rng(21)
+    masks = []
+    for i in range(24):
+        kind = i % 4
+        if kind == 0:
+            m = rng.random((256, 256)) > 0.2 + 0.03 * i
+        elif kind == 1:
+            m = ndimage.gaussian_filter(rng.normal(size=(256, 256)), 2 + i % 5) > 0.01 * (i - 12)
+        elif kind == 2:
+            m = ndimage.gaussian_filter(rng.normal(size=(256, 256)), 6) > 0
+            m ^= rng.random((256, 256)) > 0.995
+        else:
+            m = np.zeros((256, 256), bool)
+            m[::2, ::2] = True                     # a lattice of isolated pixels ...
+            m[100:140, 90:170] = True              # ... around one block, plus diagonal one-pixel bridges
+            idx = np.arange(60)
+            m[140 + idx, 170 + idx] = True
+        masks.append(m.astype(np.float32))
+    got = engine.quality_scores(torch.from_numpy(np.stack(masks)).cuda()).cpu().numpy()[:, 1]
+    for i, m in enumerate(masks):
+        assert got[i] == om.mask_completeness(m), i

@@ -65,6 +65,9 @@ def test_golden_vectors_from_the_reference(vec):
     for i, a in enumerate(vec["arrays"]):
         assert om.probability_distribution(a) == vec["distribution"][i]
         assert om.probability_confidence(a) == vec["confidence"][i]
+    masks = [a for a in vec["arrays"]] + [m.astype(np.float32) for m in np.unpackbits(vec["completeness_masks"], axis=-1)]
+    for i, m in enumerate(masks):
+        assert om.mask_completeness(m) == vec["completeness"][i], i
     for i, q in enumerate(vec["quads"]):
         got, want = om.quadrangle_regularity(q), vec["regularity"][i]
         assert got == want or (np.isnan(got) and np.isnan(want))
@@ -85,3 +88,9 @@ def test_against_the_live_reference():
         a = rng.normal(size=(64, 64)).astype(np.float32)
         assert om.probability_distribution(a) == ref_pipe.probability_distribution(a)
         assert om.probability_confidence(a) == ref_pipe.probability_confidence(a)
+    import cv2
+    ref_pipe.cv2 = cv2
+    for seed in range(12):                                  # small random masks: noise at several densities, blobs
+        r = np.random.default_rng(seed)
+        m = (r.random((48, 64)) > (0.3 + 0.05 * seed)).astype(np.float32)
+        assert om.mask_completeness(m) == ref_pipe.mask_completeness(m), seed
