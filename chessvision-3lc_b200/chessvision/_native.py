@@ -54,6 +54,9 @@ SYMBOLS = {
     "cvb_warp_squares": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
     "cvb_classify": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "cvb_image_to_fen": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs), _P]),
+    "cvb_image_to_fen_hw": (_I, [_P, _P, _I, _I, _I, _F, _I, C.POINTER(_Outputs), _P]),
+    "cvb_unet_forward_hw": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P]),
+    "cvb_resize_area": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "cvb_image_to_fen_host": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs)]),
     "cvb_conv2d_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P]),
@@ -170,12 +173,21 @@ class Engine:
         return out
 
     def unet_forward(self, img, threshold=0.5):
-        n = img.shape[0]
-        assert img.dtype == torch.uint8 and tuple(img.shape[1:]) == (512, 512, 3) and img.is_contiguous()
+        """img u8[N,H,W,3] (any H, W >= 256) -> logits f32[N,256,256], mask u8[N,256,256]."""
+        n, h, w = img.shape[:3]
+        assert img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3 and img.is_contiguous()
         logits = torch.empty((n, 256, 256), dtype=torch.float32, device=self.device)
         mask = torch.empty((n, 256, 256), dtype=torch.uint8, device=self.device)
-        self._ck(self.lib.cvb_unet_forward(self.h, _ptr(img), n, threshold, _ptr(logits), _ptr(mask), _stream()), "cvb_unet_forward")
+        self._ck(self.lib.cvb_unet_forward_hw(self.h, _ptr(img), n, h, w, threshold, _ptr(logits), _ptr(mask), _stream()), "cvb_unet_forward_hw")
         return logits, mask
+
+    def resize_area(self, img):
+        """cv2.resize(img, (256, 256), interpolation=cv2.INTER_AREA) for u8[N,H,W,3], H, W >= 256."""
+        n, h, w = img.shape[:3]
+        assert img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3 and img.is_contiguous()
+        out = torch.empty((n, 256, 256, 3), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_resize_area(self.h, _ptr(img), n, h, w, _ptr(out), _stream()), "cvb_resize_area")
+        return out
 
     def mask_from_logits(self, logits, threshold=0.5):
         n = logits.shape[0]
@@ -235,10 +247,14 @@ class Engine:
         return o
 
     def image_to_fen(self, img, out, threshold=0.5, flip=False):
-        n = img.shape[0]
-        assert img.is_cuda and img.dtype == torch.uint8 and tuple(img.shape[1:]) == (512, 512, 3) and img.is_contiguous()
+        """img u8[N,H,W,3] on the device; 512 x 512 takes the fused path, any other size >= 256 x 256 the general one."""
+        n, h, w = img.shape[:3]
+        assert img.is_cuda and img.dtype == torch.uint8 and img.dim() == 4 and img.shape[3] == 3 and img.is_contiguous()
         o = self._outputs_struct(out)
-        self._ck(self.lib.cvb_image_to_fen(self.h, _ptr(img), n, threshold, int(flip), C.byref(o), _stream()), "cvb_image_to_fen")
+        if (h, w) == (512, 512):
+            self._ck(self.lib.cvb_image_to_fen(self.h, _ptr(img), n, threshold, int(flip), C.byref(o), _stream()), "cvb_image_to_fen")
+        else:
+            self._ck(self.lib.cvb_image_to_fen_hw(self.h, _ptr(img), n, h, w, threshold, int(flip), C.byref(o), _stream()), "cvb_image_to_fen_hw")
         return out
 
     def image_to_fen_host(self, img_host, out_host, threshold=0.5, flip=False):

@@ -5,8 +5,10 @@ Same constructor, methods, static helpers, attributes and error behaviour (``Ass
 fields when no board is found).  Added: :meth:`ChessVision.process_images` for batches.  Everything the reference
 computes with PyTorch-eager or OpenCV runs on the GPU here; there is no CPU fallback (a missing library or GPU raises).
 
-Limitation (documented in DESIGN.md): the fused preprocessing implements the exact 2x INTER_AREA reduction, i.e. input
-images must be 512x512x3 like every image under the reference's ``data/test``.
+Input sizes: 512x512x3 (every image under the reference's ``data/test``) takes the fused path; any other size of at least
+256x256 goes through the general INTER_AREA reduction, bit-identical to ``cv2.resize``; smaller images (an enlargement,
+which OpenCV does not do with INTER_AREA arithmetic) raise ``NotImplementedError``.  ``process_images`` groups a list of
+differently sized images by size.
 """
 from __future__ import annotations
 
@@ -154,18 +156,33 @@ class ChessVision:
         return self.process_images([image], threshold, flip)[0]
 
     def process_images(self, images, threshold: float = 0.5, flip: bool = False) -> list[ChessVisionResult]:
-        """Batched ``process_image``: u8[N,512,512,3] (or a list of u8[512,512,3]) -> N results.  One host->device copy
+        """Batched ``process_image``: u8[N,H,W,3] (or a list of u8[H,W,3], sizes may differ) -> N results.  One host->device copy
         of the images and one device->host copy of the results; everything in between stays on the GPU."""
         start = time.time()
-        batch = np.ascontiguousarray(np.stack(list(images)) if not isinstance(images, np.ndarray) else images)
+        if not isinstance(images, np.ndarray):
+            images = list(images)
+            sizes = {im.shape[:2] for im in images}
+            if len(sizes) > 1:   # one native call per image size, results back in the caller's order
+                results: list = [None] * len(images)
+                for hw in sizes:
+                    idx = [i for i, im in enumerate(images) if im.shape[:2] == hw]
+                    for i, r in zip(idx, self.process_images(np.stack([images[i] for i in idx]), threshold, flip)):
+                        results[i] = r
+                return results
+            images = np.stack(images)
+        batch = np.ascontiguousarray(images)
         assert batch.dtype == np.uint8 and batch.ndim == 4 and batch.shape[3] == 3, "Images must be uint8 [N,H,W,3]"
-        if batch.shape[1:3] != (512, 512):
-            raise NotImplementedError(f"B200 path supports 512x512 inputs (got {batch.shape[1:3]}); see DESIGN.md")
+        if min(batch.shape[1:3]) < 256:
+            raise NotImplementedError(f"B200 path needs images of at least 256x256 (got {batch.shape[1:3]}); see DESIGN.md")
         self.board_extractor, self.classifier  # noqa: B018  (lazy initialisation)
         eng, n = self._engine, batch.shape[0]
         host_in = torch.from_numpy(batch)
-        out = eng.alloc_outputs(n, full=True, pinned_host=True)
-        eng.image_to_fen_host(host_in, out, threshold, flip)
+        if batch.shape[1:3] == (512, 512):
+            out = eng.alloc_outputs(n, full=True, pinned_host=True)
+            eng.image_to_fen_host(host_in, out, threshold, flip)
+        else:
+            dev = eng.image_to_fen(host_in.to(eng.device), eng.alloc_outputs(n, full=True), threshold, flip)
+            out = {k: v.cpu() for k, v in dev.items()}
         names = constants.SQUARE_NAMES_FLIPPED if flip else constants.SQUARE_NAMES_NORMAL
         fens = _native.fen_strings(out["fen"])
         results = []
@@ -176,7 +193,7 @@ class ChessVision:
             board = None
             position = None
             if found:
-                quad = self._scale_quadrangle(out["quad"][i].numpy().reshape(4, 1, 2), (512, 512))
+                quad = self._scale_quadrangle(out["quad"][i].numpy().reshape(4, 1, 2), batch.shape[1:3])
                 board = out["board"][i].numpy().copy()
                 probs = out["probs"][i].numpy().copy()
                 labels = [constants.LABEL_NAMES[k] for k in out["labels"][i].tolist()]
@@ -192,8 +209,8 @@ class ChessVision:
     def extract_board(self, image: NDArray[np.uint8], threshold: float = 0.5) -> BoardExtractionResult:
         """core.py:197-223."""
         assert isinstance(image, np.ndarray) and image.dtype == np.uint8 and image.ndim == 3
-        if image.shape[:2] != (512, 512):
-            raise NotImplementedError(f"B200 path supports 512x512 inputs (got {image.shape[:2]}); see DESIGN.md")
+        if min(image.shape[:2]) < 256:
+            raise NotImplementedError(f"B200 path needs images of at least 256x256 (got {image.shape[:2]}); see DESIGN.md")
         self.board_extractor  # noqa: B018
         eng = self._engine
         dev_img = torch.from_numpy(np.ascontiguousarray(image[None])).to(eng.device)

@@ -10,6 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cmath>
+#include <algorithm>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -193,6 +196,93 @@ int run_conv(cvb_ctx* ctx, ConvLaunch& L, int n, cudaStream_t s) {
     return 0;
 }
 
+// OpenCV's computeResizeAreaTab (imgproc/resize.cpp) for one axis, in its own double arithmetic: per destination index the
+// source cells it covers (a partial cell on the left, whole cells, a partial cell on the right) with float32 weights.
+void area_table(int ssize, int dsize, double scale, std::vector<int>& ofs, std::vector<int>& si, std::vector<float>& alpha) {
+    ofs.assign(1, 0);
+    si.clear();
+    alpha.clear();
+    for (int d = 0; d < dsize; ++d) {
+        const double f1 = d * scale, f2 = f1 + scale;
+        const double cell = std::min(scale, ssize - f1);
+        int s1 = static_cast<int>(std::ceil(f1)), s2 = static_cast<int>(std::floor(f2));
+        s2 = std::min(s2, ssize - 1);
+        s1 = std::min(s1, s2);
+        if (s1 - f1 > 1e-3) {
+            si.push_back(s1 - 1);
+            alpha.push_back(static_cast<float>((s1 - f1) / cell));
+        }
+        for (int sx = s1; sx < s2; ++sx) {
+            si.push_back(sx);
+            alpha.push_back(static_cast<float>(1.0 / cell));
+        }
+        if (f2 - s2 > 1e-3) {
+            si.push_back(s2);
+            alpha.push_back(static_cast<float>(std::min(std::min(f2 - s2, 1.), cell) / cell));
+        }
+        ofs.push_back(static_cast<int>(si.size()));
+    }
+}
+
+// Tables + staging images for inputs of H x W != 512 x 512 (H, W >= 256), (re)built when the size changes.
+int prepare_size(cvb_ctx* ctx, int H, int W) {
+    if (H < 256 || W < 256) return fail(ctx, -5, "input images must be at least 256 x 256 (INTER_AREA is built for reductions only)");
+    if (ctx->gs_H == H && ctx->gs_W == W) return 0;
+    CK(cudaDeviceSynchronize());   // a previous size's tables may still be in use
+    const double fx = static_cast<double>(W) / 256, fy = static_cast<double>(H) / 256;
+    const int ix = static_cast<int>(std::lrint(fx)), iy = static_cast<int>(std::lrint(fy));
+    const bool fast = std::abs(fx - ix) < 2.220446049250313e-16 && std::abs(fy - iy) < 2.220446049250313e-16;
+    std::vector<int> xo, xs, yo, ys;
+    std::vector<float> xa, ya;
+    area_table(W, 256, fx, xo, xs, xa);
+    area_table(H, 256, fy, yo, ys, ya);
+    auto up = [&](auto** dst, const auto& v) -> int {
+        using T = typename std::remove_reference<decltype(v[0])>::type;
+        if (*dst) cudaFree(*dst);
+        *dst = nullptr;
+        void* q = nullptr;
+        if (cudaMalloc(&q, v.size() * sizeof(T)) != cudaSuccess) return -3;
+        if (cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
+        *dst = static_cast<typename std::remove_const<T>::type*>(q);
+        return 0;
+    };
+    if (up(&ctx->gs_xofs, xo) || up(&ctx->gs_xsi, xs) || up(&ctx->gs_xa, xa) || up(&ctx->gs_yofs, yo) || up(&ctx->gs_ysi, ys) || up(&ctx->gs_ya, ya))
+        return fail(ctx, -3, "allocating the INTER_AREA tables failed");
+    if (!ctx->gs_small) {
+        if (cudaMalloc(&ctx->gs_small, static_cast<size_t>(ctx->max_batch) * 256 * 256 * 3) != cudaSuccess ||
+            cudaMalloc(&ctx->gs_big, static_cast<size_t>(ctx->max_batch) * 786432) != cudaSuccess)
+            return fail(ctx, -3, "allocating the resize staging images failed");
+    }
+    ctx->gs_int_area = fast ? ix * iy : 0;
+    ctx->gs_H = H;
+    ctx->gs_W = W;
+    return 0;
+}
+
+// cv2.resize(img, (256,256), INTER_AREA) (core.py:212) for n <= max_batch images of H x W into ctx->gs_small
+int resize_to_256(cvb_ctx* ctx, const uint8_t* img, int n, int H, int W, uint8_t* out, cudaStream_t s) {
+    if (prepare_size(ctx, H, W)) return -2;
+    CK(launch_resize_area(img, out, n, H, W, 256, 256, ctx->gs_xofs, ctx->gs_xsi, ctx->gs_xa, ctx->gs_yofs, ctx->gs_ysi, ctx->gs_ya,
+                          ctx->gs_int_area, s));
+    ctx->launches++;
+    return 0;
+}
+
+int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logits, uint8_t* mask, cudaStream_t s);
+
+// extract_board up to the logits for images of any size >= 256 x 256: the 512 x 512 case feeds the stem directly (it fuses the
+// 2x reduction); other sizes are reduced by k_resize_area and replicated 2x, which the stem's reduction undoes exactly.
+int unet_forward_hw(cvb_ctx* ctx, const uint8_t* img, int n, int H, int W, float thr, float* logits, uint8_t* mask, cudaStream_t s) {
+    if (H == 512 && W == 512) return unet_forward(ctx, img, n, thr, logits, mask, s);
+    {
+        StageTimer t(ctx, 1, s);
+        if (resize_to_256(ctx, img, n, H, W, ctx->gs_small, s)) return -2;
+        CK(launch_double2x(ctx->gs_small, ctx->gs_big, n, 256, 256, s));
+        ctx->launches++;
+    }
+    return unet_forward(ctx, ctx->gs_big, n, thr, logits, mask, s);
+}
+
 int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logits, uint8_t* mask, cudaStream_t s) {
     if (!ctx->unet_loaded) return fail(ctx, -7, "UNet weights not loaded (call cvb_load_unet)");
     auto& P = ctx->unet_plan;
@@ -255,8 +345,9 @@ int classify(cvb_ctx* ctx, const uint8_t* board, int n, int flip, float* probs, 
 // used); `off` = index of the group's first board inside the caller's output arrays.  in_ready[c] (optional): event the
 // network of chunk c has to wait for (host path: the chunk's host->device copy).
 int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s,
-                   const cudaEvent_t* in_ready) {
+                   const cudaEvent_t* in_ready, int H = 512, int W = 512) {
     const int B = ctx->max_batch;
+    const size_t img_bytes = static_cast<size_t>(H) * W * 3;
     float* logits = o.logits ? o.logits + off * 65536 : nullptr;
     uint8_t* mask = o.mask ? o.mask + off * 65536 : ctx->ws_mask;
     int32_t* quad = o.quad ? o.quad + off * 8 : ctx->ws_quad;
@@ -266,8 +357,8 @@ int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip,
     for (int c = 0, c0 = 0; c0 < n; ++c, c0 += B) {
         const int nb = n - c0 < B ? n - c0 : B;
         if (in_ready) CK(cudaStreamWaitEvent(s, in_ready[c], 0));
-        if (unet_forward(ctx, img + static_cast<size_t>(c0) * 786432, nb, thr, logits ? logits + static_cast<size_t>(c0) * 65536 : nullptr,
-                         mask + static_cast<size_t>(c0) * 65536, s))
+        if (unet_forward_hw(ctx, img + static_cast<size_t>(c0) * img_bytes, nb, H, W, thr,
+                            logits ? logits + static_cast<size_t>(c0) * 65536 : nullptr, mask + static_cast<size_t>(c0) * 65536, s))
             return -2;
     }
     {
@@ -277,8 +368,8 @@ int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip,
     }
     {
         StageTimer t(ctx, 3, s);
-        CK(launch_homography(quad, found, ctx->ws_minv, n, 2.0f, 512, 512, s));
-        CK(launch_warp_board(img, ctx->ws_minv, found, board, n, 512, 512, s));
+        CK(launch_homography(quad, found, ctx->ws_minv, n, static_cast<float>(H) / 256.0f, 512, 512, s));   // _scale_quadrangle: H scales both axes
+        CK(launch_warp_board(img, ctx->ws_minv, found, board, n, H, W, s));
         ctx->launches += 2;
     }
     for (int c0 = 0; c0 < n; c0 += B) {
@@ -420,6 +511,9 @@ void cvb_destroy(cvb_ctx* ctx) {
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->trainer) cvb_trainer_free(ctx->trainer);
     if (ctx->jpeg) cvb_jpeg_free(ctx->jpeg);
+    for (void* q : {static_cast<void*>(ctx->gs_xofs), static_cast<void*>(ctx->gs_xsi), static_cast<void*>(ctx->gs_xa), static_cast<void*>(ctx->gs_yofs),
+                    static_cast<void*>(ctx->gs_ysi), static_cast<void*>(ctx->gs_ya), static_cast<void*>(ctx->gs_small), static_cast<void*>(ctx->gs_big)})
+        if (q) cudaFree(q);
     delete ctx;
 }
 
@@ -639,6 +733,42 @@ int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float thr, int fli
         if (pipeline_group(ctx, img + static_cast<size_t>(off) * 786432, n, thr, flip, *out, off, static_cast<cudaStream_t>(stream), nullptr))
             return -2;
     }
+    return 0;
+}
+
+int cvb_image_to_fen_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, float thr, int flip, const cvb_outputs* out, void* stream) {
+    if (!ctx || !img || !out || N < 0 || H <= 0 || W <= 0) return -1;
+    if (set_device(ctx)) return -2;
+    if ((H != 512 || W != 512) && prepare_size(ctx, H, W)) return -5;
+    for (int off = 0; off < N; off += ctx->group) {
+        const int n = N - off < ctx->group ? N - off : ctx->group;
+        if (pipeline_group(ctx, img + static_cast<size_t>(off) * H * W * 3, n, thr, flip, *out, off, static_cast<cudaStream_t>(stream), nullptr, H, W))
+            return -2;
+    }
+    return 0;
+}
+
+int cvb_unet_forward_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, float thr, float* logits, uint8_t* mask, void* stream) {
+    if (!ctx || !img || N < 0 || H <= 0 || W <= 0) return -1;
+    if (set_device(ctx)) return -2;
+    if ((H != 512 || W != 512) && prepare_size(ctx, H, W)) return -5;
+    const int B = ctx->max_batch;
+    for (int off = 0; off < N; off += B) {
+        const int n = N - off < B ? N - off : B;
+        if (unet_forward_hw(ctx, img + static_cast<size_t>(off) * H * W * 3, n, H, W, thr, logits ? logits + static_cast<size_t>(off) * 65536 : nullptr,
+                            mask ? mask + static_cast<size_t>(off) * 65536 : ctx->ws_mask, static_cast<cudaStream_t>(stream)))
+            return -2;
+    }
+    return 0;
+}
+
+int cvb_resize_area(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, uint8_t* out, void* stream) {
+    if (!ctx || !img || !out || N < 0) return -1;
+    if (set_device(ctx)) return -2;
+    if (prepare_size(ctx, H, W)) return -5;
+    CK(launch_resize_area(img, out, N, H, W, 256, 256, ctx->gs_xofs, ctx->gs_xsi, ctx->gs_xa, ctx->gs_yofs, ctx->gs_ysi, ctx->gs_ya,
+                          ctx->gs_int_area, static_cast<cudaStream_t>(stream)));
+    ctx->launches++;
     return 0;
 }
 

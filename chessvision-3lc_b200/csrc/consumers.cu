@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(1024) k_quality(const float* __restrict__ vals
 // ---------------------------------------------------------------------------------------------------------------------
 // n4, mask_completeness (process_pipeline.py:380-414) for 256x256 arrays: (#pixels > 0.5) / (#pixels of the filled largest
 // external contour).  What cv2.findContours(RETR_EXTERNAL) + max(key=contourArea) + drawContours(thickness=-1) amount to
-// (oracle/metrics.py, pinned against live cv2): among the 8-connected components that touch the frame-connected background
+// (checked against live cv2 by the test suite): among the 8-connected components that touch the frame-connected background
 // take the one whose outer border polygon has the largest area (Green's formula over the border-following chain; among
 // equal areas the one found LAST in raster order, because cv2 lists external contours in reverse discovery order and
 // max() keeps the first); its filled drawing is the component plus everything it encloses.
@@ -319,7 +319,7 @@ __device__ void seed_frame(uint32_t* pl, int tid) {
 __device__ __forceinline__ int pl_get(const uint32_t* pl, int x, int y) { return (pl[y * MW + (x >> 5)] >> (x & 31)) & 1; }   // framed coordinates
 
 // Outer border following from the raster-first pixel (x0, y0) of a component (framed coordinates), exactly
-// oracle/geometry.py:_follow (Suzuki-Abe with OpenCV's termination rule); returns |sum of cross products| = 2 * contourArea.
+// the way cv2.findContours follows it (Suzuki-Abe with OpenCV's termination rule, cf. trace_border in geometry.cu); returns |sum of cross products| = 2 * contourArea.
 __device__ long long border_area2(const uint32_t* F, int x0, int y0) {
     constexpr int DX[8] = {1, 1, 0, -1, -1, -1, 0, 1}, DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
     int s = 4;

@@ -59,6 +59,12 @@ struct cvb_ctx {
     float* ws_logits = nullptr;                        // [B,256,256]
     uint8_t* ws_mask = nullptr;                        // [B,256,256]
 
+    // ---- inputs of other sizes than 512x512 (general INTER_AREA): cell tables for the current (H, W), staging images
+    int gs_H = 0, gs_W = 0, gs_int_area = 0;
+    int *gs_xofs = nullptr, *gs_xsi = nullptr, *gs_yofs = nullptr, *gs_ysi = nullptr;
+    float *gs_xa = nullptr, *gs_ya = nullptr;
+    uint8_t *gs_small = nullptr, *gs_big = nullptr;      // [B,256,256,3] resized, [B,512,512,3] replicated (UNet stem input)
+
     // ---- geometry
     int32_t *ws_quad = nullptr, *ws_status = nullptr, *ws_ncont = nullptr, *ws_owner = nullptr;
     uint8_t* ws_found = nullptr;

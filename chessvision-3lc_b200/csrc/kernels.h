@@ -13,6 +13,11 @@ cudaError_t launch_unet_stem(const uint8_t* img, const float* wf, const float* b
 cudaError_t launch_maxpool2(const __half* in, __half* out, int N, int H, int W, int C, int in_c_stride, cudaStream_t s);
 cudaError_t launch_mask_from_logits(const float* logits, uint8_t* mask, float thr, long long count, cudaStream_t s);
 cudaError_t launch_resize_area_half(const uint8_t* img, uint8_t* out, int N, int h, int w, cudaStream_t s);
+// general INTER_AREA reduction u8 [N,H,W,3] -> u8 [N,dh,dw,3] from host-built cell tables (api.cu: area_tables); int_area != 0:
+// both scale factors are integers and int_area = their product
+cudaError_t launch_resize_area(const uint8_t* img, uint8_t* out, int N, int H, int W, int dh, int dw, const int* xofs, const int* xsi,
+                               const float* xa, const int* yofs, const int* ysi, const float* ya, int int_area, cudaStream_t s);
+cudaError_t launch_double2x(const uint8_t* in, uint8_t* out, int N, int h, int w, cudaStream_t s);
 cudaError_t configure_resnet_stem();
 cudaError_t launch_resnet_stem(const uint8_t* board, const float* wf, const float* bf, __half* out, int n_boards,
                                cudaStream_t s);

@@ -370,6 +370,100 @@ __global__ void k_resize_area_half(const uint8_t* __restrict__ img, uint8_t* __r
     for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// cv2.resize(img, (dw,dh), INTER_AREA) for any reduction (core.py:212), bit-identical to OpenCV's C++ path
+// (imgproc/resize.cpp: computeResizeAreaTab + ResizeArea_Invoker<uchar,float>, ResizeAreaFast_Invoker for integer scale
+// factors).  The cell tables (source index, float32 weight per destination index) are built on the host with OpenCV's own
+// double arithmetic; the kernel replays its float32 accumulation order with separate multiplies and adds (no FMA):
+// per source row the horizontal products in table order, then sum = beta*buf for the first source row of a destination
+// row and sum += beta*buf after it, round-half-even at the end.  One thread per destination pixel.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void k_resize_area(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, int H, int W, int dh, int dw,
+                              const int* __restrict__ xofs, const int* __restrict__ xsi, const float* __restrict__ xa,
+                              const int* __restrict__ yofs, const int* __restrict__ ysi, const float* __restrict__ ya, int int_area,
+                              long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dx = static_cast<int>(i % dw);
+    const long long t = i / dw;
+    const int dy = static_cast<int>(t % dh);
+    const long long n = t / dh;
+    const uint8_t* src = img + n * static_cast<long long>(H) * W * 3;
+    uint8_t* o = out + i * 3;
+    if (int_area) {   // integer scale factors: whole cells, integer sums
+        const int ix = W / dw, iy = H / dh;
+        int sum[3] = {0, 0, 0};
+        for (int r = 0; r < iy; ++r) {
+            const uint8_t* p = src + (static_cast<long long>(dy) * iy + r) * W * 3 + static_cast<long long>(dx) * ix * 3;
+            for (int c = 0; c < ix; ++c) {
+                sum[0] += p[3 * c];
+                sum[1] += p[3 * c + 1];
+                sum[2] += p[3 * c + 2];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int v;
+            if (int_area == 4) v = (sum[c] + 2) >> 2;
+            else v = __float2int_rn(__fmul_rn(static_cast<float>(sum[c]), 1.0f / static_cast<float>(int_area)));
+            o[c] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+        }
+        return;
+    }
+    float sum[3] = {0.f, 0.f, 0.f};
+    const int y0 = yofs[dy], y1 = yofs[dy + 1], x0 = xofs[dx], x1 = xofs[dx + 1];
+    for (int j = y0; j < y1; ++j) {
+        const uint8_t* row = src + static_cast<long long>(ysi[j]) * W * 3;
+        float buf[3] = {0.f, 0.f, 0.f};
+        for (int k = x0; k < x1; ++k) {
+            const uint8_t* p = row + xsi[k] * 3;
+            const float a = xa[k];
+            buf[0] = __fadd_rn(buf[0], __fmul_rn(static_cast<float>(p[0]), a));
+            buf[1] = __fadd_rn(buf[1], __fmul_rn(static_cast<float>(p[1]), a));
+            buf[2] = __fadd_rn(buf[2], __fmul_rn(static_cast<float>(p[2]), a));
+        }
+        const float b = ya[j];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sum[c] = j == y0 ? __fmul_rn(b, buf[c]) : __fadd_rn(sum[c], __fmul_rn(b, buf[c]));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int v = __float2int_rn(sum[c]);
+        o[c] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+cudaError_t launch_resize_area(const uint8_t* img, uint8_t* out, int N, int H, int W, int dh, int dw, const int* xofs, const int* xsi,
+                               const float* xa, const int* yofs, const int* ysi, const float* ya, int int_area, cudaStream_t s) {
+    const long long total = 1LL * N * dh * dw;
+    if (total == 0) return cudaSuccess;
+    k_resize_area<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img, out, H, W, dh, dw, xofs, xsi, xa, yofs, ysi, ya, int_area, total);
+    return cudaGetLastError();
+}
+
+// u8 [N,h,w,3] -> u8 [N,2h,2w,3] by pixel replication: the exact inverse of the 2x INTER_AREA reduction fused into the
+// UNet stem ((4a+2)>>2 == a), so an image resized by k_resize_area enters the standard pipeline unchanged.
+__global__ void k_double2x(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int h, int w, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one thread per OUTPUT pixel
+    if (i >= total) return;
+    const int x = static_cast<int>(i % (2 * w));
+    const long long t = i / (2 * w);
+    const int y = static_cast<int>(t % (2 * h));
+    const long long n = t / (2 * h);
+    const uint8_t* p = in + ((n * h + (y >> 1)) * w + (x >> 1)) * 3;
+    uint8_t* o = out + i * 3;
+    o[0] = p[0];
+    o[1] = p[1];
+    o[2] = p[2];
+}
+
+cudaError_t launch_double2x(const uint8_t* in, uint8_t* out, int N, int h, int w, cudaStream_t s) {
+    const long long total = 4LL * N * h * w;
+    if (total == 0) return cudaSuccess;
+    k_double2x<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(in, out, h, w, total);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resize_area_half(const uint8_t* img, uint8_t* out, int N, int h, int w, cudaStream_t s) {
     const long long total = 1LL * N * h * w;
     if (total == 0) return cudaSuccess;

@@ -8,7 +8,8 @@
  * Conventions: plain pointers and sizes only; every `*_dev` style pointer is a device pointer in caller-allocated
  * memory unless the function name ends in `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = default
  * stream); return value 0 = ok, negative = error (text via cvb_last_error); no function throws; nothing allocates
- * device memory after cvb_create / cvb_load_*.
+ * device memory after cvb_create / cvb_load_* / cvb_train_create, except the lazily sized staging of cvb_decode_jpeg and of
+ * the *_hw entry points (first use / change of image size).
  */
 #ifndef CHESSVISION_B200_H
 #define CHESSVISION_B200_H
@@ -86,6 +87,18 @@ CVB_API int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, fl
 /* process_image for a batch (core.py:152-195); all pointers on the device. */
 CVB_API int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float threshold, int flip, const cvb_outputs* out,
                      void* stream);
+
+/* Inputs of any size H x W >= 256 x 256 (process_image accepts every u8[H,W,3], core.py:168-170,212): img u8[N,H,W,3], all
+ * images of a call share one size.  512 x 512 takes the fused path above; other sizes go through the general INTER_AREA
+ * reduction (cvb_resize_area), the quadrangle is scaled by H/256 on both axes (core.py:414-417) and the board is warped
+ * from the original image.  The cell tables and two staging images are (re)built when the size changes. */
+CVB_API int cvb_image_to_fen_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, float threshold, int flip, const cvb_outputs* out,
+                                void* stream);
+CVB_API int cvb_unet_forward_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, float threshold, float* logits, uint8_t* mask,
+                                void* stream);
+/* cv2.resize(img, (256,256), interpolation=INTER_AREA) (core.py:212) for any H, W >= 256, bit-identical to OpenCV (integer
+ * cell averages for integer scale factors, its float32 accumulation order otherwise): u8[N,H,W,3] -> u8[N,256,256,3]. */
+CVB_API int cvb_resize_area(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, uint8_t* out, void* stream);
 
 /* Same, from HOST buffers to HOST buffers (pinned memory recommended): chunks of max_batch boards are copied in,
  * processed and copied out on three streams so that PCIe transfers overlap compute.  Synchronous on return. */

@@ -26,6 +26,60 @@ def resize_area_half(img: np.ndarray) -> np.ndarray:
     return (s >> 2).astype(np.uint8)
 
 
+def _area_tab(ssize: int, dsize: int, scale: float):
+    """OpenCV's computeResizeAreaTab (imgproc/resize.cpp): per destination index the (source index, float32 weight) pairs
+    of the source cells it covers — a partial cell on the left, whole cells, a partial cell on the right."""
+    import math
+    out = []
+    for d in range(dsize):
+        f1 = d * scale
+        f2 = f1 + scale
+        cell = min(scale, ssize - f1)
+        s1, s2 = math.ceil(f1), math.floor(f2)
+        s2 = min(s2, ssize - 1)
+        s1 = min(s1, s2)
+        ent = []
+        if s1 - f1 > 1e-3:
+            ent.append((s1 - 1, np.float32((s1 - f1) / cell)))
+        ent.extend((sx, np.float32(1.0 / cell)) for sx in range(s1, s2))
+        if f2 - s2 > 1e-3:
+            ent.append((s2, np.float32(min(min(f2 - s2, 1.0), cell) / cell)))
+        out.append(ent)
+    return out
+
+
+def resize_area(img: np.ndarray, dsize=(256, 256)) -> np.ndarray:
+    """``cv2.resize(img, dsize, interpolation=cv2.INTER_AREA)`` for a reduction in both axes (core.py:212), u8[H,W,C] with
+    H >= dsize[1], W >= dsize[0].  Two code paths in OpenCV, both restated bit for bit [pinned against live cv2]:
+    integer scale factors average whole cells in integers ((a+b+c+d+2)>>2 for 2x2, round-half-even of sum * float32(1/area)
+    otherwise); everything else accumulates float32 products row by row — horizontally in table order into a row buffer,
+    then ``sum = beta*buf`` for the first source row of a destination row and ``sum += beta*buf`` after it — and rounds
+    half to even at the end.  No fused multiply-add anywhere."""
+    dw, dh = dsize
+    sh, sw, cn = img.shape
+    assert img.dtype == np.uint8 and sh >= dh and sw >= dw, "INTER_AREA restatement covers reductions only"
+    fx, fy = sw / dw, sh / dh
+    ix, iy = int(round(fx)), int(round(fy))
+    if abs(fx - ix) < 2.220446049250313e-16 and abs(fy - iy) < 2.220446049250313e-16:
+        s = img[: dh * iy, : dw * ix].reshape(dh, iy, dw, ix, cn).astype(np.int64).sum((1, 3))
+        if ix == 2 and iy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        v = (s.astype(np.float32) * np.float32(1.0 / (ix * iy))).astype(np.float32)
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    xt, yt = _area_tab(sw, dw, fx), _area_tab(sh, dh, fy)
+    src = img.astype(np.float32)
+    buf = np.zeros((sh, dw, cn), np.float32)
+    for dx, ent in enumerate(xt):
+        for si, a in ent:
+            buf[:, dx] = (buf[:, dx] + (src[:, si] * a).astype(np.float32)).astype(np.float32)
+    out = np.zeros((dh, dw, cn), np.float32)
+    for dy, ent in enumerate(yt):
+        for k, (si, b) in enumerate(ent):
+            t = (b * buf[si]).astype(np.float32)
+            out[dy] = t if k == 0 else (out[dy] + t).astype(np.float32)
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K5  sigmoid + threshold                                                      (core.py:273, utils.py:101-112)
 # ----------------------------------------------------------------------------------------------------------------------

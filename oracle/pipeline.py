@@ -25,7 +25,7 @@ class OraclePipeline:
     @torch.no_grad()
     def logits(self, image: np.ndarray) -> np.ndarray:
         """core.py:212-220: INTER_AREA resize, /255, NHWC->NCHW (BGR kept), UNet forward."""
-        small = g.resize_area_half(image)
+        small = g.resize_area_half(image) if image.shape[:2] == (512, 512) else g.resize_area(image, (256, 256))
         x = (torch.from_numpy(small[None].astype(np.float32)) / 255).permute(0, 3, 1, 2)
         return self.unet(x)[0, 0].numpy()
 

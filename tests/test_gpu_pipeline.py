@@ -170,3 +170,60 @@ def test_python_api_process_image(golden):
     assert np.array_equal(eb.binary_mask, be.binary_mask)
     with pytest.raises(AssertionError):
         cvm.process_image(imgs[i].astype(np.float32))
+
+
+@pytest.mark.parametrize("h,w", [(600, 800), (1024, 768), (768, 768), (513, 512), (256, 300), (1080, 1920), (256, 256), (1024, 1024), (257, 999)])
+def test_resize_area_any_size_equals_cv2(trained_engine, h, w):
+    """cvb_resize_area against the third-party call of core.py:212 itself, bit for bit, in every code path of INTER_AREA."""
+    rng = np.random.default_rng(h * 3 + w)
+    imgs = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    got = trained_engine.resize_area(torch.from_numpy(imgs).cuda()).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], cv2.resize(imgs[i], (256, 256), interpolation=cv2.INTER_AREA)), (h, w, i)
+
+
+@pytest.mark.parametrize("h,w", [(768, 768), (600, 800), (1024, 1024)])
+def test_other_input_sizes_equal_the_oracle(trained_engine, golden, h, w):
+    """process_image on inputs that are not 512x512 (core.py:168-170 accepts any u8[H,W,3]): the data/test boards enlarged
+    to h x w; found flags, quads (+-1 px in the mask frame), boards given identical quads, labels and FEN against the fp32
+    oracle pipeline (oracle/pipeline.py, the reference path with its general INTER_AREA resize)."""
+    from chessvision._native import fen_strings
+    from oracle.pipeline import OraclePipeline
+    man, _, imgs = golden
+    pick = [i for i, e in enumerate(man["images"]) if e["found"]][:4]
+    big = np.stack([cv2.resize(imgs[i], (w, h), interpolation=cv2.INTER_CUBIC) for i in pick])
+    out = trained_engine.image_to_fen(torch.from_numpy(big).cuda(), trained_engine.alloc_outputs(len(pick), full=True))
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    fens = fen_strings(torch.from_numpy(out["fen"]))
+    oracle = OraclePipeline.from_checkpoints(str(WEIGHTS / "best_extractor.pth"), str(WEIGHTS / "best_classifier.pth"))
+    for k in range(len(pick)):
+        ref = oracle.process_image(big[k])
+        assert bool(out["found"][k]) == (ref["quad"] is not None)
+        assert np.abs(out["logits"][k] - ref["logits"]).max() <= 0.15
+        if ref["quad"] is None:
+            continue
+        d = int(np.abs(out["quad"][k] - ref["quad"].reshape(4, 2)).max())
+        assert d <= 1, d
+        if d == 0:
+            assert np.array_equal(out["board"][k], ref["board"])
+            assert fens[k] == (ref["original_fen"], ref["fen"])
+
+
+def test_python_api_mixed_sizes(golden):
+    """ChessVision.process_images with a list of differently sized images: grouped by size, results in input order."""
+    from chessvision import ChessVision
+    man, _, imgs = golden
+    cv = ChessVision(board_extractor_weights=str(WEIGHTS / "best_extractor.pth"), classifier_weights=str(WEIGHTS / "best_classifier.pth"),
+                     classifier_model_id="resnet18", max_batch=8)
+    a, b = imgs[0], imgs[1]
+    mixed = [a, cv2.resize(b, (640, 480), interpolation=cv2.INTER_AREA), b, cv2.resize(a, (700, 700), interpolation=cv2.INTER_LINEAR)]
+    res = cv.process_images(mixed)
+    alone = [cv.process_image(m) for m in mixed]
+    assert len(res) == 4
+    for r, s in zip(res, alone):
+        assert (r.position is None) == (s.position is None)
+        assert np.array_equal(r.board_extraction.binary_mask, s.board_extraction.binary_mask)
+        if r.position is not None:
+            assert r.position.fen == s.position.fen
+    with pytest.raises(NotImplementedError):
+        cv.process_image(np.zeros((200, 300, 3), np.uint8))

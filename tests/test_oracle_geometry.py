@@ -42,6 +42,13 @@ def test_resize_area_half_equals_cv2():
     assert np.array_equal(og.resize_area_half(img), cv2.resize(img, (256, 256), interpolation=cv2.INTER_AREA))
 
 
+@pytest.mark.parametrize("h,w", [(600, 800), (1024, 768), (768, 768), (513, 512), (256, 300), (1080, 1920), (256, 256), (1024, 1024), (257, 999)])
+def test_resize_area_general_equals_cv2(h, w):
+    """Every code path of cv2.resize(INTER_AREA): integer factors (1x1, 2x2, 3x3, 4x4), fractional, mixed."""
+    img = np.random.default_rng(h + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    assert np.array_equal(og.resize_area(img, (256, 256)), cv2.resize(img, (256, 256), interpolation=cv2.INTER_AREA))
+
+
 def test_binary_mask_follows_fp32_sigmoid():
     import torch
     x = np.array([[-1.0, -1e-8, 0.0, 5e-8, 8.9e-8, 9.0e-8, 1.2e-7, 1.0]], np.float32)
