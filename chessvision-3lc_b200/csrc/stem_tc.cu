@@ -20,7 +20,7 @@
 namespace cvb {
 namespace {
 
-constexpr int kThreads = 288;      // UNet stem: 4 producer + 4 epilogue + 1 MMA warps
+constexpr int kThreads = 416;      // UNet stem: 4 producer + 2 x 4 epilogue (alternate tiles) + 1 MMA warps
 constexpr int kRsThreads = 416;    // ResNet stem: 4 producer + 8 epilogue + 1 MMA warps
 constexpr int kStages = 4;
 constexpr int kABytes = 128 * 128;   // 128 im2col rows x 64 fp16
@@ -50,27 +50,27 @@ struct Bars {
     uint32_t full, empty, tfull, tempty;
 };
 
-// Common prologue: barriers + TMEM (128 columns = two 64-column accumulators).  Called by all threads.
-template <int kMmaWarp, int kEpiThreads>
+// Common prologue: barriers + TMEM (kAcc 64-column accumulators).  Called by all threads.
+template <int kMmaWarp, int kEpiThreads, int kAcc>
 __device__ __forceinline__ uint32_t setup(uint64_t* bars, uint32_t* tmem_slot, Bars& b, int warp, int lane) {
     b.full = smem_u32(bars);
     b.empty = b.full + 8 * kStages;
     b.tfull = b.empty + 8 * kStages;
-    b.tempty = b.tfull + 16;
+    b.tempty = b.tfull + 8 * kAcc;
     if (warp == kMmaWarp) {
         if (lane == 0) {
             for (int i = 0; i < kStages; ++i) {
                 mbar_init(b.full + 8 * i, 128);
                 mbar_init(b.empty + 8 * i, 1);
             }
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < kAcc; ++i) {
                 mbar_init(b.tfull + 8 * i, 1);
                 mbar_init(b.tempty + 8 * i, kEpiThreads);
             }
             mbar_fence_init();
         }
         __syncwarp();
-        tmem_alloc(smem_u32(tmem_slot), 128);
+        tmem_alloc(smem_u32(tmem_slot), 64 * kAcc);
     }
     fence_proxy_async();   // weight tile / zero chunks written with ordinary stores are read by the tensor core
     tc_fence_before();
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
         *reinterpret_cast<uint4*>(base + kRsOffA + (i >> 7) * kABytes + sw128(i & 127, 7)) = make_uint4(0, 0, 0, 0);
     if (tid < 64) reinterpret_cast<float*>(base + kRsOffBias)[tid] = __ldg(bias + tid);
     Bars b;
-    const uint32_t tmem_base = setup<12, 256>(bars, tmem_slot, b, warp, lane);
+    const uint32_t tmem_base = setup<12, 256, 2>(bars, tmem_slot, b, warp, lane);
 
     if (warp < 4) {
         // ------------------------------------------------------------------------------------------------ producers
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
     const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
     uint8_t* base = smem_raw + (base_addr - raw_addr);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + kUsOffBars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_units = n_images * 32;
 
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
     if (tid < 64) reinterpret_cast<float*>(base + kUsOffBias)[tid] = __ldg(bias + tid);
     if (tid == 0) tma_prefetch_desc(&omap);
     Bars b;
-    const uint32_t tmem_base = setup<8, 128>(bars, tmem_slot, b, warp, lane);
+    const uint32_t tmem_base = setup<12, 128, 4>(bars, tmem_slot, b, warp, lane);
 
     if (warp < 4) {
         // ------------------------------------------------------------------------------------------------ producers
@@ -353,18 +353,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
             }
             buf ^= 1;
         }
-    } else if (warp < 8) {
+    } else if (warp < 12) {
         // ------------------------------------------------------------------------------------------------ epilogue
-        // TMEM -> bias + ReLU -> fp16 -> swizzled staging tile -> one TMA store of the 2-row x 64-column x 64-channel box
-        const int e = warp & 3, etid = tid - 128;
+        // TMEM -> bias + ReLU -> fp16 -> swizzled staging tile -> one TMA store of the 2-row x 64-column x 64-channel box.
+        // Two groups of four warps take alternate tiles (the chain wait -> TMEM load -> convert -> stage -> store is
+        // latency-bound, two tiles in flight hide it); four accumulators, one staging buffer per group.
+        const int e = warp & 3, g = (warp - 4) >> 2, etid = (tid - 128) & 127;
         const int row = e * 32 + lane;
         const float4* b4 = reinterpret_cast<const float4*>(base + kUsOffBias);
+        uint8_t* dst = base + kUsOffOut + g * kABytes;
         int iter = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const int n = unit >> 5, y0 = ((unit >> 2) & 7) * 32, x0 = (unit & 3) * 64;
             for (int t = 0; t < 16; ++t, ++iter) {
-                const int acc = iter & 1;
-                mbar_wait(b.tfull + 8 * acc, (iter >> 1) & 1);
+                if ((iter & 1) != g) continue;
+                const int acc = iter & 3;
+                mbar_wait(b.tfull + 8 * acc, (iter >> 2) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + acc * 64;
                 uint32_t v0[32], v1[32];
@@ -382,17 +386,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
                     o[16 + 2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[4 * i + 1]) + bb.y, 0.f)));
                     o[16 + 2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[4 * i + 3]) + bb.w, 0.f)));
                 }
-                const int buf = iter & 1;
-                if (etid == 0) bulk_wait_read<1>();   // the store issued two tiles ago has finished reading this buffer
-                named_bar(2, 128);
-                uint8_t* dst = base + kUsOffOut + buf * kABytes;
+                if (etid == 0) bulk_wait_read<0>();   // this group's previous store has finished reading its buffer
+                named_bar(2 + g, 128);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(dst + sw128(row, j)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 fence_proxy_async();
-                named_bar(2, 128);
+                named_bar(2 + g, 128);
                 if (etid == 0) {
-                    tma_store_4d(&omap, base_addr + kUsOffOut + buf * kABytes, 0, x0, y0 + 2 * t, n);
+                    tma_store_4d(&omap, base_addr + kUsOffOut + g * kABytes, 0, x0, y0 + 2 * t, n);
                     bulk_commit();
                 }
             }
@@ -405,8 +407,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
         uint32_t phase = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             for (int t = 0; t < 16; ++t, ++iter) {
-                const int acc = iter & 1;
-                mbar_wait(b.tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
+                const int acc = iter & 3;
+                mbar_wait(b.tempty + 8 * acc, ((iter >> 2) & 1) ^ 1);
                 mbar_wait(b.full + 8 * stage, phase);
                 tc_fence_after();
                 if (elect_one()) {
@@ -421,9 +423,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 12) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 256);
     }
 }
 
