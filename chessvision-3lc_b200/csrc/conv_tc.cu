@@ -559,8 +559,11 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
 // One CTA streams a strip of rs_rows output rows x 128 columns of one image; weights (9*Cin*64*2 B) stay resident.
 // The MMA-issuing thread is the critical resource of this kernel (12 MMAs per row, each only 96 tensor-clocks long): the
 // TMEM runs and descriptor words of a row are computed once, the K loop is fully unrolled, and one elected thread runs
-// the whole role loop.  Two epilogue groups (warps 4-7 / 8-11) drain alternate output rows and write fp16 NHWC with
-// 256-bit global stores (one full 32-byte sector per lane and instruction), so the epilogue adds no shared-memory traffic.
+// the role loop runs warp-uniformly with only the tcgen05 instructions predicated on the elected lane.  Two epilogue
+// groups (warps 4-7 / 8-11) drain alternate output ROW PAIRS and write fp16 NHWC with 256-bit global stores (one full
+// 32-byte sector per lane and instruction), so the epilogue adds no shared-memory traffic; a thread therefore sees both
+// rows of a 2x2 window and the encoder's max-pool is fused here.  The same kernel runs the 16x16 ResNet level: a streamed
+// row is then the same image row of eight squares (box {64 ch, 16 px, 1 row, 8 images}, MODE 0).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kRsBarBytes = 512;
 constexpr int kRsThreads = 384;   // TMA warp, MMA warp, TMEM warp, one idle warp, two epilogue groups of four warps
