@@ -600,7 +600,7 @@ __device__ __forceinline__ void rs_runs(uint32_t s_base, int lo, int hi, uint32_
 // All K steps of one pipeline stage for an interior input row (its three column blocks land on slots s_base .. s_base+2
 // of the ring).  NA = slots before the ring wraps (3: no wrap; 2 or 1: the remaining 3 - NA blocks go to slot 0 on).
 // Straight-line code: every N and every operand offset is a compile-time constant.
-template <int NA, int NDX>
+template <int NA, int ADX>
 __device__ __forceinline__ void rs_issue_row(uint32_t tmem_base, uint32_t s_base, uint64_t desc_hi, uint32_t a_lo, uint32_t b_lo,
                                              uint32_t b_dx_stride, uint32_t idesc0, bool first) {
     constexpr int NB = 3 - NA;
@@ -609,10 +609,10 @@ __device__ __forceinline__ void rs_issue_row(uint32_t tmem_base, uint32_t s_base
     const uint32_t i_a = idesc0 | (static_cast<uint32_t>(NA * 8) << 17);
     const uint32_t i_b = idesc0 | (static_cast<uint32_t>(NB * 8) << 17);
 #pragma unroll
-    for (int dd = 0; dd < NDX; ++dd) {
+    for (int dd = 0; dd < 3; ++dd) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint64_t a_desc = desc_hi | (a_lo + 8u * dd + 2u * k);
+            const uint64_t a_desc = desc_hi | (a_lo + static_cast<uint32_t>(ADX) * dd + 2u * k);
             const uint32_t b_k = b_lo + dd * b_dx_stride + 2u * k;
             if (dd == 0 && k == 0 && first) {
                 umma_f16(d_a, a_desc, desc_hi | b_k, idesc0 | (8u << 17), 0u);
@@ -625,23 +625,22 @@ __device__ __forceinline__ void rs_issue_row(uint32_t tmem_base, uint32_t s_base
     }
 }
 
-// Same for the first / last two input rows of a strip, whose window is partial (4 of rs_rows + 2 rows: kept out of line
-// so that its bookkeeping is not hoisted into the hot loop).
-template <int NDX>
+// Same for the first / last input rows of a strip, whose window is partial (kept out of line so that its bookkeeping is
+// not hoisted into the hot loop).  fresh_blocks: the first K step overwrites blocks dy < fresh_blocks (new output rows).
+template <int ADX>
 __device__ __noinline__ void rs_issue_partial(uint32_t tmem_base, uint32_t s_base, int dy_lo, int dy_hi, uint64_t desc_hi, uint32_t a_lo,
-                                              uint32_t b_lo, uint32_t b_dx_stride, uint32_t idesc0, bool fresh) {
-    RsRuns all, rest;
+                                              uint32_t b_lo, uint32_t b_dx_stride, uint32_t idesc0, int fresh_blocks) {
+    RsRuns all;
     rs_runs(s_base, dy_lo, dy_hi, idesc0, all);
-    rs_runs(s_base, 1, dy_hi, idesc0, rest);
-    for (int dd = 0; dd < NDX; ++dd) {
+    for (int dd = 0; dd < 3; ++dd) {
         for (int k = 0; k < 4; ++k) {
-            const uint64_t a_desc = desc_hi | (a_lo + 8u * dd + 2u * k);
+            const uint64_t a_desc = desc_hi | (a_lo + static_cast<uint32_t>(ADX) * dd + 2u * k);
             const uint32_t b_k = b_lo + dd * b_dx_stride + 2u * k;
-            if (fresh) {
-                umma_f16(tmem_base + s_base * 64u, a_desc, desc_hi | b_k, idesc0 | (8u << 17), 0u);
-                if (rest.n > 0) umma_f16(tmem_base + rest.col[0], a_desc, desc_hi | (b_k + rest.boff[0]), rest.idesc[0], 1u);
-                if (rest.n > 1) umma_f16(tmem_base + rest.col[1], a_desc, desc_hi | (b_k + rest.boff[1]), rest.idesc[1], 1u);
-                fresh = false;
+            if (fresh_blocks > 0) {   // first K step of the row: block by block, overwriting the new output rows
+                for (int dy = dy_lo; dy <= dy_hi; ++dy)
+                    umma_f16(tmem_base + ((s_base + dy) & 7u) * 64u, a_desc, desc_hi | (b_k + dy * (64u * 128u >> 4)), idesc0 | (8u << 17),
+                             dy < fresh_blocks ? 0u : 1u);
+                fresh_blocks = 0;
             } else {
                 umma_f16(tmem_base + all.col[0], a_desc, desc_hi | (b_k + all.boff[0]), all.idesc[0], 1u);
                 if (all.n > 1) umma_f16(tmem_base + all.col[1], a_desc, desc_hi | (b_k + all.boff[1]), all.idesc[1], 1u);
@@ -650,15 +649,18 @@ __device__ __noinline__ void rs_issue_partial(uint32_t tmem_base, uint32_t s_bas
     }
 }
 
-// MODE 0: one TMA box {64 ch, 128 px} per (row, dx).  MODE 1: one box {64 ch, 130 px} per row, horizontal tap dx
-// addressed 128*dx bytes further (the 128-byte swizzle is a function of the shared-memory address, so a start address
-// that is a multiple of 128 B inside a 1024-byte group keeps the pattern the TMA wrote).
+// A pipeline stage holds everything one input row (and one 64-channel chunk) contributes: all three horizontal taps.
+// MODE 0: three TMA boxes {64 ch, 128 px}, one per dx, 16 KB apart (also the 8 x 16 form: pixels of different images are
+// not contiguous).  MODE 1: one box {64 ch, 130 px}, tap dx addressed 128*dx bytes further (the 128-byte swizzle is a
+// function of the shared-memory address, so a start address that is a multiple of 128 B inside a 1024-byte group keeps
+// the pattern the TMA wrote).
+// A strip that covers the whole image height (the 16x16 squares) skips input rows -1 and rs_rows: they are all zero.
 template <int EPI, int MODE>
 __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_constant__ ConvParams p) {
     constexpr uint32_t kBBytes = 64 * 128;
-    constexpr uint32_t a_bytes = MODE == 0 ? 128u * 128u : 130u * 128u;   // bytes one TMA box delivers
-    constexpr uint32_t stage_bytes = MODE == 0 ? 16384u : 17408u;         // 1024-aligned stage pitch
-    constexpr int NDX = MODE == 0 ? 1 : 3;                                // horizontal taps served by one stage
+    constexpr uint32_t a_bytes = MODE == 0 ? 3u * 128u * 128u : 130u * 128u;   // bytes the TMA delivers per stage
+    constexpr uint32_t stage_bytes = MODE == 0 ? 49152u : 17408u;              // 1024-aligned stage pitch
+    constexpr int ADX = MODE == 0 ? 1024 : 8;                                  // A descriptor step per horizontal tap (16-byte units)
     const int S = p.vr_stages;
     const int R = p.rs_rows;
 
@@ -711,7 +713,9 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
 
     const int strips_per_image = p.tiles_h * p.tiles_w;
     const int total_strips = p.tiles_n * strips_per_image;
-    const int loads_per_row = MODE == 0 ? 3 * p.c_chunks : p.c_chunks;
+    const int loads_per_row = p.c_chunks;
+    const bool skip_halo = R == p.H;   // the strip is the whole image: input rows -1 and R are outside it
+    const int j_lo = skip_halo ? 0 : -1, j_hi = skip_halo ? R - 1 : R;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -728,14 +732,17 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                 const int w0 = (t % p.tiles_w) * p.tw;
                 const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
                 const int n0 = (t / strips_per_image) * p.tn;
-                for (int j = -1; j <= R; ++j) {
-                    for (int l = 0; l < loads_per_row; ++l) {
-                        const int kc = MODE == 0 ? l / 3 : l;
-                        const int dxi = MODE == 0 ? l - 3 * kc : 0;
+                for (int j = j_lo; j <= j_hi; ++j) {
+                    for (int kc = 0; kc < loads_per_row; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * stage, a_bytes);
-                        tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[MODE == 0 ? 0 : 1], bar_full + 8 * stage,
-                                    p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
+                        if (MODE == 0) {
+                            for (int dxi = 0; dxi < 3; ++dxi)
+                                tma_load_4d(stages_addr + stage * stage_bytes + dxi * 16384u, &p.a_map[0], bar_full + 8 * stage,
+                                            p.a_c_off + kc * 64, w0 + dxi - 1, h0 + j, n0);
+                        } else {
+                            tma_load_4d(stages_addr + stage * stage_bytes, &p.a_map[1], bar_full + 8 * stage, p.a_c_off + kc * 64, w0 - 1, h0 + j, n0);
+                        }
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -759,36 +766,42 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
         uint32_t phase = 0;
         uint32_t rho0 = 0;   // output rows this CTA has started before the current strip
         for (int t = blockIdx.x; t < total_strips; t += gridDim.x, rho0 += R) {
-            for (int j = -1; j <= R; ++j) {
+            for (int j = j_lo; j <= j_hi; ++j) {
                 // input row j feeds output rows j + 1 - dy, dy in [dy_lo, dy_hi]
                 const int dy_lo = j + 2 - R > 0 ? j + 2 - R : 0;
                 const int dy_hi = j + 1 < 2 ? j + 1 : 2;
                 const uint32_t rho_new = rho0 + static_cast<uint32_t>(j + 1);
                 const uint32_t s_base = (0u - rho_new) & 7u;   // slot of block dy = (s_base + dy) & 7
+                // output rows this input row starts (their first K step overwrites): block 0 always, and block 1 too when
+                // the zero row above the image is skipped and this is input row 0
+                const int fresh_blocks = dy_lo == 0 ? (skip_halo && j == 0 ? 2 : 1) : 0;
                 const bool interior = dy_lo == 0 && dy_hi == 2;
-                if (dy_lo == 0) {   // block 0 starts output row rho_new: its slot must have been drained
-                    mbar_wait(bar_tempty + 8 * s_base, ((rho_new >> 3) & 1u) ^ 1u);
-                    tc_fence_after();
+                for (int f = 0; f < fresh_blocks; ++f) {   // a new output row's slot must have been drained
+                    const uint32_t rho = rho_new - static_cast<uint32_t>(f);
+                    mbar_wait(bar_tempty + 8 * ((s_base + f) & 7u), ((rho >> 3) & 1u) ^ 1u);
                 }
-                for (int l = 0; l < loads_per_row; ++l) {
+                tc_fence_after();
+                for (int kc = 0; kc < loads_per_row; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const int kc = MODE == 0 ? l / 3 : l;
-                    const int dx0 = MODE == 0 ? l - 3 * kc : 0;
                     const uint32_t a_lo = a_lo0 + stage * (stage_bytes >> 4);
-                    const uint32_t b_lo = w_lo + static_cast<uint32_t>(kc * 3) * (kBBytes >> 4) + dx0 * b_dx_stride;
-                    const bool first = l == 0 && dy_lo == 0;   // overwrite block 0 on the first K step of a new output row
+                    const uint32_t b_lo = w_lo + static_cast<uint32_t>(kc * 3) * (kBBytes >> 4);
+                    const bool first = kc == 0 && fresh_blocks > 0;   // overwrite on the first K step of a new output row
                     if (leader) {
                         if (interior) {
-                            if (s_base <= 5u) rs_issue_row<3, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
-                            else if (s_base == 6u) rs_issue_row<2, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
-                            else rs_issue_row<1, NDX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
-                        } else {   // first / last two input rows of a strip: a partial window
-                            rs_issue_partial<NDX>(tmem_base, s_base, dy_lo, dy_hi, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                            if (s_base <= 5u) rs_issue_row<3, ADX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                            else if (s_base == 6u) rs_issue_row<2, ADX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                            else rs_issue_row<1, ADX>(tmem_base, s_base, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first);
+                        } else {   // first / last input rows of a strip: a partial window
+                            rs_issue_partial<ADX>(tmem_base, s_base, dy_lo, dy_hi, desc_hi, a_lo, b_lo, b_dx_stride, idesc0, first ? fresh_blocks : 0);
                         }
                         umma_commit(bar_empty + 8 * stage);
-                        // after the last K step of input row j, output row j - 1 is complete
-                        if (l == loads_per_row - 1 && j >= 1) umma_commit(bar_tfull + 8 * ((s_base + 2u) & 7u));
+                        if (kc == loads_per_row - 1) {
+                            // after the last K step of input row j, output row j - 1 is complete; so is row R - 1 when
+                            // there is no input row R to wait for
+                            if (j >= 1) umma_commit(bar_tfull + 8 * ((s_base + 2u) & 7u));
+                            if (skip_halo && j == R - 1) umma_commit(bar_tfull + 8 * ((s_base + 1u) & 7u));
+                        }
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -1145,12 +1158,12 @@ bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     const char* m = getenv("CVB_RS_MODE");
     const int mode = squares ? 0 : (m ? atoi(m) : 1);   // the 130-pixel box of mode 1 needs contiguous pixels: wide images only
     if (mode < 0 || mode > 1) return false;
-    const int stage = mode == 0 ? 16384 : 17408;
+    const int stage = mode == 0 ? 49152 : 17408;
     const int w_bytes = 9 * (Cin / 64) * 64 * 128;
     const int fixed = 1024 + kRsBarBytes + kEpiConstBytes;
     int stages = (kVrMaxSmem - fixed - w_bytes) / stage;
     if (stages > 8) stages = 8;
-    if (stages < (mode == 0 ? 3 : 2)) return false;
+    if (stages < 2) return false;
     p.vr_stages = stages;
     p.w_stationary = 1;
     p.rs_rows = R;
