@@ -655,7 +655,9 @@ __device__ __noinline__ void rs_issue_partial(uint32_t tmem_base, uint32_t s_bas
 // function of the shared-memory address, so a start address that is a multiple of 128 B inside a 1024-byte group keeps
 // the pattern the TMA wrote).
 // A strip that covers the whole image height (the 16x16 squares) skips input rows -1 and rs_rows: they are all zero.
-template <int EPI, int MODE>
+// POOL: the 2x2 max-pool of the output is written as well (p.pool_out); a template parameter so that the row-pair
+// registers of the pooling form and the residual registers of the other do not share one register budget.
+template <int EPI, int MODE, bool POOL>
 __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_constant__ ConvParams p) {
     constexpr uint32_t kBBytes = 64 * 128;
     constexpr uint32_t a_bytes = MODE == 0 ? 3u * 128u * 128u : 130u * 128u;   // bytes the TMA delivers per stage
@@ -820,23 +822,25 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
             const int w0 = (t % p.tiles_w) * p.tw + row % p.tw;
             const int h0 = ((t / p.tiles_w) % p.tiles_h) * R;
             const int n = (t / strips_per_image) * p.tn + row / p.tw;
+            const bool has_res = EPI == EPI_STORE && !POOL && p.res != nullptr && n < p.N;
             for (int r2 = 2 * group; r2 < R; r2 += 4) {
-                uint32_t o_prev[32];
+                uint32_t o_prev[POOL ? 32 : 1];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     const int r = r2 + half;
                     const uint32_t rho = rho0 + static_cast<uint32_t>(r);
                     const uint32_t slot = (0u - rho) & 7u;
                     const size_t pix = (static_cast<size_t>(n) * p.H + h0 + r) * p.W + w0;
-                    const bool has_res = EPI == EPI_STORE && p.res != nullptr && n < p.N;
-                    uint32_t res0[32];
-                    if (has_res) res_load64(p.res + pix * p.res_c_stride, res0);
+                    // requested before the accumulator is waited for (a one-row look-ahead costs 32 more live registers and
+                    // spills: measured slower)
+                    uint32_t res_cur[32];
+                    if (has_res) res_load64(p.res + pix * p.res_c_stride, res_cur);
                     mbar_wait(bar_tfull + 8 * slot, (rho >> 3) & 1u);
                     tc_fence_after();
                     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * 64u;
                     if constexpr (EPI == EPI_OUTC) {
                         int unused = 0;
-                        epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res0);
+                        epilogue_tile<64, EPI>(p, taddr, row, n, h0 + r, w0, n, h0 + r, w0, n < p.N, 0, s_bias, s_outw, nullptr, 0u, unused, 0, res_cur);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);
@@ -845,18 +849,18 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                         tmem_ld_32x32(taddr, va);
                         tmem_ld_32x32(taddr + 32, vb);
                         tmem_ld_wait(va);
-                        pack_chunk<0>(va, s_bias, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                        pack_chunk<0>(va, s_bias, res_cur, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[0]));
                         tmem_ld_wait(vb);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tempty + 8 * slot);   // the accumulator is in registers: release the slot early
-                        pack_chunk<16>(vb, s_bias + 32, res0, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                        pack_chunk<16>(vb, s_bias + 32, res_cur, has_res, p.relu != 0, reinterpret_cast<uint32_t(&)[16]>(o[16]));
                         if (n < p.N) {
                             __half* dst = p.out + pix * p.out_c_stride + p.out_c_off;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) st_global_v8(dst + 16 * q, o + 8 * q);
                         }
-                        if (p.pool_out != nullptr) {
+                        if constexpr (POOL) {
                             if (half == 0) {
 #pragma unroll
                                 for (int i = 0; i < 32; ++i) o_prev[i] = o[i];
@@ -1102,10 +1106,12 @@ cudaError_t conv_configure() {
     if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
     if ((e = configure_vr<128, EPI_STORE, false>()) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_OUTC, true>()) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_OUTC, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1193,11 +1199,15 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     const int grid = (int)(total < sm_count ? total : sm_count);
     if (L.variant == 2) {
         if (L.epilogue == EPI_OUTC) {
-            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_OUTC, 0><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
-            else conv3x3_rs_kernel<EPI_OUTC, 1><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_OUTC, 0, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            else conv3x3_rs_kernel<EPI_OUTC, 1, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+        } else if (p.pool_out != nullptr) {   // pooling form: no residual (the encoder convs have none)
+            if (p.res != nullptr) return cudaErrorInvalidValue;
+            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_STORE, 0, true><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            else conv3x3_rs_kernel<EPI_STORE, 1, true><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
         } else {
-            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_STORE, 0><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
-            else conv3x3_rs_kernel<EPI_STORE, 1><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_STORE, 0, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            else conv3x3_rs_kernel<EPI_STORE, 1, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
         }
         return cudaGetLastError();
     }
