@@ -140,6 +140,7 @@ int parse_header(const uint8_t* d, size_t n, JpegHeader& H, const char** msg) {
         } else if ((m >= 0xC1 && m <= 0xCF) && m != 0xC4 && m != 0xC8 && m != 0xCC) {
             return bad("only baseline (SOF0) JPEGs are supported");
         } else if (m == 0xDD) {
+            if (sl < 2) return bad("corrupt JPEG: restart interval segment");
             H.restart = (s[0] << 8) | s[1];
         } else if (m == 0xE1 && sl > 6 && memcmp(s, "Exif\0\0", 6) == 0) {
             const int o = exif_orientation(s + 6, sl - 6);

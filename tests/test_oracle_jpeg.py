@@ -61,3 +61,32 @@ def test_unsupported_streams_are_rejected():
         oj.parse(buf.tobytes())
     with pytest.raises(_native.NativeError):
         _native.jpeg_info(b"not a jpeg at all")
+
+
+def test_corrupted_streams_never_crash_the_host_decoder():
+    """Memory safety of the host half (csrc/jpeg.cu): random byte damage and truncation anywhere in a valid file must end in
+    an error code or a decoded image, never in an out-of-bounds access (run under the normal allocator; a crash kills pytest)."""
+    import ctypes as C
+    from chessvision import _native
+    lib = _native.load_library()
+    rng = np.random.default_rng(3)
+    coef = np.empty(512 * 512 * 3 // 2 + 64, np.int16)
+    qt = np.empty((3, 64), np.uint16)
+    ok = err = 0
+    for base in (FILES[0].read_bytes(), RESTART[0].read_bytes()):
+        for trial in range(300):
+            d = bytearray(base)
+            if trial % 3 == 0:
+                d = d[: int(rng.integers(2, len(d)))]                          # truncation, headers included
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(0, min(len(d), 700 if trial % 2 else len(d))))   # every other trial aims at the headers
+                d[pos] = int(rng.integers(0, 256))
+            buf = np.frombuffer(bytes(d), np.uint8)
+            h, w = C.c_int32(), C.c_int32()
+            if lib.cvb_jpeg_info(C.c_void_p(buf.ctypes.data), buf.size, C.byref(h), C.byref(w)) != 0 or (h.value, w.value) != (512, 512):
+                err += 1
+                continue                                                        # rejected (or a different size: the caller's buffer would not fit)
+            rc = lib.cvb_jpeg_coefficients(C.c_void_p(buf.ctypes.data), buf.size, C.c_void_p(coef.ctypes.data), C.c_void_p(qt.ctypes.data))
+            ok += rc == 0
+            err += rc != 0
+    assert ok + err == 600 and ok > 0 and err > 0
