@@ -37,6 +37,25 @@ H2D_PER_BOARD = 512 * 512 * 3
 D2H_PER_BOARD = 4 * 2 * 4 + 1 + 4 + 64 * 13 * 4 + 64 + 64 + 2 * 72   # quad, found, status, probs, labels x2, fen
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at N > 1), so file
+    descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text: str):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def synthetic_boards(n_distinct: int):
     """Generator A of SURVEY.md §8(d): a real data/test image under a random homography plus per-channel gain/offset,
     so that the trained UNet segments it.  Deterministic (seed 20261017)."""
@@ -146,7 +165,7 @@ def run_reference(args):
         "e2e": {"value": thr, "unit": "boards/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "found_rate": found_rate,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
 
 
 def synthetic_training_batch(b: int, seed: int):
@@ -191,13 +210,13 @@ def run_train_reference(args):
     dt = time.perf_counter() - t0
     thr = b * args.steps / dt
     cores = os.cpu_count() or 1
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "UNet training images/sec (fwd+bwd+clip+RMSprop)", "value": thr, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "configs[4]: UNet training step", "batch_per_step": b},
         "cpu_baseline": {"value": thr, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of batch {b}, fp32 torch oracle of train_unet.py's step, {cores} threads"},
-        "e2e": {"value": thr, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        "e2e": {"value": thr, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def run_train(args):
@@ -265,7 +284,7 @@ def run_train(args):
     peak_tf, _, peak_src = measured_peaks()
     tflops = 3 * UNET_GFLOP * value / 1000.0
     if rank == 0:
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "UNet training images/sec (fwd+bwd+clip+RMSprop)", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands, f32 master weights/accumulation", "data": "synthetic (quad masks + checkerboard images), trained start weights",
@@ -278,7 +297,7 @@ def run_train(args):
             "roofline": {"bound": "tensor", "kernel": "whole step (conv_tc fwd + dgrad, wgrad_tc)", "achieved": tflops, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": tflops / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_gflop_per_image": 3 * UNET_GFLOP},
-            "clocks": clocks, "loss": float(loss.item())}), flush=True)
+            "clocks": clocks, "loss": float(loss.item())}))
     tr.close()
     if world > 1:
         dist.destroy_process_group()
@@ -329,7 +348,7 @@ def run_decode(args):
         cpu_s = time.perf_counter() - t0
     _, hbm, src = measured_peaks()
     px = 512 * 512
-    print(json.dumps({
+    emit(json.dumps({
         "metric": "JPEG decode images/sec (files -> u8 BGR in HBM)", "value": n / (ms / 1000.0), "unit": "images/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 / u8", "data": "the reference's 38 data/test JPEGs (512x512, 4:2:0), cycled",
@@ -342,7 +361,7 @@ def run_decode(args):
                      "note": "idct: 3 B/px coefficients in + 1.5 out; colour: 1.5 in + 3 out; per-launch durations: profiles/ ncu launch list"},
         "cpu_baseline": {"value": len(sample) / cpu_s, "unit": "images/s", "cores": threads, "kind": "reference",
                          "sample": f"cv2.imdecode of {len(sample)} of the same files on {threads} threads ({cpu_s:.1f} s)"},
-        "clocks": clk.summary()}), flush=True)
+        "clocks": clk.summary()}))
     eng.close()
 
 
@@ -361,6 +380,7 @@ def main():
     ap.add_argument("--cpu-boards-per-step", type=int, default=8, help="--impl reference: boards per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    capture_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_train_reference(args) if args.workload == "train" else run_reference(args)
@@ -491,7 +511,7 @@ def main():
             "gflop_per_board": UNET_GFLOP + CLS_GFLOP,
             "model_tflops": value * (UNET_GFLOP + CLS_GFLOP) / 1000.0,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     eng.close()
     if world > 1:
         dist.destroy_process_group()
