@@ -12,7 +12,6 @@
 
 #include <cmath>
 #include <algorithm>
-#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -224,6 +223,21 @@ void area_table(int ssize, int dsize, double scale, std::vector<int>& ofs, std::
     }
 }
 
+// (Re)place a device copy of a host table; the previous copy, if any, is released.
+template <class T>
+int upload_table(T** dst, const std::vector<T>& v) {
+    if (*dst) cudaFree(*dst);
+    *dst = nullptr;
+    void* q = nullptr;
+    if (cudaMalloc(&q, v.size() * sizeof(T)) != cudaSuccess) return -3;
+    if (cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(q);
+        return -2;
+    }
+    *dst = static_cast<T*>(q);
+    return 0;
+}
+
 // Tables + staging images for inputs of H x W != 512 x 512 (H, W >= 256), (re)built when the size changes.
 int prepare_size(cvb_ctx* ctx, int H, int W) {
     if (H < 256 || W < 256) return fail(ctx, -5, "input images must be at least 256 x 256 (INTER_AREA is built for reductions only)");
@@ -236,17 +250,8 @@ int prepare_size(cvb_ctx* ctx, int H, int W) {
     std::vector<float> xa, ya;
     area_table(W, 256, fx, xo, xs, xa);
     area_table(H, 256, fy, yo, ys, ya);
-    auto up = [&](auto** dst, const auto& v) -> int {
-        using T = typename std::remove_reference<decltype(v[0])>::type;
-        if (*dst) cudaFree(*dst);
-        *dst = nullptr;
-        void* q = nullptr;
-        if (cudaMalloc(&q, v.size() * sizeof(T)) != cudaSuccess) return -3;
-        if (cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return -2;
-        *dst = static_cast<typename std::remove_const<T>::type*>(q);
-        return 0;
-    };
-    if (up(&ctx->gs_xofs, xo) || up(&ctx->gs_xsi, xs) || up(&ctx->gs_xa, xa) || up(&ctx->gs_yofs, yo) || up(&ctx->gs_ysi, ys) || up(&ctx->gs_ya, ya))
+    if (upload_table(&ctx->gs_xofs, xo) || upload_table(&ctx->gs_xsi, xs) || upload_table(&ctx->gs_xa, xa) ||
+        upload_table(&ctx->gs_yofs, yo) || upload_table(&ctx->gs_ysi, ys) || upload_table(&ctx->gs_ya, ya))
         return fail(ctx, -3, "allocating the INTER_AREA tables failed");
     if (!ctx->gs_small) {
         if (cudaMalloc(&ctx->gs_small, static_cast<size_t>(ctx->max_batch) * 256 * 256 * 3) != cudaSuccess ||
