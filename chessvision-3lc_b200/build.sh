@@ -17,5 +17,5 @@ $NVCC $FLAGS -c csrc/consumers.cu -o build/consumers.o &
 $NVCC $FLAGS -c csrc/jpeg.cu -o build/jpeg.o &
 # a failed compile must fail the build (a bare `wait` returns 0 and the link would reuse a stale object)
 for job in $(jobs -p); do wait "$job"; done
-$NVCC -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o build/wgrad_tc.o build/train_kernels.o build/train.o build/consumers.o build/jpeg.o -lpthread
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o build/wgrad_tc.o build/train_kernels.o build/train.o build/consumers.o build/jpeg.o -lpthread
 echo "built $(pwd)/libchessvision_b200.so"
