@@ -26,7 +26,7 @@ class _Tensor(C.Structure):
 
 class _Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("logits", "mask", "quad", "found", "status", "board", "probs", "labels", "labels_valid", "fen")]
+                ("logits", "mask", "quad", "found", "status", "board", "probs", "labels", "labels_valid", "fen", "squares")]
 
 
 OUTPUT_FIELDS = tuple(n for n, _ in _Outputs._fields_)
@@ -52,12 +52,14 @@ SYMBOLS = {
     "cvb_mask_from_logits": (_I, [_P, _P, _I, _F, _P, _P]),
     "cvb_mask_to_quad": (_I, [_P, _P, _I, _P, _P, _P, _P]),
     "cvb_warp_squares": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    "cvb_warp_perspective": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P, _P]),
     "cvb_classify": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P]),
     "cvb_image_to_fen": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs), _P]),
     "cvb_image_to_fen_hw": (_I, [_P, _P, _I, _I, _I, _F, _I, C.POINTER(_Outputs), _P]),
     "cvb_unet_forward_hw": (_I, [_P, _P, _I, _I, _I, _F, _P, _P, _P]),
     "cvb_resize_area": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "cvb_image_to_fen_host": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs)]),
+    "cvb_image_to_fen_host_progress": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs), _P]),
     "cvb_conv2d_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P]),
     "cvb_unet_stem": (_I, [_P, _P, _I, _P, _P]),
@@ -134,8 +136,8 @@ class Engine:
         if not torch.cuda.is_available():
             raise NativeError("no CUDA device: the B200 path has no CPU fallback")
         self.device = torch.device("cuda", device)
-        torch.cuda.set_device(self.device)
-        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        with torch.cuda.device(self.device):   # the caller's current device is left as it was
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
         self.h = self.lib.cvb_create(device, max_batch)
         if not self.h:
             raise NativeError("cvb_create failed (see stderr): the library needs an sm_100 GPU and enough free memory")
@@ -210,6 +212,17 @@ class Engine:
         self._ck(self.lib.cvb_warp_squares(self.h, _ptr(img), _ptr(quad), _ptr(found), n, H, W, _ptr(board), _stream()), "cvb_warp_squares")
         return board
 
+    def warp_perspective(self, img, corners, out_size):
+        """utils.extract_perspective on the device: img u8[H,W] or u8[H,W,C] (C = 1 or 3), corners f32[4,2] -> u8[h,w(,C)]."""
+        assert img.is_cuda and img.dtype == torch.uint8 and img.is_contiguous() and img.dim() in (2, 3)
+        H, W = img.shape[:2]
+        ch = 1 if img.dim() == 2 else img.shape[2]
+        ow, oh = int(out_size[0]), int(out_size[1])
+        c = corners.to(device=self.device, dtype=torch.float32).reshape(4, 2).contiguous()
+        out = torch.empty((oh, ow) if img.dim() == 2 else (oh, ow, ch), dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.cvb_warp_perspective(self.h, _ptr(img), H, W, ch, _ptr(c), ow, oh, _ptr(out), _stream()), "cvb_warp_perspective")
+        return out
+
     def classify(self, board, flip=False):
         n = board.shape[0]
         probs = torch.empty((n, 64, 13), dtype=torch.float32, device=self.device)
@@ -220,9 +233,9 @@ class Engine:
                                        _stream()), "cvb_classify")
         return probs, labels, labels_valid, fen
 
-    def alloc_outputs(self, n, full=False, pinned_host=False):
-        """Allocate the cvb_outputs buffers (device, or pinned host when ``pinned_host``)."""
-        kw = dict(device="cpu", pin_memory=True) if pinned_host else dict(device=self.device)
+    def alloc_outputs(self, n, full=False, pinned_host=False, squares=False, host=False):
+        """Allocate the cvb_outputs buffers (device; pinned host when ``pinned_host``; ordinary host memory when ``host``)."""
+        kw = dict(device="cpu", pin_memory=True) if pinned_host else (dict(device="cpu") if host else dict(device=self.device))
         out = {
             "quad": torch.empty((n, 4, 2), dtype=torch.int32, **kw),
             "found": torch.empty((n,), dtype=torch.uint8, **kw),
@@ -236,6 +249,8 @@ class Engine:
             out["logits"] = torch.empty((n, 256, 256), dtype=torch.float32, **kw)
             out["mask"] = torch.empty((n, 256, 256), dtype=torch.uint8, **kw)
             out["board"] = torch.empty((n, 512, 512), dtype=torch.uint8, **kw)
+        if squares:
+            out["squares"] = torch.empty((n, 64, 64, 64, 1), dtype=torch.uint8, **kw)
         return out
 
     @staticmethod
@@ -257,13 +272,20 @@ class Engine:
             self._ck(self.lib.cvb_image_to_fen_hw(self.h, _ptr(img), n, h, w, threshold, int(flip), C.byref(o), _stream()), "cvb_image_to_fen_hw")
         return out
 
-    def image_to_fen_host(self, img_host, out_host, threshold=0.5, flip=False):
-        """img_host: torch CPU uint8 [N,512,512,3] (pinned for overlap) ; out_host: dict of CPU tensors."""
+    def image_to_fen_host(self, img_host, out_host, threshold=0.5, flip=False, progress=None):
+        """img_host: torch CPU uint8 [N,512,512,3] (pinned for overlap) ; out_host: dict of CPU tensors.  ``progress``: optional
+        int32 numpy array of one element that the library advances to the number of leading boards whose results have
+        landed (read by another thread while this call, which releases the GIL, is still running)."""
         n = img_host.shape[0]
         assert not img_host.is_cuda and img_host.dtype == torch.uint8 and img_host.is_contiguous()
         o = self._outputs_struct(out_host)
-        self._ck(self.lib.cvb_image_to_fen_host(self.h, C.c_void_p(img_host.data_ptr()), n, threshold, int(flip), C.byref(o)),
-                 "cvb_image_to_fen_host")
+        if progress is None:
+            self._ck(self.lib.cvb_image_to_fen_host(self.h, C.c_void_p(img_host.data_ptr()), n, threshold, int(flip), C.byref(o)),
+                     "cvb_image_to_fen_host")
+        else:
+            assert progress.dtype == np.int32 and progress.size == 1
+            self._ck(self.lib.cvb_image_to_fen_host_progress(self.h, C.c_void_p(img_host.data_ptr()), n, threshold, int(flip), C.byref(o),
+                                                             C.c_void_p(progress.ctypes.data)), "cvb_image_to_fen_host_progress")
         return out_host
 
     # ---- building blocks for parity tests

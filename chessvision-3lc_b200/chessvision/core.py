@@ -5,15 +5,18 @@ Same constructor, methods, static helpers, attributes and error behaviour (``Ass
 fields when no board is found).  Added: :meth:`ChessVision.process_images` for batches.  Everything the reference
 computes with PyTorch-eager or OpenCV runs on the GPU here; there is no CPU fallback (a missing library or GPU raises).
 
-Input sizes: 512x512x3 (every image under the reference's ``data/test``) takes the fused path; any other size of at least
-256x256 goes through the general INTER_AREA reduction, bit-identical to ``cv2.resize``; smaller images (an enlargement,
-which OpenCV does not do with INTER_AREA arithmetic) raise ``NotImplementedError``.  ``process_images`` groups a list of
-differently sized images by size.
+Input sizes: 512x512x3 (every image under the reference's ``data/test``) takes the fused path; any other size goes through
+``cv2.resize(..., INTER_AREA)`` restated bit for bit on the device (true area interpolation when both axes shrink, OpenCV's
+fixed-point bilinear emulation as soon as one axis is smaller than 256).  ``process_images`` groups a list of differently
+sized images by size.
 """
 from __future__ import annotations
 
+import atexit
 import logging
+import threading
 import time
+import weakref
 
 import numpy as np
 import torch
@@ -25,14 +28,48 @@ from .cv_types import BoardExtractionResult, ChessVisionResult, PositionResult, 
 logger = logging.getLogger(__name__)
 
 _shared_engine: _native.Engine | None = None
+_live_engines: "weakref.WeakSet[_native.Engine]" = weakref.WeakSet()
+
+
+class QuadCapacityError(RuntimeError):
+    """mask->quad met a mask whose contours exceed every capacity of the contour kernels; ``indices`` are the
+    positions of those boards in the batch.  The reference's cv2 path has no such limit, so this is raised rather than
+    reported as "no board found"."""
+
+    def __init__(self, indices):
+        self.indices = list(indices)
+        super().__init__(f"mask->quad: contour capacity exceeded for board(s) {self.indices} (QUAD_OVERFLOW, DESIGN.md §4a)")
+
+
+def _close_shared_engine() -> None:
+    global _shared_engine
+    if _shared_engine is not None:
+        try:
+            _shared_engine.close()
+        finally:
+            _shared_engine = None
 
 
 def _engine_for_statics() -> _native.Engine:
-    """Weight-less context used by the static helpers (mask->quad, warp)."""
+    """Context used by the static helpers (mask->quad, warp) and by evaluation / quality / decode: the context of a live
+    ``ChessVision`` on the current device when there is one, otherwise one small weight-less context shared by all of them
+    (closed at interpreter exit, before PyTorch tears CUDA down)."""
     global _shared_engine
-    if _shared_engine is None:
-        _shared_engine = _native.Engine(torch.cuda.current_device() if torch.cuda.is_available() else 0, max_batch=4)
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    for eng in list(_live_engines):
+        if getattr(eng, "h", None) and eng.device.index == dev:
+            return eng
+    if _shared_engine is None or _shared_engine.device.index != dev:
+        _close_shared_engine()
+        _shared_engine = _native.Engine(dev, max_batch=1)
+        atexit.register(_close_shared_engine)
     return _shared_engine
+
+
+def _check_status(status) -> None:
+    bad = np.flatnonzero(np.asarray(status) == 2)
+    if bad.size:
+        raise QuadCapacityError(bad.tolist())
 
 
 class _NetHandle:
@@ -47,6 +84,17 @@ class _NetHandle:
     def eval(self):
         return self
 
+    @staticmethod
+    def _as_u8(x: torch.Tensor) -> torch.Tensor:
+        """The native stems consume 8-bit pixels (the reference feeds ``u8 / 255``, core.py:215-216, 236-237): anything else
+        (normalised, augmented, out-of-range data) would be quantised silently, so it is rejected."""
+        v = x.detach().float() * 255.0
+        r = v.round()
+        if not bool(((v - r).abs() <= 1e-3).all()) or float(r.min()) < 0 or float(r.max()) > 255:
+            raise ValueError("native network handles take u8/255 images only (the reference's own preprocessing); got values that "
+                             "are not multiples of 1/255 in [0, 1]")
+        return r.to(torch.uint8)
+
     def to(self, *_, **__):
         return self
 
@@ -57,13 +105,13 @@ class _NetHandle:
             # x: f32[N,3,256,256] = u8/255 (core.py:215-216).  The native stem fuses the 2x INTER_AREA reduction, and a
             # 2x pixel replication is its exact inverse ((4a+2)>>2 == a), so the u8 image is recovered and replicated.
             assert x.dim() == 4 and tuple(x.shape[1:]) == (3, 256, 256), "expected f32[N,3,256,256]"
-            u8 = (x.detach().float() * 255.0).round().clamp_(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+            u8 = self._as_u8(x).permute(0, 2, 3, 1)
             u8 = u8.repeat_interleave(2, 1).repeat_interleave(2, 2).contiguous().to(eng.device)
             logits, _ = eng.unet_forward(u8, 0.5)
             return logits.unsqueeze(1)
         # classifier: x f32[N,1,64,64] = u8/255 (core.py:236-237); N must be a multiple of 64 (whole boards)
         assert x.dim() == 4 and tuple(x.shape[1:]) == (1, 64, 64) and x.shape[0] % 64 == 0, "expected f32[64k,1,64,64]"
-        u8 = (x.detach().float() * 255.0).round().clamp_(0, 255).to(torch.uint8)
+        u8 = self._as_u8(x)
         n = x.shape[0] // 64
         board = u8.reshape(n, 8, 8, 64, 64).permute(0, 1, 3, 2, 4).reshape(n, 512, 512).contiguous().to(eng.device)
         probs, _, _, _ = eng.classify(board, False)
@@ -111,7 +159,20 @@ class ChessVision:
     def _engine(self) -> _native.Engine:
         if self._engine_obj is None:
             self._engine_obj = _native.Engine(self._device_index, self._max_batch)
+            _live_engines.add(self._engine_obj)
         return self._engine_obj
+
+    @classmethod
+    def from_engine(cls, engine: _native.Engine) -> "ChessVision":
+        """A ``ChessVision`` on top of an existing native context whose weights are already loaded (no second copy of the
+        activation workspaces); used by callers that drive the C ABI directly as well (bench.py)."""
+        self = cls(device_index=engine.device.index, max_batch=engine.max_batch)
+        self._engine_obj = engine
+        _live_engines.add(engine)
+        self._board_extractor = _NetHandle(self, "unet", {})
+        self._classifier = _NetHandle(self, "resnet18", {})
+        self._classifier_model_id = "resnet18"
+        return self
 
     @property
     def board_extractor(self) -> _NetHandle:
@@ -156,11 +217,19 @@ class ChessVision:
         return self.process_images([image], threshold, flip)[0]
 
     def process_images(self, images, threshold: float = 0.5, flip: bool = False) -> list[ChessVisionResult]:
-        """Batched ``process_image``: u8[N,H,W,3] (or a list of u8[H,W,3], sizes may differ) -> N results.  One host->device copy
-        of the images and one device->host copy of the results; everything in between stays on the GPU."""
+        """Batched ``process_image``: u8[N,H,W,3] (or a list of u8[H,W,3], sizes may differ) -> N results, each with every
+        field the reference's ``process_image`` returns (core.py:191-195).
+
+        512x512 batches stream through ``cvb_image_to_fen_host_progress``: the library copies chunk after chunk in, runs the
+        pipeline and copies each group's results straight into the arrays the result objects will view (no per-board
+        copies: logits, mask, board image, squares and probabilities of board i are views of row i of batch-sized arrays).
+        The native call runs in a worker thread (it releases the GIL) while this thread turns the groups that have already
+        landed into result objects, so the Python half is hidden behind the GPU."""
         start = time.time()
         if not isinstance(images, np.ndarray):
             images = list(images)
+            if not images:
+                return []
             sizes = {im.shape[:2] for im in images}
             if len(sizes) > 1:   # one native call per image size, results back in the caller's order
                 results: list = [None] * len(images)
@@ -170,47 +239,81 @@ class ChessVision:
                         results[i] = r
                 return results
             images = np.stack(images)
-        batch = np.ascontiguousarray(images)
+        if images.shape[0] == 0:
+            return []
+        batch = images if images.flags["C_CONTIGUOUS"] else np.ascontiguousarray(images)
         assert batch.dtype == np.uint8 and batch.ndim == 4 and batch.shape[3] == 3, "Images must be uint8 [N,H,W,3]"
-        if min(batch.shape[1:3]) < 256:
-            raise NotImplementedError(f"B200 path needs images of at least 256x256 (got {batch.shape[1:3]}); see DESIGN.md")
         self.board_extractor, self.classifier  # noqa: B018  (lazy initialisation)
         eng, n = self._engine, batch.shape[0]
         host_in = torch.from_numpy(batch)
-        if batch.shape[1:3] == (512, 512):
-            out = eng.alloc_outputs(n, full=True, pinned_host=True)
-            eng.image_to_fen_host(host_in, out, threshold, flip)
-        else:
-            dev = eng.image_to_fen(host_in.to(eng.device), eng.alloc_outputs(n, full=True), threshold, flip)
-            out = {k: v.cpu() for k, v in dev.items()}
         names = constants.SQUARE_NAMES_FLIPPED if flip else constants.SQUARE_NAMES_NORMAL
-        fens = _native.fen_strings(out["fen"])
-        results = []
-        elapsed = (time.time() - start) / max(n, 1)
-        for i in range(n):
-            found = bool(out["found"][i])
-            quad = None
-            board = None
-            position = None
-            if found:
-                quad = self._scale_quadrangle(out["quad"][i].numpy().reshape(4, 1, 2), batch.shape[1:3])
-                board = out["board"][i].numpy().copy()
-                probs = out["probs"][i].numpy().copy()
-                labels = [constants.LABEL_NAMES[k] for k in out["labels"][i].tolist()]
-                fixed = [constants.LABEL_NAMES[k] for k in out["labels_valid"][i].tolist()]
-                fixes = [ValidationFix(names[j], a, b, "no_pawns_on_ends") for j, (a, b) in enumerate(zip(labels, fixed)) if a != b]
-                position = PositionResult(fen=fens[i][1], original_fen=fens[i][0], model_probabilities=probs,
-                                          squares=self.extract_squares(board), square_names=names, validation_fixes=fixes)
-            extraction = BoardExtractionResult(probabilities=out["logits"][i].numpy().copy(), binary_mask=out["mask"][i].numpy().copy(),
-                                               quadrangle=quad, board_image=board)
-            results.append(ChessVisionResult(board_extraction=extraction, position=position, processing_time=elapsed))
+        results: list = []
+        scale = batch.shape[1] / 256.0
+
+        def build(lo: int, hi: int, out) -> None:
+            """Result objects of boards [lo, hi) from the batch-sized host arrays (views only)."""
+            _check_status(out["status"][lo:hi].numpy())
+            found = out["found"][lo:hi].numpy().astype(bool)
+            quads = np.array(out["quad"][lo:hi].numpy().reshape(-1, 4, 1, 2) * scale, dtype=np.float32)   # _scale_quadrangle, vectorised
+            fen_rows = out["fen"][lo:hi].numpy()
+            labels, fixed = out["labels"][lo:hi].numpy(), out["labels_valid"][lo:hi].numpy()
+            changed = (labels != fixed).any(axis=1)
+            logits, masks, boards = out["logits"].numpy(), out["mask"].numpy(), out["board"].numpy()
+            squares, probs = out["squares"].numpy(), out["probs"].numpy()
+            elapsed = (time.time() - start) / n
+            for k in range(hi - lo):
+                i = lo + k
+                if found[k]:
+                    fixes = []
+                    if changed[k]:
+                        fixes = [ValidationFix(names[j], constants.LABEL_NAMES[labels[k, j]], constants.LABEL_NAMES[fixed[k, j]], "no_pawns_on_ends")
+                                 for j in np.flatnonzero(labels[k] != fixed[k])]
+                    row = fen_rows[k]
+                    position = PositionResult(fen=row[1].tobytes().split(b"\0", 1)[0].decode(), original_fen=row[0].tobytes().split(b"\0", 1)[0].decode(),
+                                              model_probabilities=probs[i], squares=squares[i], square_names=names, validation_fixes=fixes)
+                    extraction = BoardExtractionResult(probabilities=logits[i], binary_mask=masks[i], quadrangle=quads[k], board_image=boards[i])
+                else:
+                    position = None
+                    extraction = BoardExtractionResult(probabilities=logits[i], binary_mask=masks[i], quadrangle=None, board_image=None)
+                results.append(ChessVisionResult(board_extraction=extraction, position=position, processing_time=elapsed))
+
+        if batch.shape[1:3] == (512, 512):
+            out = eng.alloc_outputs(n, full=True, squares=True, host=True)
+            progress = np.zeros(1, np.int32)
+            err: list = []
+
+            def run() -> None:
+                try:
+                    eng.image_to_fen_host(host_in, out, threshold, flip, progress=progress)
+                except BaseException as e:   # noqa: BLE001  (re-raised in the calling thread)
+                    err.append(e)
+
+            worker = threading.Thread(target=run, name="cvb-image-to-fen", daemon=True)
+            worker.start()
+            done = 0
+            while done < n:
+                ready = int(progress[0])
+                if ready > done:
+                    build(done, ready, out)
+                    done = ready
+                elif not worker.is_alive():
+                    break
+                else:
+                    time.sleep(0.0005)
+            worker.join()
+            if err:
+                raise err[0]
+            ready = int(progress[0])
+            if ready > done:
+                build(done, ready, out)
+        else:
+            dev = eng.image_to_fen(host_in.to(eng.device), eng.alloc_outputs(n, full=True, squares=True), threshold, flip)
+            build(0, n, {k: v.cpu() for k, v in dev.items()})
         return results
 
     def extract_board(self, image: NDArray[np.uint8], threshold: float = 0.5) -> BoardExtractionResult:
         """core.py:197-223."""
         assert isinstance(image, np.ndarray) and image.dtype == np.uint8 and image.ndim == 3
-        if min(image.shape[:2]) < 256:
-            raise NotImplementedError(f"B200 path needs images of at least 256x256 (got {image.shape[:2]}); see DESIGN.md")
         self.board_extractor  # noqa: B018
         eng = self._engine
         dev_img = torch.from_numpy(np.ascontiguousarray(image[None])).to(eng.device)
@@ -231,7 +334,8 @@ class ChessVision:
     @staticmethod
     def _logits_to_board(eng, logits_dev, img_dev, hw, threshold) -> BoardExtractionResult:
         mask = eng.mask_from_logits(logits_dev, threshold)
-        quad, found, _ = eng.mask_to_quad(mask)
+        quad, found, status = eng.mask_to_quad(mask)
+        _check_status(status.cpu().numpy())
         logits = logits_dev[0].cpu().numpy()
         if not bool(found[0]):
             logger.info("Failed to extract board from image")
@@ -272,8 +376,7 @@ class ChessVision:
         assert isinstance(mask, np.ndarray) and mask.dtype == np.uint8 and mask.shape == (256, 256)
         eng = _engine_for_statics()
         quad, found, status = eng.mask_to_quad(torch.from_numpy(np.ascontiguousarray(mask[None])).to(eng.device))
-        if int(status[0]) == 2:
-            raise RuntimeError("mask->quad: contour exceeds the kernel's capacity (see DESIGN.md, QUAD_OVERFLOW)")
+        _check_status(status.cpu().numpy())
         return quad[0].cpu().numpy().reshape(4, 1, 2) if bool(found[0]) else None
 
     @staticmethod

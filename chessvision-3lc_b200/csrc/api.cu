@@ -223,6 +223,28 @@ void area_table(int ssize, int dsize, double scale, std::vector<int>& ofs, std::
     }
 }
 
+// OpenCV's coefficient loop of the bilinear resizer in "area mode" (imgproc/resize.cpp, cv::resize with INTER_AREA when an
+// axis is enlarged): (source index, round(2048*(1-f)), round(2048*f)) per destination index; returns xmax.
+int linear_area_table(int ssize, int dsize, std::vector<int>& tab) {
+    const double inv = static_cast<double>(dsize) / ssize, scale = 1.0 / inv;
+    int xmax = dsize;
+    tab.resize(3 * static_cast<size_t>(dsize));
+    for (int d = 0; d < dsize; ++d) {
+        int s = static_cast<int>(std::floor(d * scale));
+        float f = static_cast<float>((d + 1) - (s + 1) * inv);
+        f = f <= 0 ? 0.f : f - std::floor(f);
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s + 1 >= ssize) {
+            xmax = std::min(xmax, d);
+            if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
+        }
+        tab[3 * d] = s;
+        tab[3 * d + 1] = static_cast<int>(std::lrintf((1.f - f) * 2048.f));   // saturate_cast<short>: round half to even
+        tab[3 * d + 2] = static_cast<int>(std::lrintf(f * 2048.f));
+    }
+    return xmax;
+}
+
 // (Re)place a device copy of a host table; the previous copy, if any, is released.
 template <class T>
 int upload_table(T** dst, const std::vector<T>& v) {
@@ -238,11 +260,26 @@ int upload_table(T** dst, const std::vector<T>& v) {
     return 0;
 }
 
-// Tables + staging images for inputs of H x W != 512 x 512 (H, W >= 256), (re)built when the size changes.
+// Tables + staging images for inputs of H x W != 512 x 512, (re)built when the size changes.
 int prepare_size(cvb_ctx* ctx, int H, int W) {
-    if (H < 256 || W < 256) return fail(ctx, -5, "input images must be at least 256 x 256 (INTER_AREA is built for reductions only)");
+    if (H < 1 || W < 1) return fail(ctx, -5, "input images must not be empty");
     if (ctx->gs_H == H && ctx->gs_W == W) return 0;
     CK(cudaDeviceSynchronize());   // a previous size's tables may still be in use
+    if (!ctx->gs_small) {
+        if (cudaMalloc(&ctx->gs_small, static_cast<size_t>(ctx->max_batch) * 256 * 256 * 3) != cudaSuccess ||
+            cudaMalloc(&ctx->gs_big, static_cast<size_t>(ctx->max_batch) * 786432) != cudaSuccess)
+            return fail(ctx, -3, "allocating the resize staging images failed");
+    }
+    ctx->gs_linear = H < 256 || W < 256;   // an enlarged axis: OpenCV switches BOTH axes to its bilinear emulation
+    if (ctx->gs_linear) {
+        std::vector<int> tx, ty;
+        ctx->gs_xmax = linear_area_table(W, 256, tx);
+        linear_area_table(H, 256, ty);
+        if (upload_table(&ctx->gs_lx, tx) || upload_table(&ctx->gs_ly, ty)) return fail(ctx, -3, "allocating the resize tables failed");
+        ctx->gs_H = H;
+        ctx->gs_W = W;
+        return 0;
+    }
     const double fx = static_cast<double>(W) / 256, fy = static_cast<double>(H) / 256;
     const int ix = static_cast<int>(std::lrint(fx)), iy = static_cast<int>(std::lrint(fy));
     const bool fast = std::abs(fx - ix) < 2.220446049250313e-16 && std::abs(fy - iy) < 2.220446049250313e-16;
@@ -253,11 +290,6 @@ int prepare_size(cvb_ctx* ctx, int H, int W) {
     if (upload_table(&ctx->gs_xofs, xo) || upload_table(&ctx->gs_xsi, xs) || upload_table(&ctx->gs_xa, xa) ||
         upload_table(&ctx->gs_yofs, yo) || upload_table(&ctx->gs_ysi, ys) || upload_table(&ctx->gs_ya, ya))
         return fail(ctx, -3, "allocating the INTER_AREA tables failed");
-    if (!ctx->gs_small) {
-        if (cudaMalloc(&ctx->gs_small, static_cast<size_t>(ctx->max_batch) * 256 * 256 * 3) != cudaSuccess ||
-            cudaMalloc(&ctx->gs_big, static_cast<size_t>(ctx->max_batch) * 786432) != cudaSuccess)
-            return fail(ctx, -3, "allocating the resize staging images failed");
-    }
     ctx->gs_int_area = fast ? ix * iy : 0;
     ctx->gs_H = H;
     ctx->gs_W = W;
@@ -267,8 +299,9 @@ int prepare_size(cvb_ctx* ctx, int H, int W) {
 // cv2.resize(img, (256,256), INTER_AREA) (core.py:212) for n <= max_batch images of H x W into ctx->gs_small
 int resize_to_256(cvb_ctx* ctx, const uint8_t* img, int n, int H, int W, uint8_t* out, cudaStream_t s) {
     if (prepare_size(ctx, H, W)) return -2;
-    CK(launch_resize_area(img, out, n, H, W, 256, 256, ctx->gs_xofs, ctx->gs_xsi, ctx->gs_xa, ctx->gs_yofs, ctx->gs_ysi, ctx->gs_ya,
-                          ctx->gs_int_area, s));
+    if (ctx->gs_linear) CK(launch_resize_linear_area(img, out, n, H, W, 256, 256, ctx->gs_lx, ctx->gs_ly, ctx->gs_xmax, s));
+    else CK(launch_resize_area(img, out, n, H, W, 256, 256, ctx->gs_xofs, ctx->gs_xsi, ctx->gs_xa, ctx->gs_yofs, ctx->gs_ysi, ctx->gs_ya,
+                               ctx->gs_int_area, s));
     ctx->launches++;
     return 0;
 }
@@ -368,13 +401,13 @@ int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip,
     }
     {
         StageTimer t(ctx, 2, s);
-        CK(launch_mask_to_quad(mask, quad, found, status, ctx->ws_ncont, ctx->ws_owner, n, ctx->quad_full_only, s));
-        ctx->launches += ctx->quad_full_only ? 1 : 2;
+        CK(launch_mask_to_quad(mask, quad, found, status, ctx->ws_ncont, ctx->ws_owner, ctx->ws_quad_big, n, ctx->quad_full_only, s));
+        ctx->launches += ctx->quad_full_only ? 2 : 3;
     }
     {
         StageTimer t(ctx, 3, s);
         CK(launch_homography(quad, found, ctx->ws_minv, n, static_cast<float>(H) / 256.0f, 512, 512, s));   // _scale_quadrangle: H scales both axes
-        CK(launch_warp_board(img, ctx->ws_minv, found, board, n, H, W, s));
+        CK(launch_warp_board(img, ctx->ws_minv, found, board, o.squares ? o.squares + off * 262144 : nullptr, n, H, W, s));
         ctx->launches += 2;
     }
     for (int c0 = 0; c0 < n; c0 += B) {
@@ -385,11 +418,6 @@ int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip,
                      o.fen ? o.fen + q * 144 : nullptr, s))
             return -2;
     }
-    return 0;
-}
-
-int set_device(cvb_ctx* ctx) {
-    CK(cudaSetDevice(ctx->device));
     return 0;
 }
 
@@ -418,7 +446,8 @@ cvb_ctx* cvb_create(int device, int max_batch) {
         cvb_destroy(ctx);
         return nullptr;
     };
-    if (cudaSetDevice(device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(); }
+    DeviceGuard guard(device);
+    if (!guard.ok) { ctx->err = "cudaSetDevice failed"; return bail(); }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { ctx->err = "cudaGetDeviceProperties failed"; return bail(); }
     if (prop.major != 10) {
@@ -465,6 +494,8 @@ cvb_ctx* cvb_create(int device, int max_batch) {
     rc |= dalloc(ctx, &ctx->ws_ncont, G);
     rc |= dalloc(ctx, &ctx->ws_owner, G * (kQuadMaxBorders + 8));
     rc |= dalloc(ctx, &ctx->ws_found, G);
+    rc |= dalloc(ctx, &ctx->ws_quad_big, quad_big_scratch_bytes());
+    if (!rc && cudaMemset(ctx->ws_quad_big, 0, quad_big_scratch_bytes()) != cudaSuccess) rc = fail(ctx, -2, "clearing the mask->quad scratch failed");
     rc |= dalloc(ctx, &ctx->ws_minv, G * 9);
     rc |= dalloc(ctx, &ctx->ws_board, G * 262144);
     // classifier activations: 3 buffers per level; per square 16x16x64, 8x8x128, 4x4x256, 2x2x512 = 16384..2048 halfs
@@ -490,7 +521,8 @@ cvb_ctx* cvb_create(int device, int max_batch) {
                      dalloc(ctx, &ctx->slot_out[i].status, G) == 0 && dalloc(ctx, &ctx->slot_out[i].probs, G * 832) == 0 &&
                      dalloc(ctx, &ctx->slot_out[i].labels, G * 64) == 0 && dalloc(ctx, &ctx->slot_out[i].labels_valid, G * 64) == 0 &&
                      dalloc(ctx, &ctx->slot_out[i].fen, G * 144) == 0 && dalloc(ctx, &ctx->slot_out[i].logits, G * 65536) == 0 &&
-                     dalloc(ctx, &ctx->slot_out[i].mask, G * 65536) == 0 && dalloc(ctx, &ctx->slot_out[i].board, G * 262144) == 0;
+                     dalloc(ctx, &ctx->slot_out[i].mask, G * 65536) == 0 && dalloc(ctx, &ctx->slot_out[i].board, G * 262144) == 0 &&
+                     dalloc(ctx, &ctx->slot_out[i].squares, G * 262144) == 0;
     }
     if (!ok) {
         if (ctx->err.empty()) ctx->err = "stream/event/slot setup failed";
@@ -501,7 +533,7 @@ cvb_ctx* cvb_create(int device, int max_batch) {
 
 void cvb_destroy(cvb_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
@@ -517,14 +549,15 @@ void cvb_destroy(cvb_ctx* ctx) {
     if (ctx->trainer) cvb_trainer_free(ctx->trainer);
     if (ctx->jpeg) cvb_jpeg_free(ctx->jpeg);
     for (void* q : {static_cast<void*>(ctx->gs_xofs), static_cast<void*>(ctx->gs_xsi), static_cast<void*>(ctx->gs_xa), static_cast<void*>(ctx->gs_yofs),
-                    static_cast<void*>(ctx->gs_ysi), static_cast<void*>(ctx->gs_ya), static_cast<void*>(ctx->gs_small), static_cast<void*>(ctx->gs_big)})
+                    static_cast<void*>(ctx->gs_ysi), static_cast<void*>(ctx->gs_ya), static_cast<void*>(ctx->gs_small), static_cast<void*>(ctx->gs_big),
+                    static_cast<void*>(ctx->gs_lx), static_cast<void*>(ctx->gs_ly)})
         if (q) cudaFree(q);
     delete ctx;
 }
 
 int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     if (!ctx || !sd) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if (ctx->unet_loaded) return fail(ctx, -8, "UNet weights already loaded");
     const int B = ctx->max_batch;
     static const int width[5] = {64, 128, 256, 512, 1024};
@@ -606,7 +639,7 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
 
 int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     if (!ctx || !sd) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if (ctx->resnet_loaded) return fail(ctx, -8, "classifier weights already loaded");
     const int S = ctx->max_batch * 64;
     if (pack_stem(ctx, sd, n, "conv1", "bn1", 1, 7, &ctx->rstem_w, &ctx->rstem_b)) return -4;
@@ -663,7 +696,7 @@ int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
 
 int cvb_resize_area_half(cvb_ctx* ctx, const uint8_t* img, int N, int h, int w, uint8_t* out, void* stream) {
     if (!ctx || !img || !out || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     CK(launch_resize_area_half(img, out, N, h, w, static_cast<cudaStream_t>(stream)));
     ctx->launches++;
     return 0;
@@ -671,7 +704,7 @@ int cvb_resize_area_half(cvb_ctx* ctx, const uint8_t* img, int N, int h, int w, 
 
 int cvb_unet_forward(cvb_ctx* ctx, const uint8_t* img, int N, float thr, float* logits, uint8_t* mask, void* stream) {
     if (!ctx || !img || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     for (int off = 0; off < N; off += ctx->max_batch) {
         const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
         if (unet_forward(ctx, img + static_cast<size_t>(off) * 786432, n, thr, logits ? logits + static_cast<size_t>(off) * 65536 : nullptr,
@@ -683,7 +716,7 @@ int cvb_unet_forward(cvb_ctx* ctx, const uint8_t* img, int N, float thr, float* 
 
 int cvb_mask_from_logits(cvb_ctx* ctx, const float* logits, int N, float thr, uint8_t* mask, void* stream) {
     if (!ctx || !logits || !mask || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     CK(launch_mask_from_logits(logits, mask, thr, static_cast<long long>(N) * 65536, static_cast<cudaStream_t>(stream)));
     ctx->launches++;
     return 0;
@@ -691,13 +724,13 @@ int cvb_mask_from_logits(cvb_ctx* ctx, const float* logits, int N, float thr, ui
 
 int cvb_mask_to_quad(cvb_ctx* ctx, const uint8_t* mask, int N, int32_t* quad, uint8_t* found, int32_t* status, void* stream) {
     if (!ctx || !mask || !quad || !found || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     for (int off = 0; off < N; off += ctx->group) {
         const int n = N - off < ctx->group ? N - off : ctx->group;
         CK(launch_mask_to_quad(mask + static_cast<size_t>(off) * 65536, quad + off * 8, found + off,
-                               status ? status + off : ctx->ws_status, ctx->ws_ncont, ctx->ws_owner, n, ctx->quad_full_only,
+                               status ? status + off : ctx->ws_status, ctx->ws_ncont, ctx->ws_owner, ctx->ws_quad_big, n, ctx->quad_full_only,
                                static_cast<cudaStream_t>(stream)));
-        ctx->launches += ctx->quad_full_only ? 1 : 2;
+        ctx->launches += ctx->quad_full_only ? 2 : 3;
     }
     return 0;
 }
@@ -705,21 +738,30 @@ int cvb_mask_to_quad(cvb_ctx* ctx, const uint8_t* mask, int N, int32_t* quad, ui
 int cvb_warp_squares(cvb_ctx* ctx, const uint8_t* img, const int32_t* quad, const uint8_t* found, int N, int H, int W, uint8_t* board,
                      void* stream) {
     if (!ctx || !img || !quad || !found || !board || N < 0 || H <= 0 || W <= 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     for (int off = 0; off < N; off += ctx->group) {
         const int n = N - off < ctx->group ? N - off : ctx->group;
         CK(launch_homography(quad + off * 8, found + off, ctx->ws_minv, n, static_cast<float>(H) / 256.0f, 512, 512, s));
-        CK(launch_warp_board(img + static_cast<size_t>(off) * H * W * 3, ctx->ws_minv, found + off, board + static_cast<size_t>(off) * 262144, n, H, W, s));
+        CK(launch_warp_board(img + static_cast<size_t>(off) * H * W * 3, ctx->ws_minv, found + off, board + static_cast<size_t>(off) * 262144, nullptr, n, H, W, s));
         ctx->launches += 2;
     }
+    return 0;
+}
+
+int cvb_warp_perspective(cvb_ctx* ctx, const uint8_t* img, int H, int W, int C, const float* corners, int out_w, int out_h, uint8_t* out,
+                         void* stream) {
+    if (!ctx || !img || !corners || !out || H <= 0 || W <= 0 || (C != 1 && C != 3) || out_w <= 0 || out_h <= 0) return -1;
+    CVB_ON_DEVICE(ctx);
+    CK(launch_warp_perspective(img, H, W, C, corners, ctx->ws_minv, out, out_w, out_h, static_cast<cudaStream_t>(stream)));
+    ctx->launches += 2;
     return 0;
 }
 
 int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, float* probs, uint8_t* labels, uint8_t* labels_valid, char* fen,
                  void* stream) {
     if (!ctx || !board || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     for (int off = 0; off < N; off += ctx->max_batch) {
         const int n = N - off < ctx->max_batch ? N - off : ctx->max_batch;
         const size_t o = off;
@@ -732,7 +774,7 @@ int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, float* pro
 
 int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float thr, int flip, const cvb_outputs* out, void* stream) {
     if (!ctx || !img || !out || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     for (int off = 0; off < N; off += ctx->group) {
         const int n = N - off < ctx->group ? N - off : ctx->group;
         if (pipeline_group(ctx, img + static_cast<size_t>(off) * 786432, n, thr, flip, *out, off, static_cast<cudaStream_t>(stream), nullptr))
@@ -743,7 +785,7 @@ int cvb_image_to_fen(cvb_ctx* ctx, const uint8_t* img, int N, float thr, int fli
 
 int cvb_image_to_fen_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, float thr, int flip, const cvb_outputs* out, void* stream) {
     if (!ctx || !img || !out || N < 0 || H <= 0 || W <= 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if ((H != 512 || W != 512) && prepare_size(ctx, H, W)) return -5;
     for (int off = 0; off < N; off += ctx->group) {
         const int n = N - off < ctx->group ? N - off : ctx->group;
@@ -755,7 +797,7 @@ int cvb_image_to_fen_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, f
 
 int cvb_unet_forward_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, float thr, float* logits, uint8_t* mask, void* stream) {
     if (!ctx || !img || N < 0 || H <= 0 || W <= 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if ((H != 512 || W != 512) && prepare_size(ctx, H, W)) return -5;
     const int B = ctx->max_batch;
     for (int off = 0; off < N; off += B) {
@@ -769,19 +811,41 @@ int cvb_unet_forward_hw(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, f
 
 int cvb_resize_area(cvb_ctx* ctx, const uint8_t* img, int N, int H, int W, uint8_t* out, void* stream) {
     if (!ctx || !img || !out || N < 0) return -1;
-    if (set_device(ctx)) return -2;
-    if (prepare_size(ctx, H, W)) return -5;
-    CK(launch_resize_area(img, out, N, H, W, 256, 256, ctx->gs_xofs, ctx->gs_xsi, ctx->gs_xa, ctx->gs_yofs, ctx->gs_ysi, ctx->gs_ya,
-                          ctx->gs_int_area, static_cast<cudaStream_t>(stream)));
-    ctx->launches++;
+    CVB_ON_DEVICE(ctx);
+    return resize_to_256(ctx, img, N, H, W, out, static_cast<cudaStream_t>(stream)) ? -5 : 0;
+}
+
+// Copy-out of one group's results from its device slot to the caller's host arrays (stream s_out); records ev_free[sl].
+static int copy_out_group(cvb_ctx* ctx, const cvb_outputs* oh, int sl, size_t o, int n) {
+    const cvb_outputs& d = ctx->slot_out[sl];
+    cudaStream_t so = ctx->s_out;
+    CK(cudaStreamWaitEvent(so, ctx->ev_comp[sl], 0));
+    if (oh->quad) CK(cudaMemcpyAsync(oh->quad + o * 8, d.quad, n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+    if (oh->found) CK(cudaMemcpyAsync(oh->found + o, d.found, n, cudaMemcpyDeviceToHost, so));
+    if (oh->status) CK(cudaMemcpyAsync(oh->status + o, d.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+    if (oh->probs) CK(cudaMemcpyAsync(oh->probs + o * 832, d.probs, static_cast<size_t>(n) * 832 * sizeof(float), cudaMemcpyDeviceToHost, so));
+    if (oh->labels) CK(cudaMemcpyAsync(oh->labels + o * 64, d.labels, n * 64, cudaMemcpyDeviceToHost, so));
+    if (oh->labels_valid) CK(cudaMemcpyAsync(oh->labels_valid + o * 64, d.labels_valid, n * 64, cudaMemcpyDeviceToHost, so));
+    if (oh->fen) CK(cudaMemcpyAsync(oh->fen + o * 144, d.fen, n * 144, cudaMemcpyDeviceToHost, so));
+    if (oh->logits) CK(cudaMemcpyAsync(oh->logits + o * 65536, d.logits, static_cast<size_t>(n) * 65536 * sizeof(float), cudaMemcpyDeviceToHost, so));
+    if (oh->mask) CK(cudaMemcpyAsync(oh->mask + o * 65536, d.mask, static_cast<size_t>(n) * 65536, cudaMemcpyDeviceToHost, so));
+    if (oh->board) CK(cudaMemcpyAsync(oh->board + o * 262144, d.board, static_cast<size_t>(n) * 262144, cudaMemcpyDeviceToHost, so));
+    if (oh->squares) CK(cudaMemcpyAsync(oh->squares + o * 262144, d.squares, static_cast<size_t>(n) * 262144, cudaMemcpyDeviceToHost, so));
+    CK(cudaEventRecord(ctx->ev_free[sl], so));
     return 0;
 }
 
-int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float thr, int flip, const cvb_outputs* oh) {
+int cvb_image_to_fen_host_progress(cvb_ctx* ctx, const uint8_t* img_host, int N, float thr, int flip, const cvb_outputs* oh,
+                                   volatile int32_t* boards_done) {
     if (!ctx || !img_host || !oh || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
+    if (boards_done) *boards_done = 0;
     const int B = ctx->max_batch, G = ctx->group;
-    int g = 0;
+    // Software pipeline over groups g (two device slots): copy-in(g) and compute(g) are enqueued BEFORE the copy-out of
+    // group g-1, so a copy-out that blocks the calling thread (pageable destination) or the wait for it below never
+    // leaves the GPU without queued work.
+    int g = 0, prev_n = 0;
+    size_t prev_o = 0;
     for (int off = 0; off < N; off += G, ++g) {
         const int n = N - off < G ? N - off : G;
         const int sl = g & 1;
@@ -800,32 +864,35 @@ int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float th
         if (!oh->logits) dev.logits = nullptr;
         if (!oh->mask) dev.mask = nullptr;
         if (!oh->board) dev.board = nullptr;
+        if (!oh->squares) dev.squares = nullptr;
         if (pipeline_group(ctx, ctx->slot_img[sl], n, thr, flip, dev, 0, ctx->s_comp, ctx->ev_in[sl].data())) return -2;
         CK(cudaEventRecord(ctx->ev_comp[sl], ctx->s_comp));
-        CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[sl], 0));
-        cudaStream_t so = ctx->s_out;
-        if (oh->quad) CK(cudaMemcpyAsync(oh->quad + o * 8, d.quad, n * 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
-        if (oh->found) CK(cudaMemcpyAsync(oh->found + o, d.found, n, cudaMemcpyDeviceToHost, so));
-        if (oh->status) CK(cudaMemcpyAsync(oh->status + o, d.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
-        if (oh->probs) CK(cudaMemcpyAsync(oh->probs + o * 832, d.probs, static_cast<size_t>(n) * 832 * sizeof(float), cudaMemcpyDeviceToHost, so));
-        if (oh->labels) CK(cudaMemcpyAsync(oh->labels + o * 64, d.labels, n * 64, cudaMemcpyDeviceToHost, so));
-        if (oh->labels_valid) CK(cudaMemcpyAsync(oh->labels_valid + o * 64, d.labels_valid, n * 64, cudaMemcpyDeviceToHost, so));
-        if (oh->fen) CK(cudaMemcpyAsync(oh->fen + o * 144, d.fen, n * 144, cudaMemcpyDeviceToHost, so));
-        if (oh->logits) CK(cudaMemcpyAsync(oh->logits + o * 65536, d.logits, static_cast<size_t>(n) * 65536 * sizeof(float), cudaMemcpyDeviceToHost, so));
-        if (oh->mask) CK(cudaMemcpyAsync(oh->mask + o * 65536, d.mask, static_cast<size_t>(n) * 65536, cudaMemcpyDeviceToHost, so));
-        if (oh->board) CK(cudaMemcpyAsync(oh->board + o * 262144, d.board, static_cast<size_t>(n) * 262144, cudaMemcpyDeviceToHost, so));
-        CK(cudaEventRecord(ctx->ev_free[sl], so));
+        if (g >= 1) {
+            if (copy_out_group(ctx, oh, sl ^ 1, prev_o, prev_n)) return -2;
+            if (boards_done) {   // progress for a caller that consumes finished groups while the rest is still running
+                CK(cudaEventSynchronize(ctx->ev_free[sl ^ 1]));
+                *boards_done = static_cast<int32_t>(prev_o + prev_n);
+            }
+        }
+        prev_o = o;
+        prev_n = n;
     }
+    if (g >= 1 && copy_out_group(ctx, oh, (g - 1) & 1, prev_o, prev_n)) return -2;
     CK(cudaStreamSynchronize(ctx->s_in));
     CK(cudaStreamSynchronize(ctx->s_comp));
     CK(cudaStreamSynchronize(ctx->s_out));
+    if (boards_done) *boards_done = N;
     return 0;
+}
+
+int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float thr, int flip, const cvb_outputs* oh) {
+    return cvb_image_to_fen_host_progress(ctx, img_host, N, thr, flip, oh, nullptr);
 }
 
 int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias, int Cout,
                    int ksize, int stride, int relu, const void* residual, void* out, void* stream) {
     if (!ctx || !in || !w_packed || !bias || !out) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if ((ksize != 1 && ksize != 3) || (stride != 1 && stride != 2)) return fail(ctx, -5, "conv2d: ksize/stride not supported");
     ConvWeights cw;
     cw.w = const_cast<__half*>(static_cast<const __half*>(w_packed));
@@ -841,7 +908,7 @@ int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, c
 int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias, int Cout,
                      void* out, int out_c_stride, int out_c_off, void* stream) {
     if (!ctx || !in || !w_packed || !bias || !out) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     ConvWeights cw;
     cw.w = const_cast<__half*>(static_cast<const __half*>(w_packed));
     cw.bias = const_cast<float*>(bias);
@@ -856,7 +923,7 @@ int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin,
 
 int cvb_unet_stem(cvb_ctx* ctx, const uint8_t* img, int N, void* out, void* stream) {
     if (!ctx || !img || !out || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if (!ctx->unet_loaded) return fail(ctx, -7, "UNet weights not loaded (call cvb_load_unet)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (ctx->stem_fp32) {
@@ -872,7 +939,7 @@ int cvb_unet_stem(cvb_ctx* ctx, const uint8_t* img, int N, void* out, void* stre
 
 int cvb_resnet_stem(cvb_ctx* ctx, const uint8_t* board, int N, void* out, void* stream) {
     if (!ctx || !board || !out || N < 0) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if (!ctx->resnet_loaded) return fail(ctx, -7, "classifier weights not loaded (call cvb_load_resnet18)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (ctx->stem_fp32) CK(launch_resnet_stem(board, ctx->rstem_w, ctx->rstem_b, static_cast<__half*>(out), N, s));
@@ -883,7 +950,7 @@ int cvb_resnet_stem(cvb_ctx* ctx, const uint8_t* board, int N, void* out, void* 
 
 int cvb_profile(cvb_ctx* ctx, int enable) {
     if (!ctx) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     if (enable && ctx->pev.empty()) {
         ctx->pev.resize(kMaxProfileEvents);
         ctx->pev_stage.resize(kMaxProfileEvents);
@@ -897,7 +964,7 @@ int cvb_profile(cvb_ctx* ctx, int enable) {
 
 int cvb_profile_read(cvb_ctx* ctx, float* ms_out, int n_stages) {
     if (!ctx || !ms_out) return -1;
-    if (set_device(ctx)) return -2;
+    CVB_ON_DEVICE(ctx);
     CK(cudaDeviceSynchronize());
     for (int i = 0; i + 1 < ctx->pev_used; i += 2) {
         float ms = 0.f;

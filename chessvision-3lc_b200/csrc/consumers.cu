@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(1024) k_quality(const float* __restrict__ vals
     }
 
     // ---- k-th largest key by radix select, most significant byte first
-    const int k = static_cast<int>(L * 0.25);
+    // np.sort(flat)[-k:] with k = int(L * 0.25): for L < 4 that is [-0:], i.e. the WHOLE array, not an empty slice
+    int k = static_cast<int>(L * 0.25);
+    if (k == 0) k = L;
     if (tid == 0) {
         s_prefix = 0;
         s_need = static_cast<uint32_t>(k);
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(1024) k_quality(const float* __restrict__ vals
             scores[n * 4 + 3] = total / k * 2.0;
         }
     } else if (tid == 0) {
-        scores[n * 4 + 3] = nan("");   // np.mean of an empty slice
+        scores[n * 4 + 3] = nan("");   // L == 0: np.mean of an empty array
     }
 
     // ---- quadrangle regularity (float32 arithmetic, process_pipeline.py:430-456)
@@ -469,7 +471,7 @@ __global__ void __launch_bounds__(256) k_mask_completeness(const float* __restri
 }
 
 int set_dev(cvb_ctx* ctx) {
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     return 0;
 }
 

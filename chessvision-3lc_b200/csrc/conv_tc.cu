@@ -16,6 +16,7 @@
 //                           fused 1x1 head producing logits + mask)
 #include "common.cuh"
 #include "conv_tc.h"
+#include "launch.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -253,6 +254,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+    griddep_wait();   // everything above overlapped the previous kernel's tail (programmatic dependent launch)
 
     const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
     const int total_tiles = m_tiles * p.n_tiles;
@@ -421,6 +424,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+    if (warp != 0) griddep_wait();   // warp 0 first requests the resident weights (no kernel writes them)
 
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
 
@@ -430,6 +435,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             for (int i = 0; i < 9 * p.c_chunks; ++i) tma_load_2d(base_addr + i * kBBytes, &p.b_map, bar_w, i * 64, 0);
         }
         __syncwarp();
+        griddep_wait();
         int stage = 0;
         uint32_t phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -712,6 +718,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_launch();
+    if (warp != 0) griddep_wait();   // warp 0 first requests the resident weights (no kernel writes them)
 
     const int strips_per_image = p.tiles_h * p.tiles_w;
     const int total_strips = p.tiles_n * strips_per_image;
@@ -728,6 +736,7 @@ __global__ void __launch_bounds__(kRsThreads, 1) conv3x3_rs_kernel(const __grid_
                     for (int dy = 0; dy < 3; ++dy)
                         tma_load_2d(base_addr + ((dxi * p.c_chunks + kc) * 3 + dy) * kBBytes, &p.b_map, bar_w,
                                     ((dy * 3 + dxi) * p.c_chunks + kc) * 64, 0);
+            griddep_wait();
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_strips; t += gridDim.x) {
@@ -1002,6 +1011,7 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
     p.bias = bias;
     L.epilogue = epilogue;
     L.n_max = Nmax;
+    L.pdl = 1;
     if (use_vr && conv_try_rs(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, 1, p.tn);
         if (!rc && p.rs_mode == 1) rc = tmap_act(&p.a_map[1], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 130, 1, 1);
@@ -1049,6 +1059,7 @@ int conv_build_k2s2(ConvLaunch& L, const __half* in, int Nmax, int Ho, int Wo, i
     p.bias = bias;
     L.epilogue = EPI_STORE;
     L.n_max = Nmax;
+    L.pdl = 1;
     return 0;
 }
 
@@ -1116,9 +1127,8 @@ cudaError_t conv_configure() {
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_one(const ConvParams& p, int grid, cudaStream_t s) {
-    conv_tc_kernel<BN, EPI><<<grid, 256, ConvCfg<BN>::kSmemBytes, s>>>(p);
-    return cudaGetLastError();
+static cudaError_t launch_one(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
+    return launch_k(conv_tc_kernel<BN, EPI>, grid, 256, ConvCfg<BN>::kSmemBytes, s, pdl, p);
 }
 
 // Decide whether the vertical-reuse kernel applies to this launch and size its pipeline.
@@ -1184,9 +1194,8 @@ bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
 }
 
 template <int BN, int EPI, bool WS>
-static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s) {
-    conv3x3_vr_kernel<BN, EPI, WS><<<grid, 256, p.smem_bytes, s>>>(p);
-    return cudaGetLastError();
+static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
+    return launch_k(conv3x3_vr_kernel<BN, EPI, WS>, grid, 256, p.smem_bytes, s, pdl, p);
 }
 
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream) {
@@ -1197,34 +1206,36 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     const long long total = 1LL * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
     if (total <= 0) return cudaSuccess;
     const int grid = (int)(total < sm_count ? total : sm_count);
+    const bool pdl = L.pdl != 0;
     if (L.variant == 2) {
+        cudaError_t e;
         if (L.epilogue == EPI_OUTC) {
-            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_OUTC, 0, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
-            else conv3x3_rs_kernel<EPI_OUTC, 1, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            if (p.rs_mode == 0) e = launch_k(conv3x3_rs_kernel<EPI_OUTC, 0, false>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
+            else e = launch_k(conv3x3_rs_kernel<EPI_OUTC, 1, false>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
         } else if (p.pool_out != nullptr) {   // pooling form: no residual (the encoder convs have none)
             if (p.res != nullptr) return cudaErrorInvalidValue;
-            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_STORE, 0, true><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
-            else conv3x3_rs_kernel<EPI_STORE, 1, true><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            if (p.rs_mode == 0) e = launch_k(conv3x3_rs_kernel<EPI_STORE, 0, true>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
+            else e = launch_k(conv3x3_rs_kernel<EPI_STORE, 1, true>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
         } else {
-            if (p.rs_mode == 0) conv3x3_rs_kernel<EPI_STORE, 0, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
-            else conv3x3_rs_kernel<EPI_STORE, 1, false><<<grid, kRsThreads, p.smem_bytes, stream>>>(p);
+            if (p.rs_mode == 0) e = launch_k(conv3x3_rs_kernel<EPI_STORE, 0, false>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
+            else e = launch_k(conv3x3_rs_kernel<EPI_STORE, 1, false>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
         }
-        return cudaGetLastError();
+        return e;
     }
     if (L.variant == 1) {
         const bool ws = p.w_stationary != 0;
-        if (L.epilogue == EPI_OUTC) return launch_vr<64, EPI_OUTC, true>(p, grid, stream);
-        if (L.block_n == 64) return ws ? launch_vr<64, EPI_STORE, true>(p, grid, stream) : launch_vr<64, EPI_STORE, false>(p, grid, stream);
-        return ws ? launch_vr<128, EPI_STORE, true>(p, grid, stream) : launch_vr<128, EPI_STORE, false>(p, grid, stream);
+        if (L.epilogue == EPI_OUTC) return launch_vr<64, EPI_OUTC, true>(p, grid, stream, pdl);
+        if (L.block_n == 64) return ws ? launch_vr<64, EPI_STORE, true>(p, grid, stream, pdl) : launch_vr<64, EPI_STORE, false>(p, grid, stream, pdl);
+        return ws ? launch_vr<128, EPI_STORE, true>(p, grid, stream, pdl) : launch_vr<128, EPI_STORE, false>(p, grid, stream, pdl);
     }
     switch (L.epilogue * 1000 + L.block_n) {
-        case EPI_STORE * 1000 + 64: return launch_one<64, EPI_STORE>(p, grid, stream);
-        case EPI_STORE * 1000 + 128: return launch_one<128, EPI_STORE>(p, grid, stream);
-        case EPI_STORE * 1000 + 256: return launch_one<256, EPI_STORE>(p, grid, stream);
-        case EPI_CONVT * 1000 + 64: return launch_one<64, EPI_CONVT>(p, grid, stream);
-        case EPI_CONVT * 1000 + 128: return launch_one<128, EPI_CONVT>(p, grid, stream);
-        case EPI_CONVT * 1000 + 256: return launch_one<256, EPI_CONVT>(p, grid, stream);
-        case EPI_OUTC * 1000 + 64: return launch_one<64, EPI_OUTC>(p, grid, stream);
+        case EPI_STORE * 1000 + 64: return launch_one<64, EPI_STORE>(p, grid, stream, pdl);
+        case EPI_STORE * 1000 + 128: return launch_one<128, EPI_STORE>(p, grid, stream, pdl);
+        case EPI_STORE * 1000 + 256: return launch_one<256, EPI_STORE>(p, grid, stream, pdl);
+        case EPI_CONVT * 1000 + 64: return launch_one<64, EPI_CONVT>(p, grid, stream, pdl);
+        case EPI_CONVT * 1000 + 128: return launch_one<128, EPI_CONVT>(p, grid, stream, pdl);
+        case EPI_CONVT * 1000 + 256: return launch_one<256, EPI_CONVT>(p, grid, stream, pdl);
+        case EPI_OUTC * 1000 + 64: return launch_one<64, EPI_OUTC>(p, grid, stream, pdl);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -61,6 +61,8 @@ struct ConvLaunch {
     int epilogue;  // ConvEpilogue
     int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel, 2 row-streaming 3x3 kernel (Cout = 64)
     int n_max;     // images the activation / output views were built for
+    int pdl;       // launch with programmatic stream serialization (resident weights are then requested before the previous
+                   // kernel has finished: only for launches whose weights no kernel in the stream writes, i.e. inference)
 };
 
 // Resolve cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda).  Returns 0 on success.

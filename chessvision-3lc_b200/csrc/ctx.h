@@ -63,11 +63,15 @@ struct cvb_ctx {
     int gs_H = 0, gs_W = 0, gs_int_area = 0;
     int *gs_xofs = nullptr, *gs_xsi = nullptr, *gs_yofs = nullptr, *gs_ysi = nullptr;
     float *gs_xa = nullptr, *gs_ya = nullptr;
+    int *gs_lx = nullptr, *gs_ly = nullptr;               // H < 256 or W < 256: tables of the fixed-point bilinear emulation
+    int gs_xmax = 0;
+    bool gs_linear = false;
     uint8_t *gs_small = nullptr, *gs_big = nullptr;      // [B,256,256,3] resized, [B,512,512,3] replicated (UNet stem input)
 
     // ---- geometry
     int32_t *ws_quad = nullptr, *ws_status = nullptr, *ws_ncont = nullptr, *ws_owner = nullptr;
     uint8_t* ws_found = nullptr;
+    uint8_t* ws_quad_big = nullptr;                    // scratch slots + locks of the large-capacity mask->quad kernel
     double* ws_minv = nullptr;
     uint8_t* ws_board = nullptr;                       // [B,512,512]
 
@@ -118,6 +122,26 @@ inline int fail(cvb_ctx* c, int code, const char* fmt, ...) {
         cudaError_t e_ = (call);                                                                          \
         if (e_ != cudaSuccess) return fail(ctx, -2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// Every exported function runs on the context's GPU and leaves the calling thread's current device as it found it
+// (a host program may drive several contexts / GPUs, and PyTorch tracks the runtime's current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;
+        if (cur == dev) { ok = true; return; }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (ok) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define CVB_ON_DEVICE(ctx)                         \
+    DeviceGuard device_guard_((ctx)->device);      \
+    if (!device_guard_.ok) return fail((ctx), -2, "cudaSetDevice(%d) failed", (ctx)->device)
 
 template <class T>
 inline int dalloc(cvb_ctx* ctx, T** p, size_t count) {

@@ -12,6 +12,8 @@
 
 #include <math.h>
 
+#include <type_traits>
+
 namespace cvb {
 
 // =====================================================================================================================
@@ -23,6 +25,13 @@ constexpr int LW = 258;                 // padded label row
 constexpr int kLabBytes = ((LW * LW * 2 + 15) / 16) * 16;
 constexpr int kQuadSmem = kLabBytes + kQuadMaxPoints * (4 + 4 + 2 + 1) + 64;
 constexpr unsigned FULL = 0xffffffffu;
+
+// large-capacity fallback (k_mask_to_quad<true>): per scratch slot int32 labels + P, S, KS, dst (kBigPoints ints each) + the
+// approxPolyDP stack (2 * kBigPoints) + the border-owner table + the chain codes
+constexpr int kBigPoints = 4 * 65536;
+constexpr int kBigBorders = 70000;
+constexpr size_t kBigLabBytes = ((static_cast<size_t>(LW) * LW * 4 + 15) / 16) * 16;
+constexpr size_t kBigSlotBytes = ((kBigLabBytes + static_cast<size_t>(kBigPoints) * 4 * 6 + (kBigBorders + 8) * 4 + kBigPoints + 255) / 256) * 256;
 
 __constant__ int c_off16[16] = {1, -LW + 1, -LW, -LW - 1, -1, LW - 1, LW, LW + 1, 1, -LW + 1, -LW, -LW - 1, -1, LW - 1, LW, LW + 1};
 __constant__ int c_kcos_t[15] = {1, 2, 3, 4, 3, 2, 1, 0, 1, 2, 3, 4, 3, 2, 1};
@@ -39,8 +48,10 @@ __device__ __forceinline__ int pack_pt(int idx) {
 __device__ __forceinline__ int px(int p) { return p & 0xffff; }
 __device__ __forceinline__ int py(int p) { return p >> 16; }
 
-// Suzuki-Abe border following from `start` (lane 0 only).
-__device__ void trace_border(int16_t* lab, int start, int nbd, bool hole, int* P, uint8_t* CODE, Contour& c) {
+// Suzuki-Abe border following from `start` (lane 0 only).  LabT: int16 labels in shared memory, int32 in the large-capacity
+// kernel; `cap` = border points the P / CODE arrays hold (points beyond it are counted, not stored).
+template <typename LabT>
+__device__ void trace_border(LabT* lab, int start, int nbd, bool hole, int* P, uint8_t* CODE, Contour& c, int cap) {
     int s_end = hole ? 0 : 4;
     int s = s_end;
     int i1;
@@ -52,7 +63,7 @@ __device__ void trace_border(int16_t* lab, int start, int nbd, bool hole, int* P
     c.minx = c.maxx = px(p0);
     c.miny = c.maxy = py(p0);
     if (s == s_end) {  // isolated pixel
-        lab[start] = static_cast<int16_t>(-nbd);
+        lab[start] = static_cast<LabT>(-nbd);
         P[0] = p0;
         c.n = 1;
         return;
@@ -67,12 +78,12 @@ __device__ void trace_border(int16_t* lab, int start, int nbd, bool hole, int* P
         } while (lab[i4] == 0);
         s &= 7;
         if (static_cast<unsigned>(s - 1) < static_cast<unsigned>(s_end)) {
-            lab[i3] = static_cast<int16_t>(-nbd);
+            lab[i3] = static_cast<LabT>(-nbd);
         } else if (lab[i3] == 1) {
-            lab[i3] = static_cast<int16_t>(nbd);
+            lab[i3] = static_cast<LabT>(nbd);
         }
         const int p = pack_pt(i3);
-        if (n < kQuadMaxPoints) {
+        if (n < cap) {
             P[n] = p;
             CODE[n] = static_cast<uint8_t>(s);
         }
@@ -267,22 +278,63 @@ __device__ int approx_poly(const int* R, int m, double epsilon, int* dst, int* s
     return new_count;
 }
 
+// BIG = false: labels (int16), border points and the TC89_KCOS work arrays in shared memory, capacities kQuadMaxPoints /
+// kQuadMaxBorders / kQuadMaxVertices; a mask that exceeds one of them gets status QUAD_OVERFLOW.
+// BIG = true:  the same algorithm for exactly those masks with every array in global scratch (int32 labels, kBigPoints
+// border points: four visits of every pixel, which border following cannot exceed), so that no mask a 256x256 image can
+// hold is ever reported as "capacity exceeded".  A handful of scratch slots are shared by the (rare) boards that need them.
+template <bool BIG>
 __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restrict__ mask, int32_t* __restrict__ quad,
                                                         uint8_t* __restrict__ found, int32_t* __restrict__ status,
                                                         int32_t* __restrict__ n_contours, int32_t* __restrict__ owner_scratch,
-                                                        int only_flagged) {
+                                                        int only_flagged, uint8_t* __restrict__ big_scratch, int* __restrict__ big_locks) {
+    using LabT = typename std::conditional<BIG, int32_t, int16_t>::type;
+    using KsT = typename std::conditional<BIG, int32_t, uint16_t>::type;
+    constexpr int kCapPoints = BIG ? kBigPoints : kQuadMaxPoints;
+    constexpr int kCapBorders = BIG ? kBigBorders : kQuadMaxBorders;
+    constexpr int kCapVertices = BIG ? kBigPoints : kQuadMaxVertices;
     extern __shared__ __align__(16) uint8_t smem[];
-    int16_t* lab = reinterpret_cast<int16_t*>(smem);
-    int* P = reinterpret_cast<int*>(smem + kLabBytes);
-    int* S = P + kQuadMaxPoints;
-    uint16_t* KS = reinterpret_cast<uint16_t*>(S + kQuadMaxPoints);
-    uint8_t* CODE = reinterpret_cast<uint8_t*>(KS + kQuadMaxPoints);
-    Contour* cshare = reinterpret_cast<Contour*>(CODE + kQuadMaxPoints);
-
     const int b = blockIdx.x, lane = threadIdx.x;
-    if (only_flagged && status[b] != QUAD_NEED_FULL) return;   // resolved by k_mask_to_quad_fast
+    if (BIG ? status[b] != QUAD_OVERFLOW : (only_flagged && status[b] != QUAD_NEED_FULL)) return;   // resolved by an earlier kernel
+    LabT* lab;
+    int *P, *S, *owner, *poly_dst, *poly_stack;
+    KsT* KS;
+    uint8_t* CODE;
+    Contour* cshare;
+    int slot = -1;
+    if constexpr (BIG) {
+        // claim one of the scratch slots (blocks that hold one run to completion on their own, so spinning cannot deadlock)
+        if (lane == 0) {
+            while (slot < 0) {
+                for (int k = 0; k < kBigSlots && slot < 0; ++k)
+                    if (atomicCAS(big_locks + k, 0, 1) == 0) slot = k;
+                if (slot < 0) __nanosleep(2000);
+            }
+            __threadfence();
+        }
+        slot = __shfl_sync(FULL, slot, 0);
+        uint8_t* base = big_scratch + static_cast<size_t>(slot) * kBigSlotBytes;
+        lab = reinterpret_cast<LabT*>(base);
+        P = reinterpret_cast<int*>(base + kBigLabBytes);
+        S = P + kBigPoints;
+        KS = S + kBigPoints;
+        poly_dst = KS + kBigPoints;
+        poly_stack = poly_dst + kBigPoints;
+        owner = poly_stack + 2 * kBigPoints;
+        CODE = reinterpret_cast<uint8_t*>(owner + kBigBorders + 8);
+        cshare = reinterpret_cast<Contour*>(smem);
+    } else {
+        lab = reinterpret_cast<LabT*>(smem);
+        P = reinterpret_cast<int*>(smem + kLabBytes);
+        S = P + kQuadMaxPoints;
+        KS = reinterpret_cast<KsT*>(S + kQuadMaxPoints);
+        CODE = reinterpret_cast<uint8_t*>(KS + kQuadMaxPoints);
+        cshare = reinterpret_cast<Contour*>(CODE + kQuadMaxPoints);
+        owner = owner_scratch + static_cast<size_t>(b) * (kQuadMaxBorders + 8);
+        poly_dst = S;
+        poly_stack = S + kQuadMaxVertices;
+    }
     const uint8_t* m = mask + static_cast<size_t>(b) * 65536;
-    int* owner = owner_scratch + static_cast<size_t>(b) * (kQuadMaxBorders + 8);
 
     // label image: 0 / 1 with a one-pixel zero frame
     for (int i = lane; i < LW; i += 32) {
@@ -294,7 +346,7 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
     for (int i = lane; i < 65536 / 4; i += 32) {
         const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(m) + i);
         const int y = i >> 6, x = (i & 63) * 4;
-        int16_t* d = lab + (y + 1) * LW + x + 1;
+        LabT* d = lab + (y + 1) * LW + x + 1;
         d[0] = (v & 0xffu) ? 1 : 0;
         d[1] = (v & 0xff00u) ? 1 : 0;
         d[2] = (v & 0xff0000u) ? 1 : 0;
@@ -312,7 +364,7 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
     int best_q[4] = {0, 0, 0, 0};
 
     for (int y = 1; y <= 256; ++y) {
-        const int16_t* row = lab + y * LW;
+        const LabT* row = lab + y * LW;
         int x = 1;
         int lnbd = 0;
         while (x <= 257) {
@@ -340,13 +392,13 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
             if (outer || hole) {
                 ++nbd;
                 const int d = ncont++;
-                if (nbd >= kQuadMaxBorders) {
+                if (nbd >= kCapBorders) {
                     overflow = true;
-                    nbd = kQuadMaxBorders - 1;  // keep labels representable; result is flagged invalid anyway
+                    nbd = kCapBorders - 1;  // keep labels representable; result is flagged invalid anyway
                 }
                 if (lane == 0) {
                     Contour c;
-                    trace_border(lab, y * LW + (hole ? xc - 1 : xc), nbd, hole, P, CODE, c);
+                    trace_border<LabT>(lab, y * LW + (hole ? xc - 1 : xc), nbd, hole, P, CODE, c, kCapPoints);
                     *cshare = c;
                     const int o = hole ? owner[lnbd] : d;
                     owner[nbd] = o;
@@ -358,7 +410,7 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
                 __syncwarp();
                 const bool big = (c.maxx - c.minx + 1) * (c.maxy - c.miny + 1) >= 22937;
                 if (d == 0 || big) {
-                    if (c.n > kQuadMaxPoints) {
+                    if (c.n > kCapPoints) {
                         overflow = true;
                     } else if (c.n > 1) {
                         const int n = c.n;
@@ -375,7 +427,7 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
                                 int k;
                                 const int sv = kcos_point(P, n, i, k);
                                 S[i] = sv;
-                                KS[i] = static_cast<uint16_t>(k);
+                                KS[i] = static_cast<KsT>(k);
                             }
                         }
                         __syncwarp();
@@ -409,7 +461,7 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
                             }
                             int is4 = 0, ov = 0, pass = 0;
                             int q[4] = {0, 0, 0, 0};
-                            if (mv > kQuadMaxVertices) {
+                            if (mv > kCapVertices) {
                                 ov = 1;
                             } else if (mv > 0) {
                                 PolyStats st;
@@ -419,9 +471,8 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
                                 const double ratio = (lo == 0 || hi == 0) ? -1.0 : static_cast<double>(lo) / static_cast<double>(hi);
                                 pass = !(area < 0.35 || area > 1.0) && !(ratio < 0.6);
                                 if (d == 0 || pass) {
-                                    int* dst = S;
-                                    int* stack = S + kQuadMaxVertices;
-                                    const int cnt = approx_poly(P, mv, 0.1 * st.arclen, dst, stack);
+                                    int* dst = poly_dst;
+                                    const int cnt = approx_poly(P, mv, 0.1 * st.arclen, dst, poly_stack);
                                     if (cnt == 4) {
                                         is4 = 1;
                                         for (int j = 0; j < 4; ++j) q[j] = dst[j];
@@ -486,6 +537,10 @@ __global__ void __launch_bounds__(32, 1) k_mask_to_quad(const uint8_t* __restric
         found[b] = ok ? 1 : 0;
         status[b] = overflow ? QUAD_OVERFLOW : (ok ? QUAD_FOUND : QUAD_NONE);
         n_contours[b] = ncont;
+        if constexpr (BIG) {
+            __threadfence();
+            atomicExch(big_locks + slot, 0);
+        }
     }
 }
 
@@ -809,21 +864,27 @@ __global__ void __launch_bounds__(32, 4) k_mask_to_quad_fast(const uint8_t* __re
 cudaError_t configure_quad() {
     cudaError_t e = cudaFuncSetAttribute(k_mask_to_quad_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastSmem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_mask_to_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem);
+    return cudaFuncSetAttribute(k_mask_to_quad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kQuadSmem);
 }
 
+size_t quad_big_scratch_bytes() { return kBigSlotBytes * kBigSlots + 256; }
+
 cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* found, int32_t* status, int32_t* n_contours,
-                                int32_t* owner_scratch, int N, bool full_only, cudaStream_t s) {
+                                int32_t* owner_scratch, uint8_t* big_scratch, int N, bool full_only, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
+    int* locks = reinterpret_cast<int*>(big_scratch + kBigSlotBytes * kBigSlots);   // zero when no kernel is running
+    cudaError_t e;
     if (full_only) {
-        k_mask_to_quad<<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch, 0);
-        return cudaGetLastError();
+        k_mask_to_quad<false><<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch, 0, nullptr, nullptr);
+    } else {
+        // compact kernel for every board, then the full-state kernel for the boards it flagged (early exit otherwise)
+        k_mask_to_quad_fast<<<N, 32, kFastSmem, s>>>(mask, quad, found, status, n_contours);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        k_mask_to_quad<false><<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch, 1, nullptr, nullptr);
     }
-    // compact kernel for every board, then the full-state kernel for the boards it flagged (early exit otherwise)
-    k_mask_to_quad_fast<<<N, 32, kFastSmem, s>>>(mask, quad, found, status, n_contours);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k_mask_to_quad<<<N, 32, kQuadSmem, s>>>(mask, quad, found, status, n_contours, owner_scratch, 1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    // ... and the large-capacity kernel for masks that exceed the shared-memory capacities (early exit otherwise)
+    k_mask_to_quad<true><<<N, 32, 256, s>>>(mask, quad, found, status, n_contours, owner_scratch, 0, big_scratch, locks);
     return cudaGetLastError();
 }
 
@@ -832,33 +893,26 @@ cudaError_t launch_mask_to_quad(const uint8_t* mask, int32_t* quad, uint8_t* fou
 // =====================================================================================================================
 namespace {
 
-__global__ void k_homography(const int32_t* __restrict__ quad, const uint8_t* __restrict__ found, double* __restrict__ minv,
-                             int N, float scale, int out_w, int out_h) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= N) return;
-    double* out = minv + static_cast<size_t>(b) * 9;
-    if (!found[b]) {
-        for (int i = 0; i < 9; ++i) out[i] = 0.0;
-        return;
-    }
+// cv2.getPerspectiveTransform(corners, ((0,0),(w,0),(w,h),(0,h))) followed by the 3x3 inversion of cv2.warpPerspective:
+// corners float32 [4][2] -> out double[9] (all zero when the system is singular).
+__device__ void homography_inverse(const float (&cx)[4], const float (&cy)[4], int out_w, int out_h, double* __restrict__ out) {
     double A[8][8], B[8];
-    const double dstx[4] = {0.0, static_cast<double>(out_w), static_cast<double>(out_w), 0.0};
-    const double dsty[4] = {0.0, 0.0, static_cast<double>(out_h), static_cast<double>(out_h)};
+    const float dstx[4] = {0.f, static_cast<float>(out_w), static_cast<float>(out_w), 0.f};
+    const float dsty[4] = {0.f, 0.f, static_cast<float>(out_h), static_cast<float>(out_h)};
     for (int i = 0; i < 8; ++i)
         for (int j = 0; j < 8; ++j) A[i][j] = 0.0;
     for (int i = 0; i < 4; ++i) {
-        // np.array(approx * sf, dtype=float32): the product is formed in float64, then rounded to float32
-        const double sx = static_cast<double>(static_cast<float>(static_cast<double>(quad[(b * 4 + i) * 2 + 0]) * static_cast<double>(scale)));
-        const double sy = static_cast<double>(static_cast<float>(static_cast<double>(quad[(b * 4 + i) * 2 + 1]) * static_cast<double>(scale)));
+        const double sx = static_cast<double>(cx[i]), sy = static_cast<double>(cy[i]);
         A[i][0] = A[i + 4][3] = sx;
         A[i][1] = A[i + 4][4] = sy;
         A[i][2] = A[i + 4][5] = 1.0;
-        A[i][6] = -sx * dstx[i];
-        A[i][7] = -sy * dstx[i];
-        A[i + 4][6] = -sx * dsty[i];
-        A[i + 4][7] = -sy * dsty[i];
-        B[i] = dstx[i];
-        B[i + 4] = dsty[i];
+        // Point2f products: OpenCV forms them in float32 (exact for the power-of-two board size, not for a general out_size)
+        A[i][6] = static_cast<double>(__fmul_rn(-cx[i], dstx[i]));
+        A[i][7] = static_cast<double>(__fmul_rn(-cy[i], dstx[i]));
+        A[i + 4][6] = static_cast<double>(__fmul_rn(-cx[i], dsty[i]));
+        A[i + 4][7] = static_cast<double>(__fmul_rn(-cy[i], dsty[i]));
+        B[i] = static_cast<double>(dstx[i]);
+        B[i + 4] = static_cast<double>(dsty[i]);
     }
     bool singular = false;
     for (int i = 0; i < 8; ++i) {
@@ -909,6 +963,66 @@ __global__ void k_homography(const int32_t* __restrict__ quad, const uint8_t* __
     out[8] = (a00 * a11 - a01 * a10) * d;
 }
 
+__global__ void k_homography(const int32_t* __restrict__ quad, const uint8_t* __restrict__ found, double* __restrict__ minv,
+                             int N, float scale, int out_w, int out_h) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= N) return;
+    double* out = minv + static_cast<size_t>(b) * 9;
+    if (!found[b]) {
+        for (int i = 0; i < 9; ++i) out[i] = 0.0;
+        return;
+    }
+    float cx[4], cy[4];
+    for (int i = 0; i < 4; ++i) {
+        // np.array(approx * sf, dtype=float32): the product is formed in float64, then rounded to float32
+        cx[i] = static_cast<float>(static_cast<double>(quad[(b * 4 + i) * 2 + 0]) * static_cast<double>(scale));
+        cy[i] = static_cast<float>(static_cast<double>(quad[(b * 4 + i) * 2 + 1]) * static_cast<double>(scale));
+    }
+    homography_inverse(cx, cy, out_w, out_h, out);
+}
+
+// utils.extract_perspective (utils.py:115-132) for ONE image and caller-supplied float32 corners: getPerspectiveTransform +
+// warpPerspective(INTER_LINEAR, BORDER_CONSTANT 0) to an arbitrary out_size, C = 1 or 3 channels, the literal arithmetic
+// of cv::WarpPerspectiveInvoker per destination pixel (destination blocks bw wide: x1 counts from the block start).
+__global__ void k_homography_f32(const float* __restrict__ corners, double* __restrict__ minv, int out_w, int out_h) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    float cx[4], cy[4];
+    for (int i = 0; i < 4; ++i) {
+        cx[i] = corners[2 * i];
+        cy[i] = corners[2 * i + 1];
+    }
+    homography_inverse(cx, cy, out_w, out_h, minv);
+}
+
+__global__ void k_warp_generic(const uint8_t* __restrict__ src, int H, int W, int C, const double* __restrict__ m, uint8_t* __restrict__ out,
+                               int out_w, int out_h, int bw) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= out_w) return;
+    const int bx = (x / bw) * bw, x1 = x - bx;
+    const double X0 = m[0] * bx + m[1] * y + m[2], Y0 = m[3] * bx + m[4] * y + m[5], W0 = m[6] * bx + m[7] * y + m[8];
+    double w = W0 + m[6] * x1;
+    w = w != 0.0 ? 32.0 / w : 0.0;
+    const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + m[0] * x1) * w));
+    const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + m[3] * x1) * w));
+    const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
+    const int sx = max(-32768, min(32767, Xi >> 5)), sy = max(-32768, min(32767, Yi >> 5));
+    const int ax = Xi & 31, ay = Yi & 31;
+    const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+    const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
+    const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
+    const uint8_t* p = src + (static_cast<long long>(sy) * W + sx) * C;
+    const uint8_t* p2 = p + static_cast<long long>(W) * C;
+    uint8_t* o = out + (static_cast<long long>(y) * out_w + x) * C;
+    for (int c = 0; c < C; ++c) {
+        int acc = 16384;
+        if (y0ok && x0ok) acc += w00 * p[c];
+        if (y0ok && x1ok) acc += w01 * p[C + c];
+        if (y1ok && x0ok) acc += w10 * p2[c];
+        if (y1ok && x1ok) acc += w11 * p2[C + c];
+        o[c] = static_cast<uint8_t>(acc >> 15);
+    }
+}
+
 // =====================================================================================================================
 // warp + gray + flip.  cv2.warpPerspective evaluates, per destination pixel of a 64-wide block starting at bx,
 //     W = W0 + M6*x1;  W = W ? 32/W : 0;  X = rint((X0 + M0*x1)*W);  Y = rint((Y0 + M3*x1)*W)         (float64, no FMA)
@@ -954,8 +1068,8 @@ __device__ __noinline__ uint32_t warp_px_exact(const uint8_t* __restrict__ src, 
 }
 
 __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
-                                                    const uint8_t* __restrict__ found, uint8_t* __restrict__ board, int H,
-                                                    int W) {
+                                                    const uint8_t* __restrict__ found, uint8_t* __restrict__ board,
+                                                    uint8_t* __restrict__ squares, int H, int W) {
     extern __shared__ __align__(16) uint8_t wsm[];
     uint32_t* patch = reinterpret_cast<uint32_t*>(wsm);
     double* rowtab = reinterpret_cast<double*>(wsm + kWpRows * kWpStride * 4);   // [64][3]: X0, Y0, W0/32 per tile row
@@ -963,8 +1077,11 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
     const int b = blockIdx.y, t = threadIdx.x;
     const int bx = (blockIdx.x & 7) * 64, by = (blockIdx.x >> 3) * 64;
     uint8_t* dst_tile = board + (static_cast<size_t>(b) * 512 + by) * 512 + (448 - bx);   // destination x -> 511 - x
+    // optional second copy in the layout extract_squares returns (core.py:420-439): u8 [64 squares][64][64], square = 8*row + col
+    uint8_t* sq_tile = squares ? squares + (static_cast<size_t>(b) * 64 + (blockIdx.x >> 3) * 8 + (7 - (blockIdx.x & 7))) * 4096 : nullptr;
     if (!found[b]) {
         *reinterpret_cast<uint4*>(dst_tile + (t >> 2) * 512 + (t & 3) * 16) = make_uint4(0, 0, 0, 0);
+        if (sq_tile) *reinterpret_cast<uint4*>(sq_tile + t * 16) = make_uint4(0, 0, 0, 0);
         return;
     }
     const double* m = minv + static_cast<size_t>(b) * 9;
@@ -1081,6 +1198,7 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
             packed |= gray << (8 * (3 - i));
         }
         *reinterpret_cast<uint32_t*>(dst_tile + ry * 512 + (60 - 4 * xq)) = packed;
+        if (sq_tile) *reinterpret_cast<uint32_t*>(sq_tile + ry * 64 + (60 - 4 * xq)) = packed;
     }
 }
 
@@ -1093,15 +1211,26 @@ cudaError_t launch_homography(const int32_t* quad, const uint8_t* found, double*
     return cudaGetLastError();
 }
 
+cudaError_t launch_warp_perspective(const uint8_t* img, int H, int W, int C, const float* corners, double* minv_scratch, uint8_t* out, int out_w,
+                                    int out_h, cudaStream_t s) {
+    if (out_w <= 0 || out_h <= 0) return cudaSuccess;
+    k_homography_f32<<<1, 32, 0, s>>>(corners, minv_scratch, out_w, out_h);
+    const int bh0 = out_h < 16 ? out_h : 16;              // cv::WarpPerspectiveInvoker: BLOCK_SZ = 32
+    const int bw = (1024 / bh0) < out_w ? (1024 / bh0) : out_w;
+    dim3 grid((out_w + 127) / 128, out_h);
+    k_warp_generic<<<grid, 128, 0, s>>>(img, H, W, C, minv_scratch, out, out_w, out_h, bw);
+    return cudaGetLastError();
+}
+
 cudaError_t configure_warp() {
     return cudaFuncSetAttribute(k_warp_board, cudaFuncAttributeMaxDynamicSharedMemorySize, kWpSmem);
 }
 
-cudaError_t launch_warp_board(const uint8_t* img, const double* minv, const uint8_t* found, uint8_t* board, int N, int H,
-                              int W, cudaStream_t s) {
+cudaError_t launch_warp_board(const uint8_t* img, const double* minv, const uint8_t* found, uint8_t* board, uint8_t* squares, int N,
+                              int H, int W, cudaStream_t s) {
     if (N == 0) return cudaSuccess;
     dim3 grid(64, N);
-    k_warp_board<<<grid, 256, kWpSmem, s>>>(img, minv, found, board, H, W);
+    k_warp_board<<<grid, 256, kWpSmem, s>>>(img, minv, found, board, squares, H, W);
     return cudaGetLastError();
 }
 

@@ -50,13 +50,18 @@ struct JpegHeader {
     int comp_q[3], comp_dc[3], comp_ac[3], comp_id[3];
 };
 
-void build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, int n) {
-    t.present = true;
+// Returns false when the code-length counts do not describe a prefix code (over-subscribed: some code of length `len`
+// would not fit in `len` bits — jdhuff.c's jpeg_make_d_derived_tbl rejects the same streams with JERR_BAD_HUFF_TABLE).
+// Such counts come from corrupt or hostile files and must never index the lookahead table.
+bool build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, int n) {
+    t.present = false;
+    if (n < 0 || n > 256) return false;
     memcpy(t.symbols, symbols, n);
     memset(t.look, 0, sizeof t.look);
     int code = 0, k = 0;
     for (int len = 1; len <= 16; ++len) {
         t.valoff[len] = k - code;
+        if (code + counts[len - 1] > (1 << len)) return false;
         for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
             if (len <= 8) {
                 const int lo = code << (8 - len);
@@ -67,6 +72,7 @@ void build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, in
         code <<= 1;
     }
     t.maxcode[17] = 0x7fffffff;
+    t.present = true;
     for (int i = 0; i < 1024; ++i) {
         t.fast_ac[i] = 0;
         const uint32_t e = t.look[i >> 2];
@@ -77,6 +83,7 @@ void build_table(HuffTable& t, const uint8_t* counts, const uint8_t* symbols, in
         if (v < (1 << (mag - 1))) v += 1 - (1 << mag);
         t.fast_ac[i] = (v * 65536) | (run << 8) | (len + mag);
     }
+    return true;
 }
 
 int exif_orientation(const uint8_t* t, size_t n) {
@@ -122,7 +129,8 @@ int parse_header(const uint8_t* d, size_t n, JpegHeader& H, const char** msg) {
                 int cnt = 0;
                 for (int k = 0; k < 16; ++k) cnt += s[j + 1 + k];
                 if (cnt > 256 || j + 17 + cnt > sl) return bad("corrupt JPEG: Huffman table");
-                build_table(tc ? H.ac[th] : H.dc[th], s + j + 1, s + j + 17, cnt);
+                if (tc > 1) return bad("corrupt JPEG: Huffman table class");
+                if (!build_table(tc ? H.ac[th] : H.dc[th], s + j + 1, s + j + 17, cnt)) return bad("corrupt JPEG: Huffman code lengths are over-subscribed");
                 j += 17 + cnt;
             }
         } else if (m == 0xC0) {
@@ -485,7 +493,7 @@ int cvb_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* coef, ui
 
 int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nbytes, int N, int H, int W, uint8_t* img, void* stream) {
     if (!ctx || !data || !nbytes || !img || N < 0 || H <= 0 || W <= 0 || H % 16 || W % 16) return fail(ctx, -1, "cvb_decode_jpeg: bad argument");
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     if (N == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t px = static_cast<size_t>(H) * W;

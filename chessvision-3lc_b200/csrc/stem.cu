@@ -441,6 +441,49 @@ cudaError_t launch_resize_area(const uint8_t* img, uint8_t* out, int N, int H, i
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// cv2.resize(..., INTER_AREA) when at least one axis is ENLARGED (inputs smaller than 256 px, core.py:212 accepts them).
+// OpenCV only has true area interpolation for reductions in both axes; otherwise it runs its fixed-point bilinear
+// resizer (imgproc/resize.cpp, resizeGeneric_ with HResizeLinear / VResizeLinear<uchar, int, short>) with "area mode"
+// coefficients built on the host (api.cu: linear_area_table): per destination column a source column and two 11-bit
+// weights, the same per row, and
+//     h(row, dx) = S[sx]*a0 + S[sx+1]*a1        (S[sx]*2048 for dx >= xmax, where sx+1 is outside the row)
+//     out        = (((b0 * (h(r0) >> 4)) >> 16) + ((b1 * (h(r1) >> 4)) >> 16) + 2) >> 2
+// in 32-bit integers.  One thread per destination pixel.
+// ----------------------------------------------------------------------------------------------------------------
+__global__ void k_resize_linear_area(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, int H, int W, int dh, int dw,
+                                     const int* __restrict__ xtab, const int* __restrict__ ytab, int xmax, long long total) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int dx = static_cast<int>(i % dw);
+    const long long t = i / dw;
+    const int dy = static_cast<int>(t % dh);
+    const long long n = t / dh;
+    const uint8_t* src = img + n * static_cast<long long>(H) * W * 3;
+    const int sx = xtab[3 * dx], a0 = xtab[3 * dx + 1], a1 = xtab[3 * dx + 2];
+    const int sy = ytab[3 * dy], b0 = ytab[3 * dy + 1], b1 = ytab[3 * dy + 2];
+    const int r0 = min(max(sy, 0), H - 1), r1 = min(max(sy + 1, 0), H - 1);
+    const uint8_t* p0 = src + (static_cast<long long>(r0) * W + sx) * 3;
+    const uint8_t* p1 = src + (static_cast<long long>(r1) * W + sx) * 3;
+    const bool edge = dx >= xmax;
+    uint8_t* o = out + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int h0 = edge ? p0[c] * 2048 : p0[c] * a0 + p0[c + 3] * a1;
+        const int h1 = edge ? p1[c] * 2048 : p1[c] * a0 + p1[c + 3] * a1;
+        const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[c] = static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+cudaError_t launch_resize_linear_area(const uint8_t* img, uint8_t* out, int N, int H, int W, int dh, int dw, const int* xtab,
+                                      const int* ytab, int xmax, cudaStream_t s) {
+    const long long total = 1LL * N * dh * dw;
+    if (total == 0) return cudaSuccess;
+    k_resize_linear_area<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(img, out, H, W, dh, dw, xtab, ytab, xmax, total);
+    return cudaGetLastError();
+}
+
 // u8 [N,h,w,3] -> u8 [N,2h,2w,3] by pixel replication: the exact inverse of the 2x INTER_AREA reduction fused into the
 // UNet stem ((4a+2)>>2 == a), so an image resized by k_resize_area enters the standard pipeline unchanged.
 __global__ void k_double2x(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int h, int w, long long total) {

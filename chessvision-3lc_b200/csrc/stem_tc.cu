@@ -16,6 +16,7 @@
 // + MMA issue.  One CTA per SM, persistent over squares / image blocks.
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace cvb {
 namespace {
@@ -117,6 +118,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
     if (tid < 64) reinterpret_cast<float*>(base + kRsOffBias)[tid] = __ldg(bias + tid);
     Bars b;
     const uint32_t tmem_base = setup<12, 256, 2>(bars, tmem_slot, b, warp, lane);
+    griddep_launch();
+    griddep_wait();   // weights, zero padding, barriers and TMEM were set up under the previous kernel's tail
 
     if (warp < 4) {
         // ------------------------------------------------------------------------------------------------ producers
@@ -292,6 +295,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
     if (tid == 0) tma_prefetch_desc(&omap);
     Bars b;
     const uint32_t tmem_base = setup<12, 128, 4>(bars, tmem_slot, b, warp, lane);
+    griddep_launch();
+    griddep_wait();
 
     if (warp < 4) {
         // ------------------------------------------------------------------------------------------------ producers
@@ -441,17 +446,15 @@ cudaError_t launch_resnet_stem_tc(const uint8_t* board, const void* wsw, const f
                                   cudaStream_t s) {
     const int n_squares = n_boards * 64;
     if (n_squares == 0) return cudaSuccess;
-    k_resnet_stem_tc<<<n_squares < sm_count ? n_squares : sm_count, kRsThreads, kRsSmem, s>>>(board, static_cast<const uint4*>(wsw), bias, out,
-                                                                                           n_squares);
-    return cudaGetLastError();
+    return launch_k(k_resnet_stem_tc, n_squares < sm_count ? n_squares : sm_count, kRsThreads, kRsSmem, s, true, board, static_cast<const uint4*>(wsw), bias,
+                    out, n_squares);
 }
 
 cudaError_t launch_unet_stem_tc(const uint8_t* img, const void* wsw, const float* bias, const CUtensorMap* omap, int N, int sm_count,
                                 cudaStream_t s) {
     const int n_units = N * 32;
     if (n_units == 0) return cudaSuccess;
-    k_unet_stem_tc<<<n_units < sm_count ? n_units : sm_count, kThreads, kUsSmem, s>>>(img, static_cast<const uint4*>(wsw), bias, *omap, N);
-    return cudaGetLastError();
+    return launch_k(k_unet_stem_tc, n_units < sm_count ? n_units : sm_count, kThreads, kUsSmem, s, true, img, static_cast<const uint4*>(wsw), bias, *omap, N);
 }
 
 }  // namespace cvb

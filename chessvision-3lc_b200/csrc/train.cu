@@ -172,7 +172,7 @@ int build_convt_wgrad(cvb_ctx* ctx, cvb_trainer* T, ConvTL& L) {
 int conv_forward(cvb_ctx* ctx, cvb_trainer* T, ConvL& L, const float* img, cudaStream_t s) {
     const long long rows = static_cast<long long>(T->B) * L.H * L.H;
     if (L.Cin == 3) LAUNCH(launch_stem_fwd(img, T->P + L.w_off, L.z, T->B, L.H, L.H, s));
-    else LAUNCH(conv_launch(L.fwd, T->B, ctx->sm_count, s));
+    else LAUNCH((L.fwd.pdl = 0, conv_launch(L.fwd, T->B, ctx->sm_count, s)));
     LAUNCH(launch_bn_stats(L.z, T->sums + 2 * L.bn_off, rows, L.Cout, s));
     LAUNCH(launch_bn_finalize(T->sums + 2 * L.bn_off, T->P + L.g_off, T->P + L.b_off, T->scale + L.bn_off, T->shift + L.bn_off,
                               T->mean + L.bn_off, T->rstd + L.bn_off, T->run_mean + L.bn_off, T->run_var + L.bn_off, L.Cout, rows,
@@ -193,7 +193,7 @@ int conv_backward(cvb_ctx* ctx, cvb_trainer* T, ConvL& L, const float* img, cuda
         return 0;
     }
     LAUNCH(wgrad_launch(L.wgrad, ctx->sm_count, s));
-    if (L.has_dgrad) LAUNCH(conv_launch(L.dgrad, T->B, ctx->sm_count, s));
+    if (L.has_dgrad) LAUNCH((L.dgrad.pdl = 0, conv_launch(L.dgrad, T->B, ctx->sm_count, s)));
     return 0;
 }
 
@@ -201,7 +201,7 @@ int convt_backward(cvb_ctx* ctx, cvb_trainer* T, ConvTL& L, cudaStream_t s) {
     const long long rows = static_cast<long long>(T->B) * 4 * L.H * L.H;
     LAUNCH(launch_colsum(L.dcat, rows, L.Cout, 2 * L.Cout, L.Cout, T->G + L.b_off, 1.0f / T->cfg.loss_scale, s));
     LAUNCH(wgrad_launch(L.wgrad, ctx->sm_count, s));
-    LAUNCH(conv_launch(L.dgrad, T->B, ctx->sm_count, s));
+    LAUNCH((L.dgrad.pdl = 0, conv_launch(L.dgrad, T->B, ctx->sm_count, s)));
     return 0;
 }
 
@@ -240,7 +240,7 @@ int cvb_train_default_config(cvb_train_config* cfg) {
 
 int cvb_train_create(cvb_ctx* ctx, const cvb_tensor* sd, int n, const cvb_train_config* cfg_in) {
     if (!ctx || !sd) return -1;
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     if (ctx->trainer) return fail(ctx, -8, "a trainer already exists on this context");
     cvb_train_config cfg;
     cvb_train_default_config(&cfg);
@@ -434,7 +434,7 @@ int cvb_train_forward_backward(cvb_ctx* ctx, const float* img, const float* mask
     if (!ctx || !img || !mask || !loss) return -1;
     cvb_trainer* T = ctx->trainer;
     if (!T) return fail(ctx, -7, "no trainer (call cvb_train_create)");
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     auto& C = T->conv;
     const int B = T->B;
@@ -451,7 +451,7 @@ int cvb_train_forward_backward(cvb_ctx* ctx, const float* img, const float* mask
         if (conv_forward(ctx, T, C[2 + 2 * d], img, s) || conv_forward(ctx, T, C[3 + 2 * d], img, s)) return -2;
     }
     for (int u = 0; u < 4; ++u) {
-        LAUNCH(conv_launch(T->convt[u].fwd, B, ctx->sm_count, s));
+        LAUNCH((T->convt[u].fwd.pdl = 0, conv_launch(T->convt[u].fwd, B, ctx->sm_count, s)));
         if (conv_forward(ctx, T, C[10 + 2 * u], img, s) || conv_forward(ctx, T, C[11 + 2 * u], img, s)) return -2;
     }
     const long long P = static_cast<long long>(B) * 65536;
@@ -486,7 +486,7 @@ int cvb_train_optimizer_step(cvb_ctx* ctx, float lr, float grad_scale, void* str
     if (!ctx) return -1;
     cvb_trainer* T = ctx->trainer;
     if (!T) return fail(ctx, -7, "no trainer (call cvb_train_create)");
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CK(launch_optimizer(T->P, T->G, T->SQ, T->MB, static_cast<long long>(T->n_params), T->norm, grad_scale, T->cfg.max_grad_norm, lr,
                         T->cfg.alpha, T->cfg.eps, T->cfg.weight_decay, T->cfg.momentum, ctx->sm_count, s));
@@ -507,7 +507,7 @@ int cvb_train_export(cvb_ctx* ctx, int what, const cvb_tensor* out, int n) {
     if (!ctx || !out) return -1;
     cvb_trainer* T = ctx->trainer;
     if (!T) return fail(ctx, -7, "no trainer (call cvb_train_create)");
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     CK(cudaDeviceSynchronize());
     std::vector<float> hp(T->n_params), hrm(T->bn_channels), hrv(T->bn_channels);
     CK(cudaMemcpy(hp.data(), what == 0 ? T->P : T->G, T->n_params * sizeof(float), cudaMemcpyDeviceToHost));
@@ -563,7 +563,7 @@ int cvb_wgrad3x3_f16(cvb_ctx* ctx, const void* dz, const void* x, int N, int H, 
                      void* stream) {
     if (!ctx || !dz || !x || !dw) return -1;
     if (H != W || Cin % 64 || Cout % 64) return fail(ctx, -5, "cvb_wgrad3x3_f16: square images and channel multiples of 64 only");
-    CK(cudaSetDevice(ctx->device));
+    CVB_ON_DEVICE(ctx);
     if (wgrad_configure() != cudaSuccess) return fail(ctx, -2, "wgrad kernel attribute setup failed");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cvb_trainer tmp;

@@ -48,6 +48,8 @@ typedef struct cvb_outputs {
     uint8_t* labels;       /* [N,64]       argmax class per square, order a8..h8,a7..h1 (core.py:326)          */
     uint8_t* labels_valid; /* [N,64]       after rule 1 "no_pawns_on_ends" (core.py:451-469)                   */
     char* fen;             /* [N,2,72]     [0] original_fen, [1] fen; NUL padded (core.py:336,350)             */
+    uint8_t* squares;      /* [N,64,64,64] the board again as 64 crops in extract_squares order (core.py:420-439:
+                              PositionResult.squares); written by the warp kernel, zero where !found               */
 } cvb_outputs;
 
 CVB_API int cvb_version(void);
@@ -80,6 +82,12 @@ CVB_API int cvb_mask_to_quad(cvb_ctx* ctx, const uint8_t* mask, int N, int32_t* 
 CVB_API int cvb_warp_squares(cvb_ctx* ctx, const uint8_t* img, const int32_t* quad, const uint8_t* found, int N, int H, int W,
                      uint8_t* board, void* stream);
 
+/* utils.extract_perspective (utils.py:115-132) for one image and caller-supplied corners: cv2.getPerspectiveTransform(corners,
+ * ((0,0),(w,0),(w,h),(0,h))) + cv2.warpPerspective(img, M, (w,h)) (INTER_LINEAR, BORDER_CONSTANT 0), bit-identical to OpenCV.
+ * img u8[H,W,C] (C = 1 or 3), corners f32[4][2] (x,y), out u8[out_h,out_w,C]; all device pointers. */
+CVB_API int cvb_warp_perspective(cvb_ctx* ctx, const uint8_t* img, int H, int W, int C, const float* corners, int out_w, int out_h,
+                                 uint8_t* out, void* stream);
+
 /* classify_position + process_position_probabilities (core.py:225-249, 310-355) on boards u8[N,512,512]. */
 CVB_API int cvb_classify(cvb_ctx* ctx, const uint8_t* board, int N, int flip, float* probs, uint8_t* labels,
                  uint8_t* labels_valid, char* fen, void* stream);
@@ -104,6 +112,11 @@ CVB_API int cvb_resize_area(cvb_ctx* ctx, const uint8_t* img, int N, int H, int 
  * processed and copied out on three streams so that PCIe transfers overlap compute.  Synchronous on return. */
 CVB_API int cvb_image_to_fen_host(cvb_ctx* ctx, const uint8_t* img_host, int N, float threshold, int flip,
                           const cvb_outputs* out_host);
+/* Same; *boards_done (host memory, may be NULL) is advanced to the number of leading boards whose results have landed in
+ * out_host, so that another host thread can consume finished groups while the rest of the batch is still in flight
+ * (ChessVision.process_images builds its result objects that way). */
+CVB_API int cvb_image_to_fen_host_progress(cvb_ctx* ctx, const uint8_t* img_host, int N, float threshold, int flip,
+                                           const cvb_outputs* out_host, volatile int32_t* boards_done);
 
 /* Building block exposed for parity tests: one convolution layer on fp16 NHWC device tensors through the tcgen05
  * kernel.  ksize in {1,3} (pad = ksize/2), stride in {1,2}; w_packed fp16 [Cout][ksize*ksize*Cin] with

@@ -48,16 +48,66 @@ def _area_tab(ssize: int, dsize: int, scale: float):
     return out
 
 
+def _linear_area_tab(ssize: int, dsize: int):
+    """Coefficient loop of OpenCV's bilinear resizer in "area mode" (imgproc/resize.cpp, cv::resize with INTER_AREA when an
+    axis is enlarged): per destination index the left source index and two weights in 1/2048 (saturate_cast<short> of
+    float32 products), and the first destination index whose right tap is outside the row."""
+    import math
+    inv = dsize / ssize
+    scale = 1.0 / inv
+    ofs = np.zeros(dsize, np.int64)
+    wgt = np.zeros((dsize, 2), np.int64)
+    dmax = dsize
+    for d in range(dsize):
+        s = math.floor(d * scale)
+        f = np.float32((d + 1) - (s + 1) * inv)
+        f = np.float32(0.0) if f <= 0 else np.float32(f - np.float32(math.floor(f)))
+        if s < 0:
+            f, s = np.float32(0), 0
+        if s + 1 >= ssize:
+            dmax = min(dmax, d)
+            if s >= ssize - 1:
+                f, s = np.float32(0), ssize - 1
+        ofs[d] = s
+        wgt[d, 0] = int(np.rint(np.float32(np.float32(1.0) - f) * np.float32(2048)))
+        wgt[d, 1] = int(np.rint(np.float32(f) * np.float32(2048)))
+    return ofs, wgt, dmax
+
+
+def resize_area_enlarge(img: np.ndarray, dsize=(256, 256)) -> np.ndarray:
+    """``cv2.resize(img, dsize, interpolation=cv2.INTER_AREA)`` when at least one axis is enlarged.  OpenCV implements true
+    area interpolation for reductions only ("In other cases it is emulated using some variant of bilinear", resize.cpp):
+    both axes then go through the 8-bit fixed-point bilinear resizer with area-mode weights,
+    ``h = S[sx]*a0 + S[sx+1]*a1`` per source row and ``(((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2`` per pixel
+    [pinned bit for bit against live cv2 in tests/test_oracle_geometry.py]."""
+    dw, dh = dsize
+    sh, sw, cn = img.shape
+    xo, xa, xmax = _linear_area_tab(sw, dw)
+    yo, ya, _ = _linear_area_tab(sh, dh)
+    src = img.astype(np.int64)
+    x1 = np.minimum(xo + 1, sw - 1)
+    hbuf = src[:, xo] * xa[None, :, 0, None] + src[:, x1] * xa[None, :, 1, None]
+    edge = np.arange(dw) >= xmax
+    hbuf[:, edge] = src[:, xo[edge]] * 2048
+    s0, s1 = hbuf[np.clip(yo, 0, sh - 1)], hbuf[np.clip(yo + 1, 0, sh - 1)]
+    b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+    out = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def resize_area(img: np.ndarray, dsize=(256, 256)) -> np.ndarray:
-    """``cv2.resize(img, dsize, interpolation=cv2.INTER_AREA)`` for a reduction in both axes (core.py:212), u8[H,W,C] with
-    H >= dsize[1], W >= dsize[0].  Two code paths in OpenCV, both restated bit for bit [pinned against live cv2]:
+    """``cv2.resize(img, dsize, interpolation=cv2.INTER_AREA)`` (core.py:212), u8[H,W,C].  An enlarged axis sends the call to
+    :func:`resize_area_enlarge`; a reduction in both axes (H >= dsize[1], W >= dsize[0]) has two code paths in OpenCV,
+    both restated bit for bit [pinned against live cv2]:
     integer scale factors average whole cells in integers ((a+b+c+d+2)>>2 for 2x2, round-half-even of sum * float32(1/area)
     otherwise); everything else accumulates float32 products row by row — horizontally in table order into a row buffer,
     then ``sum = beta*buf`` for the first source row of a destination row and ``sum += beta*buf`` after it — and rounds
     half to even at the end.  No fused multiply-add anywhere."""
     dw, dh = dsize
     sh, sw, cn = img.shape
-    assert img.dtype == np.uint8 and sh >= dh and sw >= dw, "INTER_AREA restatement covers reductions only"
+    assert img.dtype == np.uint8
+    if sh < dh or sw < dw:
+        return resize_area_enlarge(img, dsize)
     fx, fy = sw / dw, sh / dh
     ix, iy = int(round(fx)), int(round(fy))
     if abs(fx - ix) < 2.220446049250313e-16 and abs(fy - iy) < 2.220446049250313e-16:
@@ -439,6 +489,31 @@ def find_quadrangle(mask: np.ndarray):
     return None
 
 
+def find_quadrangle_cv2(mask: np.ndarray):
+    """``ChessVision._find_quadrangle`` (core.py:358-411) spelled with the same cv2 calls the reference makes -- the fast
+    checker for large fuzz suites (``find_quadrangle`` above is the cv2-free restatement and is pinned against this one and
+    against the unmodified reference in tests/test_oracle_geometry.py / oracle/make_golden_masks.py)."""
+    import cv2
+    contours, _ = cv2.findContours(mask, cv2.RETR_CCOMP, cv2.CHAIN_APPROX_TC89_KCOS)
+    if len(contours) > 1:
+        area = float(mask.shape[0] * mask.shape[1])
+        kept = []
+        for c in contours:
+            a = cv2.contourArea(c) / area
+            if a < 0.35 or a > 1.0:
+                continue
+            _, _, w, h = cv2.boundingRect(c)
+            if _ratio(h, w) < 0.6:
+                continue
+            kept.append(c)
+        contours = kept
+    for c in contours:
+        cand = cv2.approxPolyDP(c, 0.1 * cv2.arcLength(c, True), True)
+        if len(cand) == 4:
+            return cand[[3, 0, 1, 2], :, :] if cand[0, 0, 0] < cand[2, 0, 0] else cand
+    return None
+
+
 def scale_quadrangle(q: np.ndarray, orig_hw) -> np.ndarray:
     return np.array(q * (orig_hw[0] / 256.0), dtype=np.float32)  # height for both axes (core.py:414-417)
 
@@ -450,18 +525,20 @@ def scale_quadrangle(q: np.ndarray, orig_hw) -> np.ndarray:
 
 def perspective_matrix(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
     """cv2.getPerspectiveTransform: 8x8 system, LU with partial pivoting in float64."""
-    src = np.asarray(src, np.float32).reshape(4, 2).astype(np.float64)
-    dst = np.asarray(dst, np.float32).reshape(4, 2).astype(np.float64)
+    src = np.asarray(src, np.float32).reshape(4, 2)
+    dst = np.asarray(dst, np.float32).reshape(4, 2)
     A = np.zeros((8, 8))
     b = np.zeros(8)
     for i in range(4):
         A[i, 0] = A[i + 4, 3] = src[i, 0]
         A[i, 1] = A[i + 4, 4] = src[i, 1]
         A[i, 2] = A[i + 4, 5] = 1.0
-        A[i, 6] = -src[i, 0] * dst[i, 0]
-        A[i, 7] = -src[i, 1] * dst[i, 0]
-        A[i + 4, 6] = -src[i, 0] * dst[i, 1]
-        A[i + 4, 7] = -src[i, 1] * dst[i, 1]
+        # Point2f * Point2f: OpenCV forms these products in float32 before they enter the float64 system (exact whenever the
+        # destination size is a power of two, as for the 512 x 512 board)
+        A[i, 6] = np.float32(-src[i, 0] * dst[i, 0])
+        A[i, 7] = np.float32(-src[i, 1] * dst[i, 0])
+        A[i + 4, 6] = np.float32(-src[i, 0] * dst[i, 1])
+        A[i + 4, 7] = np.float32(-src[i, 1] * dst[i, 1])
         b[i] = dst[i, 0]
         b[i + 4] = dst[i, 1]
     m = 8
@@ -511,11 +588,19 @@ def invert3(M: np.ndarray) -> np.ndarray:
 WARP_BLOCK_W = 64  # cv::WarpPerspectiveInvoker tiles the destination 64 wide x 16 high for a 512x512 output
 
 
+def warp_block_width(out_w: int, out_h: int) -> int:
+    """Width of the destination blocks of cv::WarpPerspectiveInvoker (imgproc/imgwarp.cpp, BLOCK_SZ = 32):
+    bh0 = min(16, height); bw0 = min(1024 / bh0, width) -- 64 for every output at least 64 wide and 16 high."""
+    bh0 = min(16, out_h)
+    return min(1024 // bh0, out_w)
+
+
 def warp_coords(Minv: np.ndarray, out_w: int, out_h: int):
     """Fixed-point source coordinates (1/32 px) for every destination pixel, OpenCV's evaluation order."""
     m = Minv.reshape(9)
     xs = np.arange(out_w)
-    bx = (xs // WARP_BLOCK_W) * WARP_BLOCK_W
+    bw = warp_block_width(out_w, out_h)
+    bx = (xs // bw) * bw
     x1 = (xs - bx).astype(np.float64)
     bx = bx.astype(np.float64)
     ys = np.arange(out_h, dtype=np.float64)[:, None]

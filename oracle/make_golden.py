@@ -34,65 +34,7 @@ REF = os.environ.get("CV_REFERENCE", "/root/reference")
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
-def install_standins():
-    import torchvision
-
-    chess = types.ModuleType("chess")
-    chess.SQUARE_NAMES = [f + r for r in "12345678" for f in "abcdefgh"]
-
-    class Piece:
-        def __init__(self, sym):
-            self.sym = sym
-
-        @classmethod
-        def from_symbol(cls, sym):
-            return cls(sym)
-
-        def symbol(self):
-            return self.sym
-
-    class BaseBoard:
-        def __init__(self, board_fen=None):
-            self.sq = [None] * 64
-
-        def set_piece_at(self, square, piece, promoted=False):
-            self.sq[square] = piece
-
-        def board_fen(self, promoted=False):
-            rows = []
-            for r in range(7, -1, -1):
-                row, e = "", 0
-                for f in range(8):
-                    p = self.sq[r * 8 + f]
-                    if p is None:
-                        e += 1
-                    else:
-                        row += (str(e) if e else "") + p.symbol()
-                        e = 0
-                rows.append(row + (str(e) if e else ""))
-            return "/".join(rows)
-
-    chess.Piece, chess.BaseBoard = Piece, BaseBoard
-    sys.modules["chess"] = chess
-
-    timm = types.ModuleType("timm")
-
-    def create_model(model_id, num_classes=1000, in_chans=3, **kw):
-        assert model_id == "resnet18"
-        m = torchvision.models.resnet18(num_classes=num_classes)
-        m.conv1 = torch.nn.Conv2d(in_chans, 64, 7, 2, 3, bias=False)
-        return m
-
-    timm.create_model = create_model
-    sys.modules["timm"] = timm
-
-
-def load_reference():
-    install_standins()
-    sys.path.insert(0, REF)
-    import chessvision  # the reference package, unmodified
-    assert chessvision.__file__.startswith(REF), chessvision.__file__
-    return chessvision
+from oracle.ref_loader import install_standins, load_reference  # noqa: E402,F401  (stand-ins for `chess` / `timm`, see there)
 
 
 def sha(a: np.ndarray) -> str:

@@ -73,3 +73,49 @@ def board_image(rng, size=512):
     img[inside & check] = a
     img[inside & ~check] = b
     return img, q
+
+
+def comb_mask(rng, teeth=None):
+    """A board-sized blob whose border is a one-pixel comb: tens of thousands of border points in ONE contour, far beyond the
+    shared-memory capacity of the contour kernels (8,192 points) -- the large-capacity path must take it."""
+    m = np.zeros((256, 256), np.uint8)
+    x0, x1 = int(rng.integers(8, 40)), int(rng.integers(216, 248))
+    y0, y1 = int(rng.integers(8, 40)), int(rng.integers(216, 248))
+    step = teeth or int(rng.integers(2, 4))
+    m[y1 - 5:y1, x0:x1] = 255                            # the spine ...
+    m[y0:y1 - 5, x0:x1:step] = 255                       # ... and one-pixel teeth standing on it: a single component
+    return m
+
+
+def fuzz_masks(seed, n):
+    """Masks for the large mask->quad fuzz: board-like quadrilaterals made ragged by blur + noise, holes and specks, thin
+    frames (hole contours that pass the area filter), several blobs, salt-and-pepper fields with thousands of borders, and
+    combs whose single contour exceeds every shared-memory capacity."""
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        k = len(out) % 16
+        if k < 5:
+            out.append(quad_mask(rng, noise=rng.uniform(0.05, 0.5), sigma=rng.uniform(0.8, 5), holes=int(rng.integers(0, 4)),
+                                 specks=int(rng.integers(0, 10))))
+        elif k < 9:
+            out.append(quad_mask(rng, holes=int(rng.integers(0, 6)), specks=int(rng.integers(0, 16))))
+        elif k < 11:
+            out.append(quad_mask(rng))
+        elif k == 11:                                    # a frame: the hole border is the board candidate
+            m = quad_mask(rng)
+            inner = cv2.erode(m, np.ones((3, 3), np.uint8), iterations=int(rng.integers(2, 12)))
+            out.append(np.where(inner > 0, 0, m).astype(np.uint8))
+        elif k == 12:                                    # two blobs
+            m = quad_mask(rng)
+            m[:, :int(rng.integers(100, 156))] = 0
+            out.append(np.maximum(m, np.roll(m, int(rng.integers(-120, -90)), 1)))
+        elif k == 13:                                    # salt and pepper on a board
+            m = quad_mask(rng)
+            flip = rng.random(m.shape) < rng.uniform(0.01, 0.3)
+            out.append(np.where(flip, 255 - m, m).astype(np.uint8))
+        elif k == 14:
+            out.append(comb_mask(rng))
+        else:                                            # a board with a comb-like ragged edge from heavy noise
+            out.append(quad_mask(rng, noise=rng.uniform(0.5, 1.2), sigma=0.6))
+    return np.stack(out)

@@ -21,7 +21,7 @@ def test_reference_arm_prints_one_json_line():
     for k in REQUIRED:
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "boards/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "reference" and "stage_ms_per_board" in d["cpu_baseline"] and d["cpu_baseline"]["cores"] >= 1 and "workload" in d["config"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
 
 

@@ -82,3 +82,35 @@ def test_product_package_never_imports_the_oracle():
         assert "import oracle" not in text and "from oracle" not in text, f"{f.name} imports the oracle"
     for f in (PKG / "csrc").iterdir():
         assert "oracle" not in f.read_text(), f"{f.name} mentions the oracle"
+
+
+def test_jpeg_header_rejects_oversubscribed_huffman_tables(lib):
+    """A DHT segment whose code-length counts do not form a prefix code (255 codes of length 1, ...) used to index far
+    past the 256-entry lookahead table; it must come back as -6 (unsupported / corrupt), for every table class and for
+    random count vectors, and the host-only entry points must survive it (no GPU needed: parsing is host code)."""
+    import numpy as np
+    lib.cvb_jpeg_info.restype = ctypes.c_int
+    lib.cvb_jpeg_info.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+    lib.cvb_jpeg_coefficients.restype = ctypes.c_int
+    lib.cvb_jpeg_coefficients.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+
+    def stream(counts, tc_th=0x00):
+        n = int(sum(counts))
+        seg = bytes([tc_th]) + bytes(counts) + bytes(range(256))[:n]
+        return b"\xff\xd8\xff\xc4" + (len(seg) + 2).to_bytes(2, "big") + seg + b"\xff\xd9"
+
+    h, w = ctypes.c_int32(), ctypes.c_int32()
+    bad = [[255] + [0] * 15, [0, 5] + [0] * 14, [1, 1, 3] + [0] * 13, [0] * 7 + [255, 1] + [0] * 7, [2, 1] + [0] * 14]
+    for counts in bad:
+        for cls in (0x00, 0x10, 0x13):
+            buf = stream(counts, cls)
+            assert lib.cvb_jpeg_info(buf, len(buf), ctypes.byref(h), ctypes.byref(w)) == -6, counts
+    rng = np.random.default_rng(5)
+    scratch = (ctypes.c_int16 * (512 * 512 * 3 // 2))()
+    for _ in range(400):
+        counts = rng.integers(0, 20, 16).tolist()
+        if sum(counts) > 256:
+            continue
+        buf = stream(counts, int(rng.integers(0, 2)) << 4 | int(rng.integers(0, 4)))
+        assert lib.cvb_jpeg_info(buf, len(buf), ctypes.byref(h), ctypes.byref(w)) == -6   # no scan either way: never 0
+        assert lib.cvb_jpeg_coefficients(buf, len(buf), scratch, None) == -6

@@ -91,6 +91,16 @@ def test_quality_scores_on_pipeline_logits(engine):
         assert abs(scores[i, 3] - om.probability_confidence(logits[i])) <= 2e-6 * abs(scores[i, 3])
 
 
+def test_probability_confidence_of_fewer_than_four_values(engine):
+    """k = int(L * 0.25) is 0 for L < 4 and numpy's [-0:] is then the WHOLE array (process_pipeline.py:463-466), not an empty one."""
+    for L in (1, 2, 3, 4, 5, 7, 8):
+        v = np.random.default_rng(L).normal(size=(3, L)).astype(np.float32)
+        got = engine.quality_scores(torch.from_numpy(v).cuda()).cpu().numpy()[:, 3]
+        for i in range(3):
+            want = om.probability_confidence(v[i])
+            assert abs(got[i] - want) <= 2e-6 * abs(want), (L, got[i], want)
+
+
 def test_data_test_accuracy_from_device_outputs_equals_the_oracle():
     """The reference's evaluation flow (scripts/eval/evaluate.py:227-330) end to end on the device — decode, image->FEN,
     metrics — against the oracle's metrics on the REFERENCE's outputs for the same 38 files (golden vectors)."""

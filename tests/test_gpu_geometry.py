@@ -106,3 +106,108 @@ def test_warp_squares_bit_exact(engine):
             continue
         want = og.extract_board(imgs[i], og.scale_quadrangle(quads[i].reshape(4, 1, 2), (512, 512)))
         assert np.array_equal(board[i], want), f"board {i}: {(board[i] != want).sum()} bytes differ"
+
+
+def _run_quads(eng, masks):
+    quad, found, status = eng.mask_to_quad(torch.from_numpy(np.ascontiguousarray(masks)).cuda())
+    return quad.cpu().numpy(), found.cpu().numpy(), status.cpu().numpy()
+
+
+def test_mask_to_quad_fuzz_10k_against_cv2_and_the_oracle(engine):
+    """10,240 seeded masks (blur + noise, holes, specks, frames, several blobs, salt-and-pepper fields, combs) through the
+    three-kernel mask->quad path; every result must equal ChessVision._find_quadrangle spelled with the reference's own cv2
+    calls (oracle.geometry.find_quadrangle_cv2), and every 64th the cv2-free oracle too.  No status other than none / found."""
+    n_found = n_total = 0
+    for part in range(10):
+        masks = synth.fuzz_masks(seed=1000 + part, n=1024)
+        quad, found, status = _run_quads(engine, masks)
+        assert set(np.unique(status)) <= {0, 1}, f"part {part}: status values {np.unique(status)}"
+        for i, m in enumerate(masks):
+            want = og.find_quadrangle_cv2(m)
+            assert bool(found[i]) == (want is not None), f"part {part} mask {i}: found flag differs from cv2"
+            if want is not None:
+                n_found += 1
+                assert np.array_equal(quad[i], want.reshape(4, 2)), f"part {part} mask {i}: {quad[i].tolist()} != {want.reshape(4, 2).tolist()}"
+            if i % 64 == 0:
+                o = og.find_quadrangle(m)
+                assert (o is None) == (want is None) and (o is None or np.array_equal(o, want)), f"part {part} mask {i}: oracle != cv2"
+        n_total += len(masks)
+    assert n_total >= 10000 and n_found >= 0.4 * n_total, (n_found, n_total)
+
+
+def test_mask_to_quad_reference_ground_truth_masks_golden(engine):
+    """The reference's 631 ground-truth board masks (data/board_extraction/masks) against the quadrangles its UNMODIFIED
+    _find_quadrangle returned for them (tests/golden/gt_masks.npz, oracle/make_golden_masks.py)."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "gt_masks.npz")
+    masks = (np.unpackbits(g["masks"], axis=-1).reshape(-1, 256, 256) * 255).astype(np.uint8)
+    assert len(masks) == 631
+    quad, found, status = _run_quads(engine, masks)
+    assert np.array_equal(found, g["found"]) and set(np.unique(status)) <= {0, 1}
+    assert np.array_equal(quad, g["quads"]), f"{int((quad != g['quads']).any(axis=(1, 2)).sum())} masks differ"
+
+
+def test_mask_to_quad_contours_beyond_the_shared_memory_capacity(engine):
+    """Combs (one contour of ~40,000 border points), a dense checker field (tens of thousands of borders) and a board with a
+    ragged fringe: the shared-memory kernels flag them, the large-capacity kernel finishes them -- results equal to the
+    oracle and to cv2, never status 2."""
+    rng = np.random.default_rng(11)
+    masks = [synth.comb_mask(rng) for _ in range(5)] + [synth.comb_mask(rng, teeth=2).T.copy() for _ in range(3)]
+    checker = np.zeros((256, 256), np.uint8)
+    checker[::2, ::2] = 255                                     # 16,384 isolated pixels: more borders than int16 labels hold
+    checker[1::2, 1::2] = 255
+    fringe = np.zeros((256, 256), np.uint8)
+    fringe[30:226, 30:150] = 255
+    fringe[30:226:2, 150:236] = 255                             # 98 one-pixel teeth of 86 px on a board-sized block
+    masks = np.stack(masks + [checker, fringe, 255 - fringe])
+    quad, found, status = _run_quads(engine, masks)
+    for i, m in enumerate(masks):
+        want = og.find_quadrangle_cv2(m)
+        o = og.find_quadrangle(m)
+        assert (o is None) == (want is None) and (o is None or np.array_equal(o, want)), f"mask {i}: oracle != cv2"
+        assert status[i] in (0, 1), f"mask {i}: status {status[i]}"
+        assert bool(found[i]) == (want is not None), f"mask {i}"
+        if want is not None:
+            assert np.array_equal(quad[i], want.reshape(4, 2)), f"mask {i}"
+
+
+def test_warp_squares_with_corners_outside_the_image(engine):
+    """Quads that leave the image (BORDER_CONSTANT: taps outside contribute 0), including corners far outside and a
+    degenerate (collinear) quad: bytes identical to the oracle."""
+    rng = np.random.default_rng(5)
+    imgs = np.stack([synth.board_image(rng)[0] for _ in range(6)])
+    quads = np.array([
+        [[270, -20], [-15, 10], [5, 250], [260, 290]],          # every corner outside
+        [[255, 0], [0, 0], [0, 255], [255, 255]],               # the whole frame
+        [[300, 40], [100, 30], [90, 200], [310, 220]],          # right half outside
+        [[200, -60], [40, -50], [50, 120], [190, 130]],         # top outside
+        [[1000, -800], [-900, -700], [-1000, 900], [1100, 1000]],   # far outside: mostly border colour
+        [[10, 10], [100, 100], [200, 200], [250, 250]],         # collinear: singular system -> zero board
+    ], np.int32)
+    found = np.ones(6, np.uint8)
+    board = engine.warp_squares(torch.from_numpy(imgs).cuda(), torch.from_numpy(quads).cuda(), torch.from_numpy(found).cuda()).cpu().numpy()
+    for i in range(5):
+        want = og.extract_board(imgs[i], og.scale_quadrangle(quads[i].reshape(4, 1, 2), (512, 512)))
+        assert np.array_equal(board[i], want), f"board {i}: {(board[i] != want).sum()} bytes differ"
+    assert og.perspective_matrix(og.scale_quadrangle(quads[5].reshape(4, 1, 2), (512, 512)).reshape(4, 2),
+                                 np.array(((0, 0), (512, 0), (512, 512), (0, 512)), np.float32)) is None
+    assert not board[5].any()
+
+
+@pytest.mark.parametrize("shape,out_size", [((300, 400, 3), (512, 512)), ((300, 400, 3), (300, 200)), ((480, 640, 3), (640, 480)),
+                                            ((97, 131, 3), (50, 30)), ((256, 256), (64, 64)), ((200, 100), (1000, 8)),
+                                            ((64, 64, 1), (33, 77)), ((512, 512, 3), (5, 5))])
+def test_warp_perspective_any_size_equals_cv2(engine, shape, out_size):
+    """cvb_warp_perspective (utils.extract_perspective, utils.py:115-132) against cv2.getPerspectiveTransform +
+    cv2.warpPerspective themselves: float32 corners (partly outside the image), 1 and 3 channels, any output size."""
+    import cv2
+    rng = np.random.default_rng(sum(shape) + out_size[0])
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    h, w = shape[:2]
+    for _ in range(4):
+        quad = (np.array([[0.1, 0.1], [0.9, 0.15], [0.85, 0.9], [0.12, 0.8]]) * [w, h] + rng.uniform(-0.2, 0.2, (4, 2)) * [w, h]).astype(np.float32)
+        dest = np.array(((0, 0), (out_size[0], 0), (out_size[0], out_size[1]), (0, out_size[1])), np.float32)
+        want = cv2.warpPerspective(img, cv2.getPerspectiveTransform(quad, dest), out_size)
+        got = engine.warp_perspective(torch.from_numpy(img).cuda(), torch.from_numpy(quad), out_size).cpu().numpy()
+        assert np.array_equal(got.reshape(want.shape), want), f"{(got.reshape(want.shape) != want).sum()} bytes differ"
+        assert np.array_equal(og.warp_perspective_u8(img.reshape(h, w, -1) if img.ndim == 3 else img, og.perspective_matrix(quad, dest), out_size).reshape(want.shape), want)

@@ -182,3 +182,57 @@ def test_rule_one_fix():
     assert fixed[60] not in ("P", "p")
     assert fen.startswith("3Q4/")
     assert len(fixes) == 2 and fixes[0][0] == "d8"
+
+
+@pytest.mark.parametrize("h,w", [(100, 100), (128, 128), (255, 255), (200, 300), (300, 200), (64, 512), (37, 211), (256, 100), (1, 1), (2, 3), (250, 1000)])
+def test_resize_area_with_an_enlarged_axis_equals_cv2(h, w):
+    """INTER_AREA below 256 px (core.py:212 resizes any input): OpenCV's fixed-point bilinear emulation, bit for bit."""
+    rng = np.random.default_rng(h * 7 + w)
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    assert np.array_equal(og.resize_area(img, (256, 256)), cv2.resize(img, (256, 256), interpolation=cv2.INTER_AREA))
+
+
+def test_perspective_transform_and_warp_for_any_output_size_equal_cv2():
+    """utils.extract_perspective (utils.py:115-132) with float corners and output sizes other than the 512x512 board: the
+    Point2f products of getPerspectiveTransform are float32, the warp blocks are min(1024 / min(16, h), w) wide."""
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (300, 400, 3), dtype=np.uint8)
+    sizes = [(512, 512), (300, 200), (64, 64), (50, 30), (100, 10), (1000, 8), (33, 77), (640, 480), (5, 5), (17, 300)]
+    for t in range(40):
+        ow, oh = sizes[t % len(sizes)]
+        quad = np.array([[40, 30], [350, 60], [330, 260], [60, 240]], np.float32) + rng.uniform(-60, 60, (4, 2)).astype(np.float32)
+        dest = np.array(((0, 0), (ow, 0), (ow, oh), (0, oh)), np.float32)
+        M = cv2.getPerspectiveTransform(quad, dest)
+        Mo = og.perspective_matrix(quad, dest)
+        assert np.array_equal(M, Mo), (ow, oh)
+        assert np.array_equal(og.warp_perspective_u8(img, Mo, (ow, oh)), cv2.warpPerspective(img, M, (ow, oh))), (ow, oh)
+    gray = img[:, :, 1].copy()
+    assert np.array_equal(og.warp_perspective_u8(gray, Mo, (ow, oh)), cv2.warpPerspective(gray, M, (ow, oh)))
+
+
+def test_cv2_spelling_of_find_quadrangle_equals_the_cv2_free_oracle():
+    import cvb_synth as synth
+    masks = synth.fuzz_masks(seed=3, n=48)
+    n = 0
+    for m in masks:
+        a, b = og.find_quadrangle(m), og.find_quadrangle_cv2(m)
+        assert (a is None) == (b is None)
+        if a is not None:
+            n += 1
+            assert np.array_equal(a, b)
+    assert n >= 15
+
+
+def test_reference_ground_truth_masks_golden():
+    """tests/golden/gt_masks.npz (the reference's 631 GT masks + what its unmodified _find_quadrangle returns): the oracle
+    reproduces every quadrangle (a sample with the cv2-free restatement, all of them with the cv2 spelling)."""
+    from conftest import GOLDEN
+    g = np.load(GOLDEN / "gt_masks.npz")
+    masks = (np.unpackbits(g["masks"], axis=-1).reshape(-1, 256, 256) * 255).astype(np.uint8)
+    assert len(masks) == 631 and int(g["found"].sum()) == 631
+    for i, m in enumerate(masks):
+        q = og.find_quadrangle_cv2(m)
+        assert q is not None and np.array_equal(q.reshape(4, 2), g["quads"][i]), i
+        if i % 16 == 0:
+            o = og.find_quadrangle(m)
+            assert o is not None and np.array_equal(o.reshape(4, 2), g["quads"][i]), i
