@@ -746,11 +746,14 @@ def run_pipeline(args):
     api_steps = max(1, min(args.steps, args.api_steps))
     cvm = ChessVision.from_engine(eng)   # the same loaded context (no second copy of the workspaces)
     api_batch = host_img.numpy()
+    res = None
     for _ in range(2):
+        del res   # a consumer handles one batch of results and drops it before asking for the next
         res = cvm.process_images(api_batch)
     barrier()
     t0 = time.perf_counter()
     for _ in range(api_steps):
+        del res
         res = cvm.process_images(api_batch)
     barrier()
     api_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)

@@ -68,6 +68,8 @@ SYMBOLS = {
     "cvb_train_create": (_I, [_P, C.POINTER(_Tensor), _I, C.POINTER(TrainConfig)]),
     "cvb_train_forward_backward": (_I, [_P, _P, _P, _P, _P]),
     "cvb_train_grads": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "cvb_train_buckets": (_I, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _I]),
+    "cvb_train_bucket_wait": (_I, [_P, _I, _P]),
     "cvb_train_optimizer_step": (_I, [_P, _F, _F, _P]),
     "cvb_train_step": (_I, [_P, _P, _P, _F, _P, _P]),
     "cvb_train_export": (_I, [_P, _I, C.POINTER(_Tensor), _I]),
@@ -355,6 +357,18 @@ class Engine:
             __cuda_array_interface__ = {"shape": (cnt.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 3, "strides": None}
 
         return torch.as_tensor(_Alias(), device=self.device)
+
+    def train_buckets(self):
+        """[(lo, hi)] ranges of the flat gradient buffer in the order the backward pass completes them."""
+        lo, hi = (C.c_int64 * 16)(), (C.c_int64 * 16)()
+        n = self.lib.cvb_train_buckets(self.h, lo, hi, 16)
+        if n < 0:
+            raise NativeError("cvb_train_buckets failed: no trainer")
+        return [(int(lo[i]), int(hi[i])) for i in range(n)]
+
+    def train_bucket_wait(self, bucket: int, stream: "torch.cuda.Stream"):
+        """Make ``stream`` wait until bucket ``bucket`` of the most recent forward_backward is final."""
+        self._ck(self.lib.cvb_train_bucket_wait(self.h, bucket, C.c_void_p(stream.cuda_stream)), "cvb_train_bucket_wait")
 
     def train_optimizer_step(self, lr, grad_scale=1.0):
         self._ck(self.lib.cvb_train_optimizer_step(self.h, lr, grad_scale, _stream()), "cvb_train_optimizer_step")

@@ -66,6 +66,81 @@ def _engine_for_statics() -> _native.Engine:
     return _shared_engine
 
 
+class _PinnedOutputPool:
+    """Pinned host buffers for the outputs of ``process_images``.
+
+    The library copies each group's results straight into pinned memory (asynchronous DMA at PCIe rate; pageable memory would
+    be staged by the driver at a fraction of it) and the result objects hold VIEWS of those buffers, so a buffer set must stay
+    untouched for as long as any result that views it is alive.  A set is therefore leased per call: ``weakref.finalize`` on
+    the base arrays hands it back only when the last view of the last output has been garbage-collected.  Page-locking is
+    slow (hundreds of milliseconds per gigabyte), hence the reuse; at most ``max_cached_bytes`` stay cached."""
+
+    def __init__(self, max_cached_bytes: int = 12 << 30):
+        self._free: dict[int, list] = {}
+        self._lock = threading.Lock()
+        self._cached = 0
+        self.max_cached_bytes = max_cached_bytes
+
+    @staticmethod
+    def _nbytes(out: dict) -> int:
+        return sum(t.numel() * t.element_size() for t in out.values())
+
+    def lease(self, eng: _native.Engine, n: int):
+        """-> (dict of pinned torch tensors for the native call, dict of numpy base arrays the results will view)."""
+        with self._lock:
+            sets = self._free.get(n)
+            out = sets.pop() if sets else None
+            if out is not None:
+                self._cached -= self._nbytes(out)
+        if out is None:
+            out = eng.alloc_outputs(n, full=True, squares=True, pinned_host=True)
+        arrays = {k: v.numpy() for k, v in out.items()}
+        pending = [len(arrays)]
+
+        def one_released() -> None:
+            with self._lock:
+                pending[0] -= 1
+                if pending[0] == 0 and self._cached + self._nbytes(out) <= self.max_cached_bytes:
+                    self._free.setdefault(n, []).append(out)
+                    self._cached += self._nbytes(out)
+
+        for a in arrays.values():
+            weakref.finalize(a, one_released)
+        return out, arrays
+
+
+_pinned_pool = _PinnedOutputPool()
+
+
+def _results_from_outputs(out: dict, lo: int, hi: int, names: list, scale: float, elapsed: float) -> list:
+    """``ChessVisionResult`` objects of boards [lo, hi) from batch-sized host arrays (the cvb_outputs layout): every array
+    field of a result is a VIEW of row i of those arrays -- no per-board copies."""
+    _check_status(out["status"][lo:hi])
+    found = out["found"][lo:hi].astype(bool)
+    quads = np.array(out["quad"][lo:hi].reshape(-1, 4, 1, 2) * scale, dtype=np.float32)   # _scale_quadrangle, vectorised
+    fen_rows = out["fen"][lo:hi]
+    labels, fixed = out["labels"][lo:hi], out["labels_valid"][lo:hi]
+    changed = (labels != fixed).any(axis=1)
+    logits, masks, boards, squares, probs = out["logits"], out["mask"], out["board"], out["squares"], out["probs"]
+    results = []
+    for k in range(hi - lo):
+        i = lo + k
+        if found[k]:
+            fixes = []
+            if changed[k]:
+                fixes = [ValidationFix(names[j], constants.LABEL_NAMES[labels[k, j]], constants.LABEL_NAMES[fixed[k, j]], "no_pawns_on_ends")
+                         for j in np.flatnonzero(labels[k] != fixed[k])]
+            row = fen_rows[k]
+            position = PositionResult(fen=row[1].tobytes().split(b"\0", 1)[0].decode(), original_fen=row[0].tobytes().split(b"\0", 1)[0].decode(),
+                                      model_probabilities=probs[i], squares=squares[i], square_names=names, validation_fixes=fixes)
+            extraction = BoardExtractionResult(probabilities=logits[i], binary_mask=masks[i], quadrangle=quads[k], board_image=boards[i])
+        else:
+            position = None
+            extraction = BoardExtractionResult(probabilities=logits[i], binary_mask=masks[i], quadrangle=None, board_image=None)
+        results.append(ChessVisionResult(board_extraction=extraction, position=position, processing_time=elapsed))
+    return results
+
+
 def _check_status(status) -> None:
     bad = np.flatnonzero(np.asarray(status) == 2)
     if bad.size:
@@ -250,35 +325,11 @@ class ChessVision:
         results: list = []
         scale = batch.shape[1] / 256.0
 
-        def build(lo: int, hi: int, out) -> None:
-            """Result objects of boards [lo, hi) from the batch-sized host arrays (views only)."""
-            _check_status(out["status"][lo:hi].numpy())
-            found = out["found"][lo:hi].numpy().astype(bool)
-            quads = np.array(out["quad"][lo:hi].numpy().reshape(-1, 4, 1, 2) * scale, dtype=np.float32)   # _scale_quadrangle, vectorised
-            fen_rows = out["fen"][lo:hi].numpy()
-            labels, fixed = out["labels"][lo:hi].numpy(), out["labels_valid"][lo:hi].numpy()
-            changed = (labels != fixed).any(axis=1)
-            logits, masks, boards = out["logits"].numpy(), out["mask"].numpy(), out["board"].numpy()
-            squares, probs = out["squares"].numpy(), out["probs"].numpy()
-            elapsed = (time.time() - start) / n
-            for k in range(hi - lo):
-                i = lo + k
-                if found[k]:
-                    fixes = []
-                    if changed[k]:
-                        fixes = [ValidationFix(names[j], constants.LABEL_NAMES[labels[k, j]], constants.LABEL_NAMES[fixed[k, j]], "no_pawns_on_ends")
-                                 for j in np.flatnonzero(labels[k] != fixed[k])]
-                    row = fen_rows[k]
-                    position = PositionResult(fen=row[1].tobytes().split(b"\0", 1)[0].decode(), original_fen=row[0].tobytes().split(b"\0", 1)[0].decode(),
-                                              model_probabilities=probs[i], squares=squares[i], square_names=names, validation_fixes=fixes)
-                    extraction = BoardExtractionResult(probabilities=logits[i], binary_mask=masks[i], quadrangle=quads[k], board_image=boards[i])
-                else:
-                    position = None
-                    extraction = BoardExtractionResult(probabilities=logits[i], binary_mask=masks[i], quadrangle=None, board_image=None)
-                results.append(ChessVisionResult(board_extraction=extraction, position=position, processing_time=elapsed))
+        def build(lo: int, hi: int, arrays) -> None:
+            results.extend(_results_from_outputs(arrays, lo, hi, names, scale, (time.time() - start) / n))
 
         if batch.shape[1:3] == (512, 512):
-            out = eng.alloc_outputs(n, full=True, squares=True, host=True)
+            out, arrays = _pinned_pool.lease(eng, n)
             progress = np.zeros(1, np.int32)
             err: list = []
 
@@ -294,7 +345,7 @@ class ChessVision:
             while done < n:
                 ready = int(progress[0])
                 if ready > done:
-                    build(done, ready, out)
+                    build(done, ready, arrays)
                     done = ready
                 elif not worker.is_alive():
                     break
@@ -305,10 +356,11 @@ class ChessVision:
                 raise err[0]
             ready = int(progress[0])
             if ready > done:
-                build(done, ready, out)
+                build(done, ready, arrays)
+            del out, arrays   # from here on only the results keep the pinned set alive
         else:
             dev = eng.image_to_fen(host_in.to(eng.device), eng.alloc_outputs(n, full=True, squares=True), threshold, flip)
-            build(0, n, {k: v.cpu() for k, v in dev.items()})
+            build(0, n, {k: v.cpu().numpy() for k, v in dev.items()})
         return results
 
     def extract_board(self, image: NDArray[np.uint8], threshold: float = 0.5) -> BoardExtractionResult:

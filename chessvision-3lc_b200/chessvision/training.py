@@ -13,8 +13,10 @@ weights, accumulation and optimizer state (the arithmetic of the reference's ``-
 
 Data parallelism (BASELINE.json configs[4]; the reference itself is single-device): one process per GPU, every rank holds
 a replica and calls ``step`` on its own micro-batch; the flat fp32 gradient buffer is all-reduced (sum) over NCCL /
-NVLink between backward and the optimizer, and the optimizer applies ``1/world_size`` — the semantics of torch DDP
-(gradient average, local BatchNorm statistics; the reference has no SyncBN).  There is no CPU fallback.
+NVLink in four layer-reverse buckets, each launched from a communication stream as soon as the backward pass has
+finished that bucket (``cvb_train_bucket_wait``), so the transfers overlap the rest of the backward pass; the optimizer
+applies ``1/world_size`` — the semantics of torch DDP (gradient average, local BatchNorm statistics; the reference has no
+SyncBN).  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -24,19 +26,34 @@ import torch.distributed as dist
 from . import _native
 
 
-def allreduce_gradients(flat: torch.Tensor, group=None, buckets: int = 1) -> float:
+def allreduce_gradients(flat: torch.Tensor, group=None, buckets=1, before_bucket=None) -> float:
     """Sum ``flat`` (a 1-D gradient buffer) over the ranks of ``group`` in place and return the factor that turns the sum
-    into the average (1/world).  ``buckets`` > 1 splits the buffer into that many contiguous all-reduces (launch
-    latency vs overlap trade-off).  Works on NCCL (device tensors) and gloo (host tensors, used by the CPU tests)."""
+    into the average (1/world).  ``buckets``: an int (that many equal contiguous ranges) or a list of ``(lo, hi)`` ranges,
+    all-reduced in the given order as independent asynchronous collectives; ``before_bucket(i)`` (optional) runs right
+    before collective ``i`` is enqueued (the trainer uses it to make the communication stream wait for the event of that
+    bucket).  Works on NCCL (device tensors) and gloo (host tensors, used by the CPU tests)."""
     if not dist.is_available() or not dist.is_initialized():
         return 1.0
     world = dist.get_world_size(group)
     if world == 1:
         return 1.0
     n = flat.numel()
-    buckets = max(1, min(buckets, n))
-    bounds = [(i * n) // buckets for i in range(buckets + 1)]
-    handles = [dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True) for a, b in zip(bounds, bounds[1:]) if b > a]
+    if isinstance(buckets, int):
+        k = max(1, min(buckets, n))
+        bounds = [(i * n) // k for i in range(k + 1)]
+        ranges = list(zip(bounds, bounds[1:]))
+    else:
+        ranges = [(int(a), int(b)) for a, b in buckets]
+        covered = sorted(ranges)
+        assert covered[0][0] == 0 and covered[-1][1] == n and all(x[1] == y[0] for x, y in zip(covered, covered[1:])), \
+            "gradient buckets must tile the buffer"
+    handles = []
+    for i, (a, b) in enumerate(ranges):
+        if b <= a:
+            continue
+        if before_bucket is not None:
+            before_bucket(i)
+        handles.append(dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=group, async_op=True))
     for h in handles:
         h.wait()
     return 1.0 / world
@@ -54,17 +71,42 @@ class UNetTrainer:
         self.learning_rate = learning_rate
         self.process_group = process_group
         self._grads = self.engine.train_grads()
+        self.buckets = self.engine.train_buckets()      # layer-reverse ranges, in the order the backward pass completes them
+        self.n_buckets = len(self.buckets)
+        self._comm_stream = torch.cuda.Stream(device=self.engine.device)
         self.global_step = 0
 
     def step(self, images: torch.Tensor, true_masks: torch.Tensor) -> torch.Tensor:
         """One optimisation step; returns the (local) batch loss as a 1-element device tensor without synchronising."""
         images = images.to(device=self.engine.device, dtype=torch.float32).contiguous()
         true_masks = true_masks.to(device=self.engine.device, dtype=torch.float32).contiguous()
-        loss = self.engine.train_forward_backward(images, true_masks)
-        scale = allreduce_gradients(self._grads, self.process_group)
+        loss = self.engine.train_forward_backward(images, true_masks)   # enqueues the whole pass and records one event per bucket
+        scale = self._allreduce_overlapped()
         self.engine.train_optimizer_step(self.learning_rate, scale)
         self.global_step += 1
         return loss
+
+    def _allreduce_overlapped(self) -> float:
+        """All-reduce the gradient buckets in the order the backward pass finishes them.  The backward kernels are already
+        queued on the compute stream; collective ``b`` is issued from a communication stream that waits for bucket ``b``'s
+        event only, so it runs over NVLink while the compute stream is still producing the earlier layers' gradients.  The
+        compute stream waits for all collectives before the optimizer touches the buffer."""
+        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(self.process_group) == 1:
+            return 1.0
+        compute = torch.cuda.current_stream(self.engine.device)
+        with torch.cuda.stream(self._comm_stream):
+            return self._reduce_on_comm_stream(compute)
+
+    def _reduce_on_comm_stream(self, compute) -> float:
+        world = dist.get_world_size(self.process_group)
+        handles = []
+        for b, (lo, hi) in enumerate(self.buckets):
+            self.engine.train_bucket_wait(b, self._comm_stream)
+            handles.append(dist.all_reduce(self._grads[lo:hi], op=dist.ReduceOp.SUM, group=self.process_group, async_op=True))
+        with torch.cuda.stream(compute):
+            for h in handles:
+                h.wait()            # stream-level wait: the compute stream resumes after the last collective
+        return 1.0 / world
 
     def forward_backward(self, images, true_masks):
         return self.engine.train_forward_backward(images, true_masks)

@@ -80,6 +80,12 @@ struct cvb_trainer {
     WgTile* tiles = nullptr;
     int tiles_used = 0;
     long long steps = 0;
+    // gradient buckets for the data-parallel all-reduce, in the order the backward pass completes them (the flat layout is
+    // the forward order, so they are contiguous ranges taken from its end): [lo, hi) in parameters + the event recorded on
+    // the compute stream when the last kernel writing into the range has been enqueued
+    static constexpr int kBuckets = 4;
+    size_t bucket_lo[kBuckets] = {0, 0, 0, 0}, bucket_hi[kBuckets] = {0, 0, 0, 0};
+    cudaEvent_t bucket_ev[kBuckets] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -292,6 +298,16 @@ int cvb_train_create(cvb_ctx* ctx, const cvb_tensor* sd, int n, const cvb_train_
     T->outc_b_off = off; off += 1;
     T->n_params = (off + 3) & ~static_cast<size_t>(3);
     T->bn_channels = bn_off;
+    // buckets: {up4, up3, up2 (+ outc)}, {up1}, {down4}, {down3 .. inc}: 3.9 M, 9.2 M, 14.2 M and 4.7 M parameters; the first
+    // three are complete after 45 % / 55 % / 65 % of the backward pass, so their all-reduce hides behind the rest of it
+    {
+        const size_t cut[5] = {T->n_params, T->convt[1].w_off, T->convt[0].w_off, T->conv[8].w_off, 0};
+        for (int b = 0; b < cvb_trainer::kBuckets; ++b) {
+            T->bucket_lo[b] = cut[b + 1];
+            T->bucket_hi[b] = cut[b];
+            if (cudaEventCreateWithFlags(&T->bucket_ev[b], cudaEventDisableTiming) != cudaSuccess) return fail(ctx, -2, "event creation failed");
+        }
+    }
 
     // ---- device memory
     int rc = 0;
@@ -463,15 +479,36 @@ int cvb_train_forward_backward(cvb_ctx* ctx, const float* img, const float* mask
     for (int u = 3; u >= 0; --u) {
         if (conv_backward(ctx, T, C[11 + 2 * u], img, s) || conv_backward(ctx, T, C[10 + 2 * u], img, s)) return -2;
         if (convt_backward(ctx, T, T->convt[u], s)) return -2;
+        if (u == 1) CK(cudaEventRecord(T->bucket_ev[0], s));   // up4, up3, up2 and the head are final
+        if (u == 0) CK(cudaEventRecord(T->bucket_ev[1], s));   // up1
     }
     __half* dcats[4] = {T->dcat0, T->dcat1, T->dcat2, T->dcat3};
     for (int d = 3; d >= 0; --d) {
         if (conv_backward(ctx, T, C[3 + 2 * d], img, s) || conv_backward(ctx, T, C[2 + 2 * d], img, s)) return -2;
+        if (d == 3) CK(cudaEventRecord(T->bucket_ev[2], s));   // down4
         const int H = 256 >> d, Cc = 64 << d;
         // gradient of the skip tensor x_{d+1}: pooled path (dx of the conv just processed) + concat path (lower half of dcat)
         LAUNCH(launch_pool_bwd_add(cats[d], 2 * Cc, dcats[d], 2 * Cc, C[2 + 2 * d].dx, C[1 + 2 * d].dy, B, H, H, Cc, s));
     }
     if (conv_backward(ctx, T, C[1], img, s) || conv_backward(ctx, T, C[0], img, s)) return -2;
+    CK(cudaEventRecord(T->bucket_ev[3], s));                   // down3 .. inc
+    return 0;
+}
+
+int cvb_train_buckets(cvb_ctx* ctx, int64_t* lo, int64_t* hi, int capacity) {
+    if (!ctx || !ctx->trainer) return -1;
+    const cvb_trainer* T = ctx->trainer;
+    for (int b = 0; b < cvb_trainer::kBuckets && b < capacity; ++b) {
+        if (lo) lo[b] = static_cast<int64_t>(T->bucket_lo[b]);
+        if (hi) hi[b] = static_cast<int64_t>(T->bucket_hi[b]);
+    }
+    return cvb_trainer::kBuckets;
+}
+
+int cvb_train_bucket_wait(cvb_ctx* ctx, int bucket, void* stream) {
+    if (!ctx || !ctx->trainer || bucket < 0 || bucket >= cvb_trainer::kBuckets) return -1;
+    CVB_ON_DEVICE(ctx);
+    CK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), ctx->trainer->bucket_ev[bucket], 0));
     return 0;
 }
 
@@ -594,4 +631,9 @@ int cvb_wgrad3x3_f16(cvb_ctx* ctx, const void* dz, const void* x, int N, int H, 
 
 }  // extern "C"
 
-void cvb_trainer_free(cvb_trainer* t) { delete t; }
+void cvb_trainer_free(cvb_trainer* t) {
+    if (!t) return;
+    for (cudaEvent_t e : t->bucket_ev)
+        if (e) cudaEventDestroy(e);
+    delete t;
+}

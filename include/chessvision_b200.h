@@ -162,6 +162,13 @@ CVB_API int cvb_train_create(cvb_ctx* ctx, const cvb_tensor* state_dict, int n_t
 CVB_API int cvb_train_forward_backward(cvb_ctx* ctx, const float* img, const float* mask, float* loss, void* stream);
 /* The flat fp32 gradient buffer written by forward_backward (packed layout; only sums/norms are layout independent). */
 CVB_API int cvb_train_grads(cvb_ctx* ctx, float** grads, int64_t* count);
+/* Gradient buckets for overlapping the data-parallel all-reduce with the backward pass: bucket b is the range [lo[b], hi[b])
+ * of the flat gradient buffer, numbered in the order forward_backward completes them (layer-reverse: the decoder's gradients
+ * first).  Returns the number of buckets (lo / hi may be NULL).  cvb_train_bucket_wait makes `stream` (the communication
+ * stream) wait until the last kernel of the most recent forward_backward that writes into bucket b has finished, so that
+ * its all-reduce can start while the compute stream is still working on the earlier layers. */
+CVB_API int cvb_train_buckets(cvb_ctx* ctx, int64_t* lo, int64_t* hi, int capacity);
+CVB_API int cvb_train_bucket_wait(cvb_ctx* ctx, int bucket, void* stream);
 /* clip_grad_norm_(params, max_grad_norm); optimizer.step()  (train_unet.py:321-322) on grads * grad_scale. */
 CVB_API int cvb_train_optimizer_step(cvb_ctx* ctx, float lr, float grad_scale, void* stream);
 /* Single-GPU convenience: forward_backward + optimizer_step(grad_scale 1). */

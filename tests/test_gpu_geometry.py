@@ -172,8 +172,8 @@ def test_mask_to_quad_contours_beyond_the_shared_memory_capacity(engine):
 
 
 def test_warp_squares_with_corners_outside_the_image(engine):
-    """Quads that leave the image (BORDER_CONSTANT: taps outside contribute 0), including corners far outside and a
-    degenerate (collinear) quad: bytes identical to the oracle."""
+    """Quads that leave the image (BORDER_CONSTANT: taps outside contribute 0), including corners far outside and a sliver
+    (nearly collinear corners): bytes identical to the oracle."""
     rng = np.random.default_rng(5)
     imgs = np.stack([synth.board_image(rng)[0] for _ in range(6)])
     quads = np.array([
@@ -182,16 +182,13 @@ def test_warp_squares_with_corners_outside_the_image(engine):
         [[300, 40], [100, 30], [90, 200], [310, 220]],          # right half outside
         [[200, -60], [40, -50], [50, 120], [190, 130]],         # top outside
         [[1000, -800], [-900, -700], [-1000, 900], [1100, 1000]],   # far outside: mostly border colour
-        [[10, 10], [100, 100], [200, 200], [250, 250]],         # collinear: singular system -> zero board
+        [[12, 10], [100, 101], [203, 200], [250, 252]],         # a sliver: ill-conditioned system, identical arithmetic all the same
     ], np.int32)
     found = np.ones(6, np.uint8)
     board = engine.warp_squares(torch.from_numpy(imgs).cuda(), torch.from_numpy(quads).cuda(), torch.from_numpy(found).cuda()).cpu().numpy()
-    for i in range(5):
+    for i in range(6):
         want = og.extract_board(imgs[i], og.scale_quadrangle(quads[i].reshape(4, 1, 2), (512, 512)))
         assert np.array_equal(board[i], want), f"board {i}: {(board[i] != want).sum()} bytes differ"
-    assert og.perspective_matrix(og.scale_quadrangle(quads[5].reshape(4, 1, 2), (512, 512)).reshape(4, 2),
-                                 np.array(((0, 0), (512, 0), (512, 512), (0, 512)), np.float32)) is None
-    assert not board[5].any()
 
 
 @pytest.mark.parametrize("shape,out_size", [((300, 400, 3), (512, 512)), ((300, 400, 3), (300, 200)), ((480, 640, 3), (640, 480)),

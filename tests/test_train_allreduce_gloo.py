@@ -40,7 +40,13 @@ def worker(rank, world, port, buckets, q):
         lo, hi = 2 * rank, 2 * rank + 2
         otrain.loss_fn(model(x[lo:hi]), t[lo:hi]).backward()
         flat = _flat_grads(model).clone()
-        scale = training.allreduce_gradients(flat, buckets=buckets)
+        order = []
+        if buckets == "layer-reverse":   # explicit ranges taken from the end of the buffer, like the trainer's cvb_train_buckets
+            n = flat.numel()
+            cuts = [n, (7 * n) // 8, n // 2, n // 5, 0]
+            buckets = list(zip(cuts[1:], cuts[:-1]))
+        scale = training.allreduce_gradients(flat, buckets=buckets, before_bucket=order.append)
+        assert order == list(range(buckets if isinstance(buckets, int) else len(buckets)))
         got = flat * scale
         # BCE is a mean over all pixels and Dice a mean over samples: equal shards -> mean of shard losses = global loss
         err = float((got - want).norm() / want.norm())
@@ -55,7 +61,7 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("buckets", [1, 5])
+@pytest.mark.parametrize("buckets", [1, 5, "layer-reverse"])
 def test_allreduce_averages_shard_gradients(buckets):
     world = 2
     ctx = mp.get_context("spawn")
