@@ -80,6 +80,7 @@ SYMBOLS = {
     "cvb_jpeg_coefficients": (_I, [_P, C.c_int64, _P, _P]),
     "cvb_decode_jpeg": (_I, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _I, _I, _I, _P, _P]),
     "cvb_launch_count": (C.c_int64, [_P]),
+    "cvb_graph_replays": (C.c_int64, [_P]),
     "cvb_profile": (_I, [_P, _I]),
     "cvb_profile_read": (_I, [_P, C.POINTER(C.c_float), _I]),
 }
@@ -445,6 +446,9 @@ class Engine:
 
     def launch_count(self) -> int:
         return int(self.lib.cvb_launch_count(self.h))
+
+    def graph_replays(self) -> int:
+        return int(self.lib.cvb_graph_replays(self.h))
 
     def profile(self, enable: bool):
         self._ck(self.lib.cvb_profile(self.h, int(enable)), "cvb_profile")

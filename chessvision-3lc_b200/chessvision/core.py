@@ -330,6 +330,11 @@ class ChessVision:
 
         if batch.shape[1:3] == (512, 512):
             out, arrays = _pinned_pool.lease(eng, n)
+            if n <= eng.max_batch * 8:
+                # one geometry group (the single-image / small-batch latency path): nothing to overlap, no helper thread
+                eng.image_to_fen_host(host_in, out, threshold, flip)
+                build(0, n, arrays)
+                return results
             progress = np.zeros(1, np.int32)
             err: list = []
 

@@ -41,12 +41,12 @@ class _NativeNet(nn.Module):
         self._loaded_version = None
         self.max_batch = 16
 
-    def _version(self):
+    def _weights_fingerprint(self):
         return tuple((t.data_ptr(), t._version) for t in self.state_dict().values())
 
     def _context(self) -> _native.Engine:
         """(Re)pack the weights when they have changed since the last call (a context holds one packed copy)."""
-        version = self._version()
+        version = self._weights_fingerprint()
         if self._engine is None or version != self._loaded_version:
             if self._engine is not None:
                 self._engine.close()

@@ -382,8 +382,73 @@ int classify(cvb_ctx* ctx, const uint8_t* board, int n, int flip, float* probs, 
 // resident per SM and the slow boards of a launch overlap with the rest.  `o` may hold NULL members (workspaces are
 // used); `off` = index of the group's first board inside the caller's output arrays.  in_ready[c] (optional): event the
 // network of chunk c has to wait for (host path: the chunk's host->device copy).
+int pipeline_group_direct(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s,
+                          const cudaEvent_t* in_ready, int H, int W);
+
+constexpr size_t kMaxGraphs = 8;
+
+// A group of at most one chunk is the latency case (ChessVision.process_image: one board, ~50 launches of a few
+// microseconds each): its launch sequence is captured once into a CUDA graph -- programmatic-dependent-launch edges
+// included -- and replayed with one cudaGraphLaunch as long as everything the launches bake in (pointers, count,
+// threshold, orientation) is unchanged.  Larger groups are launch-bound nowhere and are enqueued directly.
 int pipeline_group(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s,
                    const cudaEvent_t* in_ready, int H = 512, int W = 512) {
+    if (!ctx->use_graph || ctx->profile || n > ctx->max_batch || n <= 0 || H != 512 || W != 512 || !ctx->unet_loaded || !ctx->resnet_loaded)
+        return pipeline_group_direct(ctx, img, n, thr, flip, o, off, s, in_ready, H, W);
+    if (in_ready) CK(cudaStreamWaitEvent(s, in_ready[0], 0));   // an event recorded outside the capture cannot be waited for inside it
+    cvb_ctx::GraphEntry want;
+    memset(want.key, 0, sizeof want.key);
+    uint32_t thr_bits;
+    memcpy(&thr_bits, &thr, 4);
+    const void* ptrs[11] = {o.logits, o.mask, o.quad, o.found, o.status, o.board, o.probs, o.labels, o.labels_valid, o.fen, o.squares};
+    want.key[0] = reinterpret_cast<uint64_t>(img);
+    want.key[1] = (static_cast<uint64_t>(n) << 40) | (static_cast<uint64_t>(flip != 0) << 32) | thr_bits;
+    want.key[2] = static_cast<uint64_t>(off);
+    want.key[3] = reinterpret_cast<uint64_t>(s);
+    for (int i = 0; i < 11; ++i) want.key[4 + i] = reinterpret_cast<uint64_t>(ptrs[i]);
+    cvb_ctx::GraphEntry* hit = nullptr;
+    for (auto& g : ctx->graphs)
+        if (memcmp(g.key, want.key, sizeof want.key) == 0) hit = &g;
+    if (!hit) {
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();   // e.g. the legacy default stream cannot be captured: enqueue directly
+            return pipeline_group_direct(ctx, img, n, thr, flip, o, off, s, nullptr, H, W);
+        }
+        const int64_t l0 = ctx->launches;
+        const int rc = pipeline_group_direct(ctx, img, n, thr, flip, o, off, s, nullptr, H, W);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ec = cudaStreamEndCapture(s, &graph);
+        want.launches = ctx->launches - l0;
+        ctx->launches = l0;
+        if (rc || ec != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            if (rc) return rc;
+            ctx->use_graph = false;   // capture is not possible here (e.g. a tool that forbids it): enqueue directly from now on
+            return pipeline_group_direct(ctx, img, n, thr, flip, o, off, s, nullptr, H, W);
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&want.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail(ctx, -2, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+        if (ctx->graphs.size() >= kMaxGraphs) {   // evict the least recently used graph
+            size_t lru = 0;
+            for (size_t i = 1; i < ctx->graphs.size(); ++i)
+                if (ctx->graphs[i].last_use < ctx->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(ctx->graphs[lru].exec);
+            ctx->graphs.erase(ctx->graphs.begin() + static_cast<long>(lru));
+        }
+        ctx->graphs.push_back(want);
+        hit = &ctx->graphs.back();
+    }
+    hit->last_use = ++ctx->graph_clock;
+    CK(cudaGraphLaunch(hit->exec, s));
+    ctx->launches += hit->launches;
+    ctx->graph_replays++;
+    return 0;
+}
+
+int pipeline_group_direct(cvb_ctx* ctx, const uint8_t* img, int n, float thr, int flip, const cvb_outputs& o, size_t off, cudaStream_t s,
+                          const cudaEvent_t* in_ready, int H, int W) {
     const int B = ctx->max_batch;
     const size_t img_bytes = static_cast<size_t>(H) * W * 3;
     float* logits = o.logits ? o.logits + off * 65536 : nullptr;
@@ -433,6 +498,7 @@ int cvb_version(void) { return 100; }
 const char* cvb_last_error(const cvb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int cvb_max_batch(const cvb_ctx* ctx) { return ctx ? ctx->max_batch : 0; }
 int64_t cvb_launch_count(const cvb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t cvb_graph_replays(const cvb_ctx* ctx) { return ctx ? ctx->graph_replays : 0; }
 
 cvb_ctx* cvb_create(int device, int max_batch) {
     if (max_batch <= 0) return nullptr;
@@ -459,6 +525,7 @@ cvb_ctx* cvb_create(int device, int max_batch) {
     if (tmap_init()) { ctx->err = "cuTensorMapEncodeTiled not available from the driver"; return bail(); }
     ctx->stem_fp32 = getenv("CVB_STEM_FP32") != nullptr;
     ctx->quad_full_only = getenv("CVB_QUAD_FULL") != nullptr;
+    ctx->use_graph = getenv("CVB_NO_GRAPH") == nullptr;
     if (const char* g = getenv("CVB_GROUP_CHUNKS")) ctx->group_chunks = atoi(g) > 0 ? atoi(g) : 1;
     ctx->group = ctx->group_chunks * max_batch;
     if (conv_configure() != cudaSuccess || configure_resnet_stem() != cudaSuccess || configure_stems_tc() != cudaSuccess ||
@@ -535,6 +602,8 @@ void cvb_destroy(cvb_ctx* ctx) {
     if (!ctx) return;
     DeviceGuard guard(ctx->device);
     cudaDeviceSynchronize();
+    for (auto& g : ctx->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : ctx->allocs) cudaFree(p);
     for (cudaEvent_t e : ctx->pev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {

@@ -368,6 +368,258 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// conv3x3(Cin -> 128) + BN + ReLU fused with the ConvTranspose2d(128 -> 64, k2, s2) that consumes it (UNet: up3.conv.3 and
+// up4.up, unet_parts.py:16-21,53).  Unfused, the 128-channel tensor is written to HBM (4 MB per board) only to be read back by a
+// transposed-convolution kernel that is bound by exactly that traffic.  Here the epilogue converts the accumulator tile
+// (128 pixels x 128 channels) to fp16 in the 128-byte-swizzled K-major layout -- the same bytes the unfused kernel would have
+// stored -- and leaves it in shared memory as the A operand of a second MMA against the resident transposed-conv weights
+// (N = 4 taps x 64 channels = 256, K = 128); its accumulator (256 TMEM columns next to the two 128-column main accumulators)
+// is drained, biased and scattered by the same four epilogue warps through the strided output views of EPI_CONVT.  The
+// results are bit-identical to the two separate kernels (same fp16 rounding point, same accumulation order).
+//   warp 0 TMA producer (transposed-conv weights once, then the main pipeline), warp 1 MMA issue (main K loop of tile i; the
+//   second MMA of tile i-1 is slipped in as soon as its A operand is ready), warp 2 TMEM, warps 4-7 epilogue.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FusedCfg {
+    static constexpr int kStages = 3;
+    static constexpr int kABytes = 128 * 128, kBBytes = 128 * 128, kStageBytes = kABytes + kBBytes;
+    static constexpr int kW2Bytes = 2 * 256 * 128;   // two K blocks of [256 rows][64 k]
+    static constexpr int kA2Bytes = 2 * 128 * 128;   // two K blocks of [128 pixels][64 k]; reused as the two store staging buffers
+    static constexpr int kSmemBytes = kStages * kStageBytes + kW2Bytes + kA2Bytes + 1024 + 256 + (128 + 64) * 4;
+};
+
+__global__ void __launch_bounds__(256, 1) conv_convt_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = FusedCfg;
+    constexpr int S = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* tiles_ptr = smem_raw + (tiles_addr - raw_addr);
+    const uint32_t w2_addr = tiles_addr + S * Cfg::kStageBytes;
+    const uint32_t a2_addr = w2_addr + Cfg::kW2Bytes;
+    uint8_t* a2_ptr = tiles_ptr + S * Cfg::kStageBytes + Cfg::kW2Bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a2_ptr + Cfg::kA2Bytes);
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * S;
+    const uint32_t bar_tfull = bar_full + 16 * S;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_w2 = bar_tfull + 32;
+    const uint32_t bar_a2full = bar_tfull + 40;
+    const uint32_t bar_d2full = bar_tfull + 48;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+    float* s_bias = reinterpret_cast<float*>(a2_ptr + Cfg::kA2Bytes + 256);
+    float* s_bias2 = s_bias + 128;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.b2_map);
+        tma_prefetch_desc(&p.a_map[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        mbar_init(bar_w2, 1);
+        mbar_init(bar_a2full, 128);
+        mbar_init(bar_d2full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 3) {
+        for (int i = lane; i < 128; i += 32) s_bias[i] = __ldg(p.bias + i);
+        for (int i = lane; i < 64; i += 32) s_bias2[i] = __ldg(p.bias2 + i);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t d2_tmem = tmem_base + 256;
+    griddep_launch();
+    if (warp != 0) griddep_wait();
+
+    const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;   // one N tile: all 128 channels of a pixel in this CTA
+    const int k_steps = p.taps * p.c_chunks;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar_w2, Cfg::kW2Bytes);
+            tma_load_2d(w2_addr, &p.b2_map, bar_w2, 0, 0);
+            tma_load_2d(w2_addr + 256 * 128, &p.b2_map, bar_w2, 64, 0);
+        }
+        __syncwarp();
+        griddep_wait();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int w0 = (t % p.tiles_w) * p.tw;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (t / (p.tiles_w * p.tiles_h)) * p.tn;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                const int hh = h0 + p.tap_dy[tap], ww = w0 + p.tap_dx[tap];
+                for (int kc = 0; kc < p.c_chunks; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t a_dst = tiles_addr + stage * Cfg::kStageBytes;
+                        mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+                        tma_load_4d(a_dst, &p.a_map[0], bar_full + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
+                        tma_load_2d(a_dst + Cfg::kABytes, &p.b_map, bar_full + 8 * stage, (tap * p.c_chunks + kc) * 64, 0);
+                    }
+                    __syncwarp();
+                    if (++stage == S) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_sw128(0));
+        const uint32_t a_lo0 = desc_lo0 + ((tiles_addr & 0x3FFFFu) >> 4);
+        const uint32_t w2_lo = desc_lo0 + ((w2_addr & 0x3FFFFu) >> 4);
+        const uint32_t a2_lo = desc_lo0 + ((a2_addr & 0x3FFFFu) >> 4);
+        const uint32_t idesc = umma_idesc_f16(128, 128, 0), idesc2 = umma_idesc_f16(128, 256, 0);
+        // second MMA of one tile: D2[128 px][(dy,dx,co)] = A2[128 px][128 ci] . W2^T, two K blocks of four K = 16 steps
+        auto mma2 = [&]() {
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(d2_tmem, desc_hi | (a2_lo + kb * (128 * 128 >> 4) + 2 * k), desc_hi | (w2_lo + kb * (256 * 128 >> 4) + 2 * k), idesc2,
+                                 (kb | k) != 0 ? 1u : 0u);
+                umma_commit(bar_d2full);
+            }
+            __syncwarp();
+        };
+        mbar_wait(bar_w2, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 128;
+            bool pending2 = iter > 0;   // the previous tile's second MMA: issued as soon as the epilogue has produced its A operand
+            for (int kb = 0; kb < k_steps; ++kb) {
+                if (pending2 && mbar_try_wait(bar_a2full, (iter - 1) & 1)) {
+                    mma2();
+                    pending2 = false;
+                }
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after();
+                if (leader) {
+                    const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
+                    const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(bar_empty + 8 * stage);
+                    if (kb == k_steps - 1) umma_commit(bar_tfull + 8 * acc);
+                }
+                __syncwarp();
+                if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+            if (pending2) {
+                mbar_wait(bar_a2full, (iter - 1) & 1);
+                mma2();
+            }
+        }
+        if (iter > 0) {
+            mbar_wait(bar_a2full, (iter - 1) & 1);
+            mma2();
+        }
+    } else if (warp >= 4) {
+        const int quarter = warp & 3, etid = threadIdx.x - 128;
+        const int row = quarter * 32 + lane;
+        const int rh = (row / p.tw) % p.th, rw = row % p.tw, rn = row / (p.th * p.tw);
+        (void)rh; (void)rw; (void)rn;
+        const uint32_t no_res[32] = {0};
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const int w0 = (t % p.tiles_w) * p.tw;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * p.th;
+            const int n0 = (t / (p.tiles_w * p.tiles_h)) * p.tn;
+            mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
+            tc_fence_after();
+            const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+            // ---- part 1: accumulator -> bias + ReLU -> fp16 -> A operand of the second MMA (both staging buffers)
+            if (etid == 0) bulk_wait_read<0>();   // the previous tile's stores have finished reading the buffers
+            named_bar_sync(1, 128);
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(tmem_base + lane_addr + acc * 128, va);
+#pragma unroll
+                for (int c = 0; c < 4; c += 2) {
+                    uint32_t o[32];
+                    tmem_ld_wait(va);
+                    tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + (c + 1) * 32, vb);
+                    pack_chunk<0>(va, s_bias + c * 32, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                    tmem_ld_wait(vb);
+                    if (c + 2 < 4) tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + (c + 2) * 32, va);
+                    pack_chunk<16>(vb, s_bias + c * 32 + 32, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                    uint8_t* dst = a2_ptr + (c >> 1) * (128 * 128) + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * acc);
+            fence_proxy_async_smem();
+            mbar_arrive(bar_a2full);
+            // ---- part 2: transposed-conv accumulator -> + bias -> fp16 -> strided tile stores (one view per (dy,dx))
+            mbar_wait(bar_d2full, iter & 1);
+            tc_fence_after();
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(d2_tmem + lane_addr, va);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t o[32];
+                    tmem_ld_wait(va);
+                    tmem_ld_32x32(d2_tmem + lane_addr + q * 64 + 32, vb);
+                    pack_chunk<0>(va, s_bias2, no_res, false, false, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                    tmem_ld_wait(vb);
+                    if (q + 1 < 4) tmem_ld_32x32(d2_tmem + lane_addr + (q + 1) * 64, va);
+                    pack_chunk<16>(vb, s_bias2 + 32, no_res, false, false, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                    const int buf = q & 1;
+                    // buffer free: q < 2 -> the second MMA has consumed the A operand (d2full); q >= 2 -> the store of q - 2 has read it
+                    if (q >= 2 && etid == 0) bulk_wait_read<1>();
+                    named_bar_sync(1, 128);
+                    uint8_t* dst = a2_ptr + buf * (128 * 128) + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (etid == 0) {
+                        tma_store_4d(&p.o_map[q], a2_addr + buf * (128 * 128), p.out_c_off, w0, h0, n0);
+                        bulk_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+        if (etid == 0) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
 // 3x3 / stride 1 variant with vertical-tap reuse (and optionally stationary weights) for the wide, shallow layers
 // (Cout = 64 or 128 at 256^2 / 128^2), which are L2->SM bandwidth bound in the generic kernel: every tap re-fetches
 // the same activations.  Here one TMA box {64 ch, 8 w, 18 h} (18 swizzle groups of 1024 B) per horizontal offset dx
@@ -1012,6 +1264,10 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
     L.epilogue = epilogue;
     L.n_max = Nmax;
     L.pdl = 1;
+    if (epilogue == EPI_FUSED_CONVT) {
+        if (L.block_n != 128 || p.n_tiles != 1 || ksize != 3 || stride != 1) return -5;
+        return 0;   // generic tile shape; conv_set_fused_convt completes the launch
+    }
     if (use_vr && conv_try_rs(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, 1, p.tn);
         if (!rc && p.rs_mode == 1) rc = tmap_act(&p.a_map[1], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, 130, 1, 1);
@@ -1091,6 +1347,26 @@ int conv_set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, 
     return rc;
 }
 
+int conv_set_fused_convt(ConvLaunch& L, const __half* w2, const float* bias2, int cout2, __half* out, int out_c_stride, int out_c_off) {
+    ConvParams& p = L.p;
+    if (L.epilogue != EPI_FUSED_CONVT || L.block_n != 128 || p.n_tiles != 1 || cout2 != 64) return -5;
+    if (tmap_init()) return -1;
+    // transposed-conv weights [4 * cout2 rows][128 k]: box {64 k, 256 rows}
+    int rc = tmap_weights(&p.b2_map, w2, 128, 4 * cout2, 256);
+    if (rc) return rc;
+    p.bias2 = bias2;
+    p.convt_cout = cout2;
+    p.out = out;
+    p.out_c_stride = out_c_stride;
+    p.out_c_off = out_c_off;
+    p.relu = 1;
+    p.out_bufs = 2;
+    const int64_t C = out_c_stride, W2 = 2 * p.W, H2 = 2 * p.H;
+    for (int q = 0; q < 4 && !rc; ++q)
+        rc = tmap_act(&p.o_map[q], out + ((q >> 1) * W2 + (q & 1)) * C, out_c_stride, p.W, p.H, L.n_max, 2 * C, 2 * W2 * C, H2 * W2 * C, p.tw, p.th, p.tn);
+    return rc;
+}
+
 constexpr int kVrMaxSmem = 227 * 1024;
 
 template <int BN, int EPI, bool WS>
@@ -1112,6 +1388,7 @@ cudaError_t conv_configure() {
     if ((e = configure_one<128, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::kSmemBytes)) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_STORE, true>()) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_STORE, false>()) != cudaSuccess) return e;
     if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
@@ -1207,6 +1484,10 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     if (total <= 0) return cudaSuccess;
     const int grid = (int)(total < sm_count ? total : sm_count);
     const bool pdl = L.pdl != 0;
+    if (L.epilogue == EPI_FUSED_CONVT) {
+        if (L.variant != 0 || L.block_n != 128 || p.n_tiles != 1 || p.bias2 == nullptr) return cudaErrorInvalidValue;
+        return launch_k(conv_convt_kernel, grid, 256, FusedCfg::kSmemBytes, stream, pdl, p);
+    }
     if (L.variant == 2) {
         cudaError_t e;
         if (L.epilogue == EPI_OUTC) {

@@ -11,6 +11,8 @@ enum ConvEpilogue : int {
     EPI_STORE = 0,   // y = acc + bias (+ residual) (ReLU optional) -> fp16 NHWC with channel stride/offset
     EPI_CONVT = 1,   // 2x2 stride-2 transposed conv: column block q=(dy,dx) scattered to pixel (2h+dy, 2w+dx)
     EPI_OUTC = 2,    // ReLU(acc + bias) . w_out + b_out -> fp32 logit + u8 mask (BLOCK_N == 64 == Cout)
+    EPI_FUSED_CONVT = 3,   // ReLU(acc + bias) stays on chip as the fp16 A operand of a second MMA: the ConvTranspose2d(k2, s2)
+                           // that follows the layer, scattered into the concat buffer (conv_convt_kernel; Cout == 128)
 };
 
 // Kernel parameter block (passed __grid_constant__; the tensor maps must stay 64-byte aligned).
@@ -18,6 +20,8 @@ struct alignas(64) ConvParams {
     CUtensorMap a_map[4];  // activation views, 4-D {C, W, H, N}, box {64, tw, th, tn}, 128-byte swizzle
     CUtensorMap b_map;     // packed weights, 2-D {K_total, Cout_total}, box {64, BLOCK_N}, 128-byte swizzle
     CUtensorMap o_map[4];  // output views for the TMA tile store, box {64, tw, th, tn}; convT: one strided view per (dy,dx)
+    CUtensorMap b2_map;    // EPI_FUSED_CONVT: packed transposed-conv weights, 2-D {Cin2 = 128, 4 * Cout2 = 256}, box {64, 256}
+    const float* bias2;    // EPI_FUSED_CONVT: [Cout2] bias of the transposed convolution
     int out_bufs;          // 16 KB staging buffers for the store (0: EPI_OUTC, 1 or 2 otherwise)
     // K loop: taps x (Cin/64) chunks.  Tap t reads view tap_map[t] at spatial offset (tap_dy[t], tap_dx[t]).
     int taps;
@@ -85,6 +89,10 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
 int conv_build_k2s2(ConvLaunch& L, const __half* in, int Nmax, int Ho, int Wo, int in_c_stride, int in_c_off, int C, const __half* w,
                     const float* bias, int rows, int K);
 int conv_set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, int relu, const __half* res, int res_c_stride);
+// EPI_FUSED_CONVT: the launch built for conv3x3(Cin -> 128) + bias + ReLU additionally applies ConvTranspose2d(128 -> cout2 = 64,
+// k2, s2) (w2 packed [(dy*2+dx)*cout2 + co][128], bias2 [cout2]) and writes channels [out_c_off, out_c_off + cout2) of the
+// double-resolution NHWC buffer `out`; the conv's own output never reaches global memory.
+int conv_set_fused_convt(ConvLaunch& L, const __half* w2, const float* bias2, int cout2, __half* out, int out_c_stride, int out_c_off);
 
 // Launch on `stream` for the first `n_images` images; grid sized to min(tiles, SM count).
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream);

@@ -99,6 +99,18 @@ struct cvb_ctx {
     cvb_trainer* trainer = nullptr;
     cvb_jpeg_state* jpeg = nullptr;
 
+    // ---- CUDA graphs of single-chunk pipeline passes (the latency path: process_image on one board is ~50 launches)
+    struct GraphEntry {
+        uint64_t key[16];            // everything the captured launches bake in: pointers, board count, threshold, flip
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;        // kernels one replay launches
+        uint64_t last_use = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    bool use_graph = true;           // CVB_NO_GRAPH=1 turns it off (A/B measurements)
+    uint64_t graph_clock = 0;
+    int64_t graph_replays = 0;
+
     // ---- profiling
     bool profile = false;
     std::vector<cudaEvent_t> pev;

@@ -572,7 +572,21 @@ __device__ __forceinline__ int pack16(int i) {
 __device__ __forceinline__ int qx(int p) { return p & 255; }
 __device__ __forceinline__ int qy(int p) { return p >> 8; }
 
-// Suzuki-Abe border following on the bit planes (lane 0 only); same control flow as trace_border.
+// The eight neighbours of bit i of plane F as a mask, bit d = F[i + c_boff16[d]] (d: 0 E, 1 NE, 2 N, 3 NW, 4 W, 5 SW, 6 S,
+// 7 SE): three funnel-shifted row reads instead of one dependent table lookup + shared-memory read per probed direction.
+__device__ __forceinline__ uint32_t nbr_mask(const uint32_t* F, int i) {
+    const int j = i - 1;
+    const int b0 = j - FBITS, b1 = j, b2 = j + FBITS;
+    const uint32_t t = __funnelshift_r(F[b0 >> 5], F[(b0 >> 5) + 1], b0 & 31) & 7u;    // bits: 0 = x-1, 1 = x, 2 = x+1
+    const uint32_t m = __funnelshift_r(F[b1 >> 5], F[(b1 >> 5) + 1], b1 & 31) & 7u;
+    const uint32_t u = __funnelshift_r(F[b2 >> 5], F[(b2 >> 5) + 1], b2 & 31) & 7u;
+    return (m >> 2) | ((t >> 2) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) | ((m & 1u) << 4) | ((u & 1u) << 5) | (((u >> 1) & 1u) << 6) |
+           ((u >> 2) << 7);
+}
+
+// Suzuki-Abe border following on the bit planes (lane 0 only); same control flow as trace_border.  Per border point the next
+// direction comes from one neighbourhood mask (rotate + find-first-set replaces the probing loop), the point's coordinates are
+// carried along instead of being divided out of the bit index.
 __device__ void trace_border_bits(const uint32_t* F, uint32_t* V, uint32_t* N, int start, bool hole, uint16_t* P, uint8_t* CODE, Contour& c) {
     int s_end = hole ? 0 : 4;
     int s = s_end;
@@ -592,34 +606,39 @@ __device__ void trace_border_bits(const uint32_t* F, uint32_t* V, uint32_t* N, i
         return;
     }
     int i3 = start, n = 0;
+    int x = qx(p0), y = qy(p0);                 // mask-frame coordinates of i3
+    int minx = x, maxx = x, miny = y, maxy = y;
     for (;;) {
         s_end = s;
-        int i4;
-        do {
-            ++s;
-            i4 = i3 + c_boff16[s & 15];
-        } while (!bit_get(F, i4));
-        s &= 7;
+        // first foreground neighbour in directions s+1, s+2, ... (the point we came from is one, so the mask is never empty)
+        const uint32_t mask = nbr_mask(F, i3);
+        const uint32_t rot = ((mask | (mask << 8)) >> ((s + 1) & 7)) & 0xffu;
+        s = (s + __ffs(rot)) & 7;
+        const int dx = static_cast<int>((0x21000122u >> (4 * s)) & 0xfu) - 1;    // {1, 1, 0, -1, -1, -1, 0, 1}
+        const int dy = static_cast<int>((0x22210001u >> (4 * s)) & 0xfu) - 1;    // {0, -1, -1, -1, 0, 1, 1, 1}
+        const int i4 = i3 + dy * FBITS + dx;
         if (static_cast<unsigned>(s - 1) < static_cast<unsigned>(s_end)) {
             bit_set(V, i3);
             bit_set(N, i3);
         } else {
             bit_set(V, i3);   // "if (label == 1) label = nbd": a visited pixel keeps its sign
         }
-        const int p = pack16(i3);
         if (n < kFastPoints) {
-            P[n] = static_cast<uint16_t>(p);
+            P[n] = static_cast<uint16_t>(x | (y << 8));
             CODE[n] = static_cast<uint8_t>(s);
         }
         ++n;
-        c.minx = min(c.minx, qx(p));
-        c.maxx = max(c.maxx, qx(p));
-        c.miny = min(c.miny, qy(p));
-        c.maxy = max(c.maxy, qy(p));
+        minx = min(minx, x);
+        maxx = max(maxx, x);
+        miny = min(miny, y);
+        maxy = max(maxy, y);
         if (i4 == start && i3 == i1) break;
         i3 = i4;
+        x += dx;
+        y += dy;
         s = (s + 4) & 7;
     }
+    c.minx = minx; c.maxx = maxx; c.miny = miny; c.maxy = maxy;
     c.n = n;
 }
 
@@ -677,8 +696,14 @@ __global__ void __launch_bounds__(32, 4) k_mask_to_quad_fast(const uint8_t* __re
         F[257 * FW + i] = 0u;
     }
     // foreground plane: 16 mask bytes per lane -> 16 bits, two lanes make one word-aligned half... assembled by shuffles
-    for (int it = 0; it < 128; ++it) {       // 512 pixels (two rows) per iteration
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(m) + it * 32 + lane);
+    for (int it0 = 0; it0 < 128; it0 += 8) {   // 512 pixels (two rows) per step; eight independent loads in flight
+      uint4 vv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) vv[u] = __ldg(reinterpret_cast<const uint4*>(m) + (it0 + u) * 32 + lane);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int it = it0 + u;
+        const uint4 v = vv[u];
         uint32_t bits = 0;
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -698,6 +723,7 @@ __global__ void __launch_bounds__(32, 4) k_mask_to_quad_fast(const uint8_t* __re
             F[y * FW + k] = (word << 1) | (k ? prev >> 31 : 0u);
             if (k == 7) F[y * FW + 8] = word >> 31;              // pixel 255 -> bit 256 of the row, bit 257 stays 0
         }
+      }
     }
     __syncwarp();
 
@@ -709,12 +735,23 @@ __global__ void __launch_bounds__(32, 4) k_mask_to_quad_fast(const uint8_t* __re
     int best_d = -1;
     int best_q[4] = {0, 0, 0, 0};
 
-    for (int y = 1; y <= 256 && !need_full; ++y) {
-        uint32_t carry = 0;
-        for (int wi = 0; wi < FW && !need_full; ++wi) {
-            const uint32_t Fw = F[y * FW + wi];
-            uint32_t T = Fw ^ ((Fw << 1) | carry);
-            carry = Fw >> 31;
+    // Raster scan for border starting points = 0/1 transitions along a row.  They depend on F alone (border following only
+    // changes V and N), so the warp finds them for three rows (27 plane words) at once and then walks the words that have
+    // any, in raster order; the visited / right-bound tests still happen at the moment a transition is reached.
+    const int r_lane = lane / FW, w_lane = lane - r_lane * FW;
+    for (int y0 = 1; y0 <= 256 && !need_full; y0 += 3) {
+        const bool act = lane < 3 * FW && y0 + r_lane <= 256;
+        const uint32_t Fl = act ? F[(y0 + r_lane) * FW + w_lane] : 0u;
+        uint32_t prevw = __shfl_up_sync(FULL, Fl, 1);
+        if (w_lane == 0) prevw = 0u;
+        const uint32_t Tl = act ? (Fl ^ ((Fl << 1) | (prevw >> 31))) : 0u;
+        unsigned pending = __ballot_sync(FULL, Tl != 0u);
+        while (pending && !need_full) {
+            const int src = __ffs(pending) - 1;
+            pending &= pending - 1;
+            const uint32_t Fw = __shfl_sync(FULL, Fl, src);
+            uint32_t T = __shfl_sync(FULL, Tl, src);
+            const int y = y0 + src / FW, wi = src % FW;
             while (T && !need_full) {
                 const int bpos = __ffs(T) - 1;
                 T &= T - 1;

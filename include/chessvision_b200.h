@@ -217,6 +217,9 @@ CVB_API int cvb_decode_jpeg(cvb_ctx* ctx, const uint8_t* const* data, const int6
 
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 CVB_API int64_t cvb_launch_count(const cvb_ctx* ctx);
+/* Pipeline passes of at most one chunk (max_batch boards) on a capturable stream are captured once into a CUDA graph and
+ * replayed (ChessVision.process_image on one board is ~50 launches); this counts the replays.  CVB_NO_GRAPH=1 disables it. */
+CVB_API int64_t cvb_graph_replays(const cvb_ctx* ctx);
 
 /* Time (ms, CUDA events on the launching stream) accumulated per stage since the last reset; stage ids:
  * 0 unet convs (tcgen05), 1 unet aux (stem, pools), 2 mask->quad, 3 homography+warp, 4 resnet stem,

@@ -317,3 +317,29 @@ def test_utils_drop_in_functions(golden):
     got = utils.extract_perspective(imgs[i], quad, (512, 512))
     dest = np.array(((0, 0), (512, 0), (512, 512), (0, 512)), np.float32)
     assert np.array_equal(got, cv2.warpPerspective(imgs[i], cv2.getPerspectiveTransform(quad.reshape(4, 2), dest), (512, 512)))
+
+
+
+def test_single_board_pass_replays_a_cuda_graph(golden, monkeypatch):
+    """process_image on one board: the ~50 launches of the pass are captured into a CUDA graph on the first call and replayed
+    afterwards; results are identical to direct launches (CVB_NO_GRAPH=1), for changing inputs, thresholds and orientations."""
+    from chessvision import ChessVision
+    man, _, imgs = golden
+    kw = dict(board_extractor_weights=str(WEIGHTS / "best_extractor.pth"), classifier_weights=str(WEIGHTS / "best_classifier.pth"),
+              classifier_model_id="resnet18", max_batch=4)
+    cv = ChessVision(**kw)
+    got = [cv.process_image(imgs[i], threshold=t, flip=f) for i, t, f in [(0, 0.5, False), (1, 0.5, False), (2, 0.5, True), (3, 0.3, False), (0, 0.5, False)]]
+    assert cv._engine.graph_replays() >= 5
+    batch = cv.process_images(imgs[:3])          # three boards: still one chunk, another graph
+    monkeypatch.setenv("CVB_NO_GRAPH", "1")
+    ref = ChessVision(**kw)
+    want = [ref.process_image(imgs[i], threshold=t, flip=f) for i, t, f in [(0, 0.5, False), (1, 0.5, False), (2, 0.5, True), (3, 0.3, False), (0, 0.5, False)]]
+    assert ref._engine.graph_replays() == 0
+    for a, b in zip(got + batch, want + [ref.process_image(imgs[i]) for i in range(3)]):
+        assert np.array_equal(a.board_extraction.probabilities, b.board_extraction.probabilities)
+        assert np.array_equal(a.board_extraction.binary_mask, b.board_extraction.binary_mask)
+        assert (a.position is None) == (b.position is None)
+        if a.position is not None:
+            assert (a.position.fen, a.position.original_fen) == (b.position.fen, b.position.original_fen)
+            assert np.array_equal(a.position.model_probabilities, b.position.model_probabilities)
+            assert np.array_equal(a.board_extraction.board_image, b.board_extraction.board_image)

@@ -127,3 +127,36 @@ def test_process_image_input_asserts():
         ChessVision.process_board_extraction_logits(np.zeros((256, 256), np.float64), np.zeros((512, 512, 3), np.uint8), 0.5)
     with pytest.raises(AssertionError):
         ChessVision.process_board_extraction_logits(np.zeros((256, 256), np.float32), np.zeros((512, 512, 3), np.uint8), 1.5)
+
+
+def test_checkpoint_writers_and_strip_optimizer(tmp_path):
+    """train_unet.py:31-40 / train_classifier.py:112-123 / strip_optimizer.py:15-47: the three-key checkpoint, its stripped form,
+    and utils.load_model_checkpoint reading every layout into a drop-in module (parameter names of timm's resnet18)."""
+    from chessvision import checkpoints
+    from chessvision.modules import NativeResNet18, NativeUNet
+    model = utils.get_classifier_model("resnet18")
+    assert isinstance(model, NativeResNet18) and sum(p.numel() for p in model.parameters()) == 11_176_909   # notebooks/model-summary.ipynb:233
+    assert sum(p.numel() for p in NativeUNet().parameters()) == 31_037_633                                  # SURVEY.md 8(e)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    path = tmp_path / "cls.pth"
+    checkpoints.save_classifier_checkpoint(model, str(path), opt, {"epochs": 2})
+    blob = torch.load(path, map_location="cpu")
+    assert set(blob) == {"model_state_dict", "optimizer_state_dict", "metadata"} and checkpoints.checkpoint_layout(str(path)) == "model_state_dict"
+    checkpoints.strip_optimizer(str(path), str(tmp_path / "stripped.pth"))
+    stripped = torch.load(tmp_path / "stripped.pth", map_location="cpu")
+    assert set(stripped) == {"model_state_dict", "metadata"} and stripped["metadata"] == {"epochs": 2}
+    fresh = utils.load_model_checkpoint(utils.get_classifier_model(), str(tmp_path / "stripped.pth"), torch.device("cpu"))
+    assert fresh.metadata == {"epochs": 2}
+    for (ka, va), (kb, vb) in zip(model.state_dict().items(), fresh.state_dict().items()):
+        assert ka == kb and torch.equal(va, vb)
+    torch.save({"state_dict": model.state_dict(), "optimizer": 1}, tmp_path / "timm.pth")
+    checkpoints.strip_optimizer(str(tmp_path / "timm.pth"))                       # in place
+    assert set(torch.load(tmp_path / "timm.pth", map_location="cpu")) == {"state_dict", "metadata"}
+    torch.save({"model": model.state_dict()}, tmp_path / "legacy.pth")
+    checkpoints.strip_optimizer(str(tmp_path / "legacy.pth"))                     # unexpected layout: left as it is
+    assert set(torch.load(tmp_path / "legacy.pth", map_location="cpu")) == {"model"}
+    with pytest.raises(RuntimeError):
+        model.train()                                                            # inference modules: training goes through chessvision.training
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            model(torch.zeros(64, 1, 64, 64))                                     # no CPU fallback behind the module either
