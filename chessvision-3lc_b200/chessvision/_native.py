@@ -62,6 +62,7 @@ SYMBOLS = {
     "cvb_image_to_fen_host_progress": (_I, [_P, _P, _I, _F, _I, C.POINTER(_Outputs), _P]),
     "cvb_conv2d_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "cvb_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P]),
+    "cvb_conv3x3_convt2x2_f16": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _I, _I, _P]),
     "cvb_unet_stem": (_I, [_P, _P, _I, _P, _P]),
     "cvb_resnet_stem": (_I, [_P, _P, _I, _P, _P]),
     "cvb_train_default_config": (_I, [C.POINTER(TrainConfig)]),
@@ -304,6 +305,12 @@ class Engine:
         n, h, w, cin = x.shape
         self._ck(self.lib.cvb_convt2x2_f16(self.h, _ptr(x), n, h, w, cin, _ptr(w_packed), _ptr(bias4), cout, _ptr(out), out.shape[3],
                                            out_c_off, _stream()), "cvb_convt2x2_f16")
+        return out
+
+    def conv3x3_convt2x2_f16(self, x, w_packed, bias, w2_packed, bias2, cout2, out, out_c_off):
+        n, h, w, cin = x.shape
+        self._ck(self.lib.cvb_conv3x3_convt2x2_f16(self.h, _ptr(x), n, h, w, cin, _ptr(w_packed), _ptr(bias), _ptr(w2_packed), _ptr(bias2), cout2,
+                                                   _ptr(out), out.shape[3], out_c_off, _stream()), "cvb_conv3x3_convt2x2_f16")
         return out
 
     def unet_stem(self, img):

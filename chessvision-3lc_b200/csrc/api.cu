@@ -343,8 +343,10 @@ int unet_forward(cvb_ctx* ctx, const uint8_t* img, int n, float thr, float* logi
     if (P[6].p.pool_out == nullptr) { StageTimer t(ctx, 1, s); CK(aux(launch_maxpool2(ctx->cat3, ctx->p4, n, 32, 32, 512, 1024, s))); }
     {
         StageTimer t(ctx, 0, s);
-        for (int i = 7; i <= 19; ++i)                                                             // down4, up1..up4.conv0
+        for (int i = 7; i <= 19; ++i) {                                                           // down4, up1..up4.conv0
+            if (i == 18 && ctx->fuse_up4) continue;                                               // up4.up ran inside P[17]
             if (run_conv(ctx, P[i], n, s)) return -2;
+        }
         ConvLaunch& last = P[20];                                                                 // up4.conv3 + outc
         last.p.logits = logits ? logits : ctx->ws_logits;
         last.p.mask = mask ? mask : ctx->ws_mask;
@@ -693,8 +695,16 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     rc |= build_conv(ctx, P[14], ctx->t2, B, 64, 64, 256, 0, 256, W[14], 3, 1, EPI_STORE);    rc |= set_store(ctx, P[14], ctx->u2, 256, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[15], ctx->u2, B, 64, 64, 256, 0, 256, W[15], 1, 1, EPI_CONVT);    rc |= set_store(ctx, P[15], ctx->cat1, 256, 128, 0, nullptr, 0);  P[15].p.convt_cout = 128;
     rc |= build_conv(ctx, P[16], ctx->cat1, B, 128, 128, 256, 0, 256, W[16], 3, 1, EPI_STORE); rc |= set_store(ctx, P[16], ctx->t1, 128, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[17], ctx->t1, B, 128, 128, 128, 0, 128, W[17], 3, 1, EPI_STORE);  rc |= set_store(ctx, P[17], ctx->u3, 128, 0, 1, nullptr, 0);
-    rc |= build_conv(ctx, P[18], ctx->u3, B, 128, 128, 128, 0, 128, W[18], 1, 1, EPI_CONVT);  rc |= set_store(ctx, P[18], ctx->cat0, 128, 64, 0, nullptr, 0);   P[18].p.convt_cout = 64;
+    ctx->fuse_up4 = getenv("CVB_NO_CONVT_FUSE") == nullptr;
+    if (ctx->fuse_up4) {
+        // up3.conv.3 + up4.up in one kernel (conv_convt_kernel): the 128-channel tensor between them never reaches HBM
+        rc |= build_conv(ctx, P[17], ctx->t1, B, 128, 128, 128, 0, 128, W[17], 3, 1, EPI_FUSED_CONVT);
+        if (!rc && conv_set_fused_convt(P[17], W[18].w, W[18].bias, 64, ctx->cat0, 128, 64)) rc = fail(ctx, -6, "fused conv + transposed conv plan failed");
+        memset(&P[18], 0, sizeof P[18]);
+    } else {
+        rc |= build_conv(ctx, P[17], ctx->t1, B, 128, 128, 128, 0, 128, W[17], 3, 1, EPI_STORE);  rc |= set_store(ctx, P[17], ctx->u3, 128, 0, 1, nullptr, 0);
+        rc |= build_conv(ctx, P[18], ctx->u3, B, 128, 128, 128, 0, 128, W[18], 1, 1, EPI_CONVT);  rc |= set_store(ctx, P[18], ctx->cat0, 128, 64, 0, nullptr, 0);   P[18].p.convt_cout = 64;
+    }
     rc |= build_conv(ctx, P[19], ctx->cat0, B, 256, 256, 128, 0, 128, W[19], 3, 1, EPI_STORE); rc |= set_store(ctx, P[19], ctx->t0, 64, 0, 1, nullptr, 0);
     rc |= build_conv(ctx, P[20], ctx->t0, B, 256, 256, 64, 0, 64, W[20], 3, 1, EPI_OUTC);     // + outc 1x1 + sigmoid/threshold
     P[20].p.relu = 1;
@@ -987,6 +997,22 @@ int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin,
     if (build_conv(ctx, L, static_cast<const __half*>(in), N, H, W, Cin, 0, Cin, cw, 1, 1, EPI_CONVT)) return -5;
     if (set_store(ctx, L, static_cast<__half*>(out), out_c_stride, out_c_off, 0, nullptr, 0)) return -6;
     L.p.convt_cout = Cout;
+    return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
+}
+
+int cvb_conv3x3_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias,
+                             const void* w2_packed, const float* bias2, int Cout2, void* out, int out_c_stride, int out_c_off, void* stream) {
+    if (!ctx || !in || !w_packed || !bias || !w2_packed || !bias2 || !out) return -1;
+    CVB_ON_DEVICE(ctx);
+    ConvWeights cw;
+    cw.w = const_cast<__half*>(static_cast<const __half*>(w_packed));
+    cw.bias = const_cast<float*>(bias);
+    cw.rows = 128;
+    cw.K = 9 * Cin;
+    ConvLaunch L;
+    if (build_conv(ctx, L, static_cast<const __half*>(in), N, H, W, Cin, 0, Cin, cw, 3, 1, EPI_FUSED_CONVT)) return -5;
+    if (conv_set_fused_convt(L, static_cast<const __half*>(w2_packed), bias2, Cout2, static_cast<__half*>(out), out_c_stride, out_c_off))
+        return fail(ctx, -5, "fused conv + transposed conv: only 128 -> 64 channels is supported");
     return run_conv(ctx, L, N, static_cast<cudaStream_t>(stream));
 }
 

@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 // is drained, biased and scattered by the same four epilogue warps through the strided output views of EPI_CONVT.  The
 // results are bit-identical to the two separate kernels (same fp16 rounding point, same accumulation order).
 //   warp 0 TMA producer (transposed-conv weights once, then the main pipeline), warp 1 MMA issue (main K loop of tile i; the
-//   second MMA of tile i-1 is slipped in as soon as its A operand is ready), warp 2 TMEM, warps 4-7 epilogue.
+//   second MMA of tile i-1 is slipped in as soon as its A operand is ready), warp 2 TMEM, warps 4-11 epilogue (two groups).
 // ---------------------------------------------------------------------------------------------------------------------
 struct FusedCfg {
     static constexpr int kStages = 3;
@@ -387,7 +387,9 @@ struct FusedCfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kW2Bytes + kA2Bytes + 1024 + 256 + (128 + 64) * 4;
 };
 
-__global__ void __launch_bounds__(256, 1) conv_convt_kernel(const __grid_constant__ ConvParams p) {
+constexpr int kFusedThreads = 384;   // TMA, MMA, TMEM, idle warp + two epilogue groups of four warps
+
+__global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = FusedCfg;
     constexpr int S = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -423,10 +425,10 @@ __global__ void __launch_bounds__(256, 1) conv_convt_kernel(const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 128);
+            mbar_init(bar_tempty + 8 * i, 256);
         }
         mbar_init(bar_w2, 1);
-        mbar_init(bar_a2full, 128);
+        mbar_init(bar_a2full, 256);
         mbar_init(bar_d2full, 1);
         mbar_fence_init();
     }
@@ -535,11 +537,16 @@ __global__ void __launch_bounds__(256, 1) conv_convt_kernel(const __grid_constan
             mma2();
         }
     } else if (warp >= 4) {
-        const int quarter = warp & 3, etid = threadIdx.x - 128;
+        // Two epilogue groups (warps 4-7 / 8-11) work on the SAME tile: group g converts channels 64g .. 64g+63 of the
+        // accumulator into K block g of the A operand, then drains taps q = 2g, 2g+1 of the transposed-conv accumulator and
+        // stores them from "its" K block (free again once the second MMA has completed).  That halves the chain
+        // accumulator -> A operand -> second MMA -> scatter, which otherwise outlasts the main K loop of the next tile.
+        const int quarter = warp & 3, g = (warp - 4) >> 2, etid = (threadIdx.x - 128) & 127;
         const int row = quarter * 32 + lane;
-        const int rh = (row / p.tw) % p.th, rw = row % p.tw, rn = row / (p.th * p.tw);
-        (void)rh; (void)rw; (void)rn;
         const uint32_t no_res[32] = {0};
+        uint8_t* my_buf = a2_ptr + g * (128 * 128);
+        const uint32_t my_buf_addr = a2_addr + g * (128 * 128);
+        const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
         int iter = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int acc = iter & 1;
@@ -548,59 +555,53 @@ __global__ void __launch_bounds__(256, 1) conv_convt_kernel(const __grid_constan
             const int n0 = (t / (p.tiles_w * p.tiles_h)) * p.tn;
             mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
             tc_fence_after();
-            const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-            // ---- part 1: accumulator -> bias + ReLU -> fp16 -> A operand of the second MMA (both staging buffers)
-            if (etid == 0) bulk_wait_read<0>();   // the previous tile's stores have finished reading the buffers
-            named_bar_sync(1, 128);
+            // ---- part 1: accumulator -> bias + ReLU -> fp16 -> K block g of the second MMA's A operand
+            if (etid == 0) bulk_wait_read<0>();   // this group's stores of the previous tile have finished reading the block
+            named_bar_sync(1 + g, 128);
             {
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(tmem_base + lane_addr + acc * 128, va);
+                uint32_t va[32], vb[32], o[32];
+                tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + g * 64, va);
+                tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + g * 64 + 32, vb);
+                tmem_ld_wait(va);
+                pack_chunk<0>(va, s_bias + g * 64, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                tmem_ld_wait(vb);
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * acc);          // the accumulator half is in registers: release it early
+                pack_chunk<16>(vb, s_bias + g * 64 + 32, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                uint8_t* dst = my_buf + row * 128;
 #pragma unroll
-                for (int c = 0; c < 4; c += 2) {
-                    uint32_t o[32];
-                    tmem_ld_wait(va);
-                    tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + (c + 1) * 32, vb);
-                    pack_chunk<0>(va, s_bias + c * 32, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[0]));
-                    tmem_ld_wait(vb);
-                    if (c + 2 < 4) tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + (c + 2) * 32, va);
-                    pack_chunk<16>(vb, s_bias + c * 32 + 32, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[16]));
-                    uint8_t* dst = a2_ptr + (c >> 1) * (128 * 128) + row * 128;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                }
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
             fence_proxy_async_smem();
             mbar_arrive(bar_a2full);
-            // ---- part 2: transposed-conv accumulator -> + bias -> fp16 -> strided tile stores (one view per (dy,dx))
+            // ---- part 2: taps q = 2g, 2g+1 of the transposed-conv accumulator -> + bias -> fp16 -> strided tile stores
             mbar_wait(bar_d2full, iter & 1);
             tc_fence_after();
             {
                 uint32_t va[32], vb[32];
-                tmem_ld_32x32(d2_tmem + lane_addr, va);
+                tmem_ld_32x32(d2_tmem + lane_addr + (2 * g) * 64, va);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
+                for (int qq = 0; qq < 2; ++qq) {
+                    const int q = 2 * g + qq;
                     uint32_t o[32];
                     tmem_ld_wait(va);
                     tmem_ld_32x32(d2_tmem + lane_addr + q * 64 + 32, vb);
                     pack_chunk<0>(va, s_bias2, no_res, false, false, reinterpret_cast<uint32_t(&)[16]>(o[0]));
                     tmem_ld_wait(vb);
-                    if (q + 1 < 4) tmem_ld_32x32(d2_tmem + lane_addr + (q + 1) * 64, va);
+                    if (qq == 0) tmem_ld_32x32(d2_tmem + lane_addr + (q + 1) * 64, va);
                     pack_chunk<16>(vb, s_bias2 + 32, no_res, false, false, reinterpret_cast<uint32_t(&)[16]>(o[16]));
-                    const int buf = q & 1;
-                    // buffer free: q < 2 -> the second MMA has consumed the A operand (d2full); q >= 2 -> the store of q - 2 has read it
-                    if (q >= 2 && etid == 0) bulk_wait_read<1>();
-                    named_bar_sync(1, 128);
-                    uint8_t* dst = a2_ptr + buf * (128 * 128) + row * 128;
+                    // block free: qq = 0 -> the second MMA has consumed it (d2full); qq = 1 -> this group's first store has read it
+                    if (qq == 1 && etid == 0) bulk_wait_read<0>();
+                    named_bar_sync(1 + g, 128);
+                    uint8_t* dst = my_buf + row * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
+                    named_bar_sync(1 + g, 128);
                     if (etid == 0) {
-                        tma_store_4d(&p.o_map[q], a2_addr + buf * (128 * 128), p.out_c_off, w0, h0, n0);
+                        tma_store_4d(&p.o_map[q], my_buf_addr, p.out_c_off, w0, h0, n0);
                         bulk_commit();
                     }
                 }
@@ -1486,7 +1487,7 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     const bool pdl = L.pdl != 0;
     if (L.epilogue == EPI_FUSED_CONVT) {
         if (L.variant != 0 || L.block_n != 128 || p.n_tiles != 1 || p.bias2 == nullptr) return cudaErrorInvalidValue;
-        return launch_k(conv_convt_kernel, grid, 256, FusedCfg::kSmemBytes, stream, pdl, p);
+        return launch_k(conv_convt_kernel, grid, kFusedThreads, FusedCfg::kSmemBytes, stream, pdl, p);
     }
     if (L.variant == 2) {
         cudaError_t e;

@@ -56,6 +56,7 @@ struct cvb_ctx {
     std::vector<ConvWeights> unet_w;                   // 17 conv3x3 + 4 convT, in plan order
     __half *cat0, *t0, *p1, *t1, *cat1, *p2, *t2, *cat2, *p3, *t3, *cat3, *p4, *t4, *x5, *u1, *u2, *u3;
     std::vector<ConvLaunch> unet_plan;                 // indices documented in build_unet_plan
+    bool fuse_up4 = true;                              // up3.conv.3 + up4.up as one kernel (CVB_NO_CONVT_FUSE=1: two launches)
     float* ws_logits = nullptr;                        // [B,256,256]
     uint8_t* ws_mask = nullptr;                        // [B,256,256]
 

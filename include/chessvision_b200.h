@@ -128,6 +128,13 @@ CVB_API int cvb_conv2d_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, in
 CVB_API int cvb_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias,
                      int Cout, void* out, int out_c_stride, int out_c_off, void* stream);
 
+/* conv3x3(Cin -> 128, pad 1) + bias + ReLU followed by ConvTranspose2d(128 -> 64, k2, s2) + bias in ONE kernel (the UNet's
+ * up3.conv.double_conv.3 + up4.up, unet_parts.py:16-21,53): the 128-channel intermediate stays on chip.  Operand layouts as in
+ * cvb_conv2d_f16 / cvb_convt2x2_f16 (bias2: fp32 [Cout2], Cout2 = 64); bit-identical to calling those two. */
+CVB_API int cvb_conv3x3_convt2x2_f16(cvb_ctx* ctx, const void* in, int N, int H, int W, int Cin, const void* w_packed, const float* bias,
+                                     const void* w2_packed, const float* bias2, int Cout2, void* out, int out_c_stride, int out_c_off,
+                                     void* stream);
+
 /* First layers alone (parity tests): fused preprocessing + first convolution of each network on tcgen05.
  * cvb_unet_stem:   img u8[N,512,512,3] -> fp16 NHWC [N,256,256,64]  = ReLU(BN(conv3x3(resize_area(img)/255)))  (core.py:212-216,
  *                  unet_parts.py:16-18);  cvb_resnet_stem: board u8[N,512,512] -> fp16 NHWC [N*64,16,16,64] = maxpool3x3s2(ReLU(BN(
