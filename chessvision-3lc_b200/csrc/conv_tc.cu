@@ -375,39 +375,43 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 // stored -- and leaves it in shared memory as the A operand of a second MMA against the resident transposed-conv weights
 // (N = 4 taps x 64 channels = 256, K = 128); its accumulator (256 TMEM columns next to the two 128-column main accumulators)
 // is drained, biased and scattered by the same four epilogue warps through the strided output views of EPI_CONVT.  The
-// results are bit-identical to the two separate kernels (same fp16 rounding point, same accumulation order).
+// results equal those of the two separate kernels (same fp16 rounding point, same accumulation order as conv3x3_vr_kernel).
 //   warp 0 TMA producer (transposed-conv weights once, then the main pipeline), warp 1 MMA issue (main K loop of tile i; the
 //   second MMA of tile i-1 is slipped in as soon as its A operand is ready), warp 2 TMEM, warps 4-11 epilogue (two groups).
 // ---------------------------------------------------------------------------------------------------------------------
 struct FusedCfg {
-    static constexpr int kStages = 3;
-    static constexpr int kABytes = 128 * 128, kBBytes = 128 * 128, kStageBytes = kABytes + kBBytes;
+    // main loop in the vertical-reuse form (see conv3x3_vr_kernel): one activation box {64 ch, 8 w, 18 h} per (K chunk, dx)
+    // serves the three vertical taps, whose weight tiles flow through a ring of their own
+    static constexpr int kAStages = 2, kBStages = 5;
+    static constexpr int kABytes = 18 * 1024, kBBytes = 128 * 128;
     static constexpr int kW2Bytes = 2 * 256 * 128;   // two K blocks of [256 rows][64 k]
     static constexpr int kA2Bytes = 2 * 128 * 128;   // two K blocks of [128 pixels][64 k]; reused as the two store staging buffers
-    static constexpr int kSmemBytes = kStages * kStageBytes + kW2Bytes + kA2Bytes + 1024 + 256 + (128 + 64) * 4;
+    static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kW2Bytes + kA2Bytes + 1024 + 256 + (128 + 64) * 4;
 };
-
 constexpr int kFusedThreads = 384;   // TMA, MMA, TMEM, idle warp + two epilogue groups of four warps
 
 __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = FusedCfg;
-    constexpr int S = Cfg::kStages;
+    constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
-    const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;
-    uint8_t* tiles_ptr = smem_raw + (tiles_addr - raw_addr);
-    const uint32_t w2_addr = tiles_addr + S * Cfg::kStageBytes;
+    const uint32_t a_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (a_addr - raw_addr);
+    const uint32_t b_addr = a_addr + SA * Cfg::kABytes;
+    const uint32_t w2_addr = b_addr + SB * Cfg::kBBytes;
     const uint32_t a2_addr = w2_addr + Cfg::kW2Bytes;
-    uint8_t* a2_ptr = tiles_ptr + S * Cfg::kStageBytes + Cfg::kW2Bytes;
+    uint8_t* a2_ptr = base_ptr + SA * Cfg::kABytes + SB * Cfg::kBBytes + Cfg::kW2Bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(a2_ptr + Cfg::kA2Bytes);
-    const uint32_t bar_full = smem_u32(bars);
-    const uint32_t bar_empty = bar_full + 8 * S;
-    const uint32_t bar_tfull = bar_full + 16 * S;
+    const uint32_t bar_afull = smem_u32(bars);
+    const uint32_t bar_aempty = bar_afull + 8 * SA;
+    const uint32_t bar_bfull = bar_aempty + 8 * SA;
+    const uint32_t bar_bempty = bar_bfull + 8 * SB;
+    const uint32_t bar_tfull = bar_bempty + 8 * SB;
     const uint32_t bar_tempty = bar_tfull + 16;
     const uint32_t bar_w2 = bar_tfull + 32;
     const uint32_t bar_a2full = bar_tfull + 40;
     const uint32_t bar_d2full = bar_tfull + 48;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 8);
     float* s_bias = reinterpret_cast<float*>(a2_ptr + Cfg::kA2Bytes + 256);
     float* s_bias2 = s_bias + 128;
 
@@ -419,9 +423,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
         tma_prefetch_desc(&p.a_map[0]);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < S; ++i) {
-            mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(bar_afull + 8 * i, 1);
+            mbar_init(bar_aempty + 8 * i, 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(bar_bfull + 8 * i, 1);
+            mbar_init(bar_bempty + 8 * i, 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
@@ -446,7 +454,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
     if (warp != 0) griddep_wait();
 
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;   // one N tile: all 128 channels of a pixel in this CTA
-    const int k_steps = p.taps * p.c_chunks;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -456,24 +463,30 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
         }
         __syncwarp();
         griddep_wait();
-        int stage = 0;
-        uint32_t phase = 0;
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int w0 = (t % p.tiles_w) * p.tw;
-            const int h0 = ((t / p.tiles_w) % p.tiles_h) * p.th;
-            const int n0 = (t / (p.tiles_w * p.tiles_h)) * p.tn;
-            for (int tap = 0; tap < p.taps; ++tap) {
-                const int hh = h0 + p.tap_dy[tap], ww = w0 + p.tap_dx[tap];
-                for (int kc = 0; kc < p.c_chunks; ++kc) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const int w0 = (t % p.tiles_w) * 8;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
+            const int n0 = t / (p.tiles_w * p.tiles_h);
+            for (int kc = 0; kc < p.c_chunks; ++kc) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(bar_aempty + 8 * as, aph ^ 1);
                     if (elect_one()) {
-                        const uint32_t a_dst = tiles_addr + stage * Cfg::kStageBytes;
-                        mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
-                        tma_load_4d(a_dst, &p.a_map[0], bar_full + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
-                        tma_load_2d(a_dst + Cfg::kABytes, &p.b_map, bar_full + 8 * stage, (tap * p.c_chunks + kc) * 64, 0);
+                        mbar_expect_tx(bar_afull + 8 * as, Cfg::kABytes);
+                        tma_load_4d(a_addr + as * Cfg::kABytes, &p.a_map[0], bar_afull + 8 * as, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
                     }
                     __syncwarp();
-                    if (++stage == S) { stage = 0; phase ^= 1; }
+                    if (++as == SA) { as = 0; aph ^= 1; }
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+                        if (elect_one()) {
+                            mbar_expect_tx(bar_bfull + 8 * bs, Cfg::kBBytes);
+                            tma_load_2d(b_addr + bs * Cfg::kBBytes, &p.b_map, bar_bfull + 8 * bs, ((dy * 3 + dxi) * p.c_chunks + kc) * 64, 0);
+                        }
+                        __syncwarp();
+                        if (++bs == SB) { bs = 0; bph ^= 1; }
+                    }
                 }
             }
         }
@@ -481,7 +494,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
         const bool leader = elect_one();
         const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_sw128(0));
-        const uint32_t a_lo0 = desc_lo0 + ((tiles_addr & 0x3FFFFu) >> 4);
+        const uint32_t a_lo0 = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
+        const uint32_t b_lo0 = desc_lo0 + ((b_addr & 0x3FFFFu) >> 4);
         const uint32_t w2_lo = desc_lo0 + ((w2_addr & 0x3FFFFu) >> 4);
         const uint32_t a2_lo = desc_lo0 + ((a2_addr & 0x3FFFFu) >> 4);
         const uint32_t idesc = umma_idesc_f16(128, 128, 0), idesc2 = umma_idesc_f16(128, 256, 0);
@@ -500,8 +514,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
             __syncwarp();
         };
         mbar_wait(bar_w2, 0);
-        int stage = 0;
-        uint32_t phase = 0;
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
         int iter = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int acc = iter & 1;
@@ -509,23 +523,34 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 128;
             bool pending2 = iter > 0;   // the previous tile's second MMA: issued as soon as the epilogue has produced its A operand
-            for (int kb = 0; kb < k_steps; ++kb) {
-                if (pending2 && mbar_try_wait(bar_a2full, (iter - 1) & 1)) {
-                    mma2();
-                    pending2 = false;
-                }
-                mbar_wait(bar_full + 8 * stage, phase);
-                tc_fence_after();
-                if (leader) {
-                    const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
-                    const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
+            for (int kc = 0; kc < p.c_chunks; ++kc) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    if (pending2 && mbar_try_wait(bar_a2full, (iter - 1) & 1)) {
+                        mma2();
+                        pending2 = false;
+                    }
+                    mbar_wait(bar_afull + 8 * as, aph);
+                    const uint32_t a_lo = a_lo0 + as * (Cfg::kABytes >> 4);
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(bar_bfull + 8 * bs, bph);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t b_lo = b_lo0 + bs * (Cfg::kBBytes >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(bar_empty + 8 * stage);
-                    if (kb == k_steps - 1) umma_commit(bar_tfull + 8 * acc);
+                            for (int k = 0; k < 4; ++k)   // tap dy: the same box one 8-row swizzle group (1024 B) further
+                                umma_f16(d_tmem, desc_hi | (a_lo + dy * 64 + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kc | dxi | dy | k) != 0 ? 1u : 0u);
+                            umma_commit(bar_bempty + 8 * bs);
+                        }
+                        __syncwarp();
+                        if (++bs == SB) { bs = 0; bph ^= 1; }
+                    }
+                    if (leader) {
+                        umma_commit(bar_aempty + 8 * as);
+                        if (kc == p.c_chunks - 1 && dxi == 2) umma_commit(bar_tfull + 8 * acc);
+                    }
+                    __syncwarp();
+                    if (++as == SA) { as = 0; aph ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == S) { stage = 0; phase ^= 1; }
             }
             if (pending2) {
                 mbar_wait(bar_a2full, (iter - 1) & 1);
@@ -542,7 +567,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
         // stores them from "its" K block (free again once the second MMA has completed).  That halves the chain
         // accumulator -> A operand -> second MMA -> scatter, which otherwise outlasts the main K loop of the next tile.
         const int quarter = warp & 3, g = (warp - 4) >> 2, etid = (threadIdx.x - 128) & 127;
-        const int row = quarter * 32 + lane;
+        const int row = quarter * 32 + lane;   // = 8 * (row of the 16 x 8 tile) + column
         const uint32_t no_res[32] = {0};
         uint8_t* my_buf = a2_ptr + g * (128 * 128);
         const uint32_t my_buf_addr = a2_addr + g * (128 * 128);
@@ -550,9 +575,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
         int iter = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int acc = iter & 1;
-            const int w0 = (t % p.tiles_w) * p.tw;
-            const int h0 = ((t / p.tiles_w) % p.tiles_h) * p.th;
-            const int n0 = (t / (p.tiles_w * p.tiles_h)) * p.tn;
+            const int w0 = (t % p.tiles_w) * 8;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
+            const int n0 = t / (p.tiles_w * p.tiles_h);
             mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
             tc_fence_after();
             // ---- part 1: accumulator -> bias + ReLU -> fp16 -> K block g of the second MMA's A operand
@@ -1266,8 +1291,11 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
     L.n_max = Nmax;
     L.pdl = 1;
     if (epilogue == EPI_FUSED_CONVT) {
-        if (L.block_n != 128 || p.n_tiles != 1 || ksize != 3 || stride != 1) return -5;
-        return 0;   // generic tile shape; conv_set_fused_convt completes the launch
+        if (L.block_n != 128 || p.n_tiles != 1 || ksize != 3 || stride != 1 || Ho % 16 || Wo % 8) return -5;
+        p.tn = 1; p.th = 16; p.tw = 8;   // the vertical-reuse tile: 16 rows x 8 columns, activation box {64, 8, 18, 1}
+        p.tiles_w = Wo / 8;
+        p.tiles_h = Ho / 16;
+        return tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);   // conv_set_fused_convt completes the launch
     }
     if (use_vr && conv_try_rs(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN, p.tw, 1, p.tn);

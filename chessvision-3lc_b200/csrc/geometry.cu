@@ -1155,19 +1155,28 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
     const int nrows = y_max + 3 - y_lo;                  // rows    y_lo .. y_max + 2
     fits = fits && ncol16 <= kWpCols16 && nrows <= kWpRows && x_max - x_min < 4096 && y_max - y_min < 4096;
     if (fits) {
-        for (int g = t; g < nrows * ncol16; g += 256) {
-            const int r = g / ncol16, c16 = g - r * ncol16;
-            const int gy = y_lo + r, gx = x_lo + 16 * c16;
-            uint32_t w[12];
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-                const uint4* s4 = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(gy) * W + gx) * 3);
-                const uint4 a = __ldg(s4), c = __ldg(s4 + 1), d = __ldg(s4 + 2);
-                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
-                w[8] = d.x; w[9] = d.y; w[10] = d.z; w[11] = d.w;
-            } else {
+        // 48-byte groups of the footprint: a thread's (up to three) groups are requested together, so that one round of
+        // DRAM latency covers the whole patch instead of one round per group
+        const int n_groups = nrows * ncol16;   // <= 88 * 7 = 616 <= 3 * 256
+        uint4 ld[3][3];
+        int gr[3], gc[3];
 #pragma unroll
-                for (int i = 0; i < 12; ++i) w[i] = 0u;
-            }
+        for (int u = 0; u < 3; ++u) {
+            const int g = t + 256 * u;
+            gr[u] = g / ncol16;
+            gc[u] = g - gr[u] * ncol16;
+            const int gy = y_lo + gr[u], gx = x_lo + 16 * gc[u];
+            const bool in = g < n_groups && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(in ? gy : 0) * W + (in ? gx : 0)) * 3);
+            ld[u][0] = in ? __ldg(s4) : make_uint4(0, 0, 0, 0);
+            ld[u][1] = in ? __ldg(s4 + 1) : make_uint4(0, 0, 0, 0);
+            ld[u][2] = in ? __ldg(s4 + 2) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            if (t + 256 * u >= n_groups) break;
+            const uint32_t w[12] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w,
+                                    ld[u][2].x, ld[u][2].y, ld[u][2].z, ld[u][2].w};
             uint32_t o[16];   // pixel k = bytes 3k..3k+2 -> (B,G,R,x); the top byte is never read
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1176,7 +1185,7 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
                 o[4 * k + 2] = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
                 o[4 * k + 3] = w[3 * k + 2] >> 8;
             }
-            uint4* d4 = reinterpret_cast<uint4*>(patch + r * kWpStride + 16 * c16);
+            uint4* d4 = reinterpret_cast<uint4*>(patch + gr[u] * kWpStride + 16 * gc[u]);
 #pragma unroll
             for (int k = 0; k < 4; ++k) d4[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
         }
