@@ -131,7 +131,7 @@ int pack_stem(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv
 // descriptor expects (16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)); k = ky*ky_stride + kx*kx_stride + ci,
 // every other k is zero.  BN scale and the 256/255 factor (inputs enter as v/256, the reference divides by 255) folded.
 int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv, const std::string& bn_prefix, int Cin, int k,
-                 int ky_stride, int kx_stride, void** d_w) {
+                 int ky_stride, int kx_stride, int bias_k, void** d_w) {
     const cvb_tensor* w = find(sd, n, conv + ".weight");
     if (!w || numel(w) != 64LL * Cin * k * k) return fail(ctx, -4, "missing/bad '%s.weight'", conv.c_str());
     Bn bn;
@@ -147,6 +147,19 @@ int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& c
                     const size_t byte = static_cast<size_t>(co) * 128 + (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2;
                     img[byte / 2] = __float2half_rn(static_cast<float>(v));
                 }
+    // The folded BatchNorm shift rides along as two more K columns (the kernels keep 1.0 in columns bias_k, bias_k + 1 of every
+    // im2col row): bias = hi + lo in fp16, exact to 2^-22 of its magnitude, accumulated in fp32 by the MMA itself.
+    for (int co = 0; co < 64; ++co) {
+        const float b = bn.shift[co];
+        const __half hi = __float2half_rn(b);
+        const __half lo = __float2half_rn(b - __half2float(hi));
+        const __half parts[2] = {hi, lo};
+        for (int j = 0; j < 2; ++j) {
+            const int kk = bias_k + j;
+            const size_t byte = static_cast<size_t>(co) * 128 + (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2;
+            img[byte / 2] = parts[j];
+        }
+    }
     __half* d = nullptr;
     if (dalloc(ctx, &d, img.size())) return -3;
     CK(cudaMemcpy(d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -633,7 +646,7 @@ int cvb_load_unet(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     const int B = ctx->max_batch;
     static const int width[5] = {64, 128, 256, 512, 1024};
     if (pack_stem(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, &ctx->stem_w, &ctx->stem_b)) return -4;
-    if (pack_stem_tc(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, 16, 4, &ctx->stem_wsw)) return -4;
+    if (pack_stem_tc(ctx, sd, n, "inc.double_conv.0", "inc.double_conv.1", 3, 3, 16, 4, 48, &ctx->stem_wsw)) return -4;
     if (tmap_act(&ctx->stem_omap, ctx->t0, 64, 256, 256, B, 64, 256 * 64, 65536LL * 64, 64, 2, 1))
         return fail(ctx, -6, "cuTensorMapEncodeTiled (stem output view) failed");
     ctx->unet_w.resize(21);
@@ -722,7 +735,7 @@ int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     if (ctx->resnet_loaded) return fail(ctx, -8, "classifier weights already loaded");
     const int S = ctx->max_batch * 64;
     if (pack_stem(ctx, sd, n, "conv1", "bn1", 1, 7, &ctx->rstem_w, &ctx->rstem_b)) return -4;
-    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, &ctx->rstem_wsw)) return -4;
+    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, 56, &ctx->rstem_wsw)) return -4;
     const cvb_tensor* fw = find(sd, n, "fc.weight");
     const cvb_tensor* fb = find(sd, n, "fc.bias");
     if (!fw || !fb || numel(fw) != 13 * 512 || numel(fb) != 13) return fail(ctx, -4, "missing/bad fc tensors");

@@ -141,6 +141,18 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
                  :
                  : "memory");
 }
+// two fp32 -> packed fp16 pair (lo in bits 0..15), round to nearest even; the .relu form clamps negative inputs to +0 in
+// the same instruction (ReLU and the monotone rounding commute, so this equals max(x, 0) followed by the conversion)
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 // Shared-memory matrix descriptor for a K-major tile whose rows are 128 B (64 x 16-bit) with the 128-byte swizzle

@@ -79,11 +79,12 @@ __device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float*
             f[2 * j + 1] += rf.y;
         }
     }
+    if (relu) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float a = relu ? fmaxf(f[2 * i], 0.f) : f[2 * i], b = relu ? fmaxf(f[2 * i + 1], 0.f) : f[2 * i + 1];
-        const __half2 h = __floats2half2_rn(a, b);
-        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int i = 0; i < 16; ++i) o[i] = pack_h2_relu(f[2 * i], f[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = pack_h2(f[2 * i], f[2 * i + 1]);
     }
 }
 

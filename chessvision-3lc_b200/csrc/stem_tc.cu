@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
 
     for (int i = tid; i < kBBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
     for (int i = tid; i < 2 * kRsInBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base + kRsOffIn)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kStages * 128; i += kRsThreads)   // K columns 56..63 (the padding chunk) stay zero for ever
-        *reinterpret_cast<uint4*>(base + kRsOffA + (i >> 7) * kABytes + sw128(i & 127, 7)) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kStages * 128; i += kRsThreads)   // the padding chunk (K columns 56..63) is written once: columns 56, 57 = 1.0
+        *reinterpret_cast<uint4*>(base + kRsOffA + (i >> 7) * kABytes + sw128(i & 127, 7)) = make_uint4(0x3C003C00u, 0, 0, 0);   // x (bias_hi, bias_lo) rows of B
     if (tid < 64) reinterpret_cast<float*>(base + kRsOffBias)[tid] = __ldg(bias + tid);
     Bars b;
     const uint32_t tmem_base = setup<12, 256, 2>(bars, tmem_slot, b, warp, lane);
@@ -183,7 +183,6 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
         // warpgroup g (warps 4-7 / 8-11) owns channels 32g .. 32g+31 of every conv pixel
         const int e = warp & 3, g = (warp - 4) >> 2, etid = (tid - 128) & 127;
         uint8_t* sH = base + kRsOffH;
-        const float4* b4 = reinterpret_cast<const float4*>(base + kRsOffBias) + 8 * g;
         int iter = 0;
         for (int sq = blockIdx.x; sq < n_squares; sq += gridDim.x) {
             for (int t = 0; t < 8; ++t, ++iter) {
@@ -198,11 +197,8 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
                 // conv pixel (y = 4t + e, x = lane): bias + ReLU -> fp16, then the horizontal half of the 3x3 max pool
                 uint32_t hv[16];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 bb = b4[i];
-                    hv[2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v[4 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * i + 1]) + bb.y, 0.f)));
-                    hv[2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v[4 * i + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * i + 3]) + bb.w, 0.f)));
-                }
+                for (int i = 0; i < 16; ++i)   // the bias is part of the accumulator (two K columns of ones x bias_hi, bias_lo)
+                    hv[i] = pack_h2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const uint32_t up = __shfl_up_sync(0xffffffffu, hv[i], 1);       // lane 0 keeps its own value
@@ -289,8 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
     const int n_units = n_images * 32;
 
     for (int i = tid; i < kBBytes / 16; i += kThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
-    for (int i = tid; i < kStages * 128 * 2; i += kThreads)   // K columns 48..63 stay zero
-        *reinterpret_cast<uint4*>(base + kUsOffA + (i >> 8) * kABytes + sw128((i >> 1) & 127, 6 + (i & 1))) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kStages * 128 * 2; i += kThreads)   // K columns 48..63 are written once: 48, 49 = 1.0 (x the bias rows of B), rest 0
+        *reinterpret_cast<uint4*>(base + kUsOffA + (i >> 8) * kABytes + sw128((i >> 1) & 127, 6 + (i & 1))) = make_uint4((i & 1) ? 0u : 0x3C003C00u, 0, 0, 0);
     if (tid < 64) reinterpret_cast<float*>(base + kUsOffBias)[tid] = __ldg(bias + tid);
     if (tid == 0) tma_prefetch_desc(&omap);
     Bars b;
@@ -365,7 +361,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
         // latency-bound, two tiles in flight hide it); four accumulators, one staging buffer per group.
         const int e = warp & 3, g = (warp - 4) >> 2, etid = (tid - 128) & 127;
         const int row = e * 32 + lane;
-        const float4* b4 = reinterpret_cast<const float4*>(base + kUsOffBias);
         uint8_t* dst = base + kUsOffOut + g * kABytes;
         int iter = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -384,12 +379,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_unet_stem_tc(const uint8_t* __r
                 mbar_arrive(b.tempty + 8 * acc);
                 uint32_t o[32];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float4 ba = b4[i], bb = b4[8 + i];
-                    o[2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[4 * i]) + ba.x, 0.f), fmaxf(__uint_as_float(v0[4 * i + 1]) + ba.y, 0.f)));
-                    o[2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v0[4 * i + 2]) + ba.z, 0.f), fmaxf(__uint_as_float(v0[4 * i + 3]) + ba.w, 0.f)));
-                    o[16 + 2 * i] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(v1[4 * i + 1]) + bb.y, 0.f)));
-                    o[16 + 2 * i + 1] = h2_bits(__floats2half2_rn(fmaxf(__uint_as_float(v1[4 * i + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v1[4 * i + 3]) + bb.w, 0.f)));
+                for (int i = 0; i < 16; ++i) {   // the bias is part of the accumulator (two K columns of ones x bias_hi, bias_lo)
+                    o[i] = pack_h2_relu(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+                    o[16 + i] = pack_h2_relu(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
                 }
                 if (etid == 0) bulk_wait_read<0>();   // this group's previous store has finished reading its buffer
                 named_bar(2 + g, 128);
