@@ -125,37 +125,62 @@ __global__ void __launch_bounds__(256) k_stem_wgrad(const float* __restrict__ x,
 }
 
 // ------------------------------------------------------------------------------------------------ batch-norm, forward
+// Column reductions over a [rows][C] fp16 matrix (C a multiple of 8, at most 1024), shared by the forward statistics, the
+// backward reduction and the bias gradients.  A thread owns 8 consecutive channels (one 16-byte load per row) and walks the
+// rows of its block four at a time, so four independent loads are in flight per thread; `256 / (C / 8)` rows are covered
+// per step by one block.  Partial sums meet in shared memory and leave as one double atomicAdd per channel and block.
+// NV = accumulators per channel (2: sum + second moment, 1: sum only).
+template <int NV>
+__device__ __forceinline__ void col_reduce_tail(float (&acc)[8 * NV], double* __restrict__ out0, double* __restrict__ out1, float* red,
+                                                int groups, int rpar, int g, int rl) {
+    // red[rl][g][8 * NV]
+#pragma unroll
+    for (int j = 0; j < 8 * NV; ++j) red[(rl * groups + g) * (8 * NV) + j] = acc[j];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < groups * 8 * NV; idx += 256) {
+        double t = 0.0;
+        for (int k = 0; k < rpar; ++k) t += static_cast<double>(red[k * groups * 8 * NV + idx]);
+        const int gg = idx / (8 * NV), j = idx - gg * (8 * NV);
+        const int c = gg * 8 + (j % 8);
+        atomicAdd((j < 8 ? out0 : out1) + c, t);
+    }
+}
+
 // Per-channel sum and sum of squares of z [rows][C] (fp16, dense).  Each block covers `rows_per_block` rows.
 __global__ void __launch_bounds__(256) k_bn_stats(const __half* __restrict__ z, double* __restrict__ sums, long long rows, int C,
                                                   int rows_per_block) {
-    const int pairs = C >> 1;
-    const int lanes = pairs < 256 ? pairs : 256;       // threads per row
-    const int rpar = 256 / lanes;                      // rows in flight
-    const int tl = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+    extern __shared__ float red[];
+    const int groups = C >> 3, per = groups < 256 ? groups : 256, rpar = 256 / per;
+    const int gl = threadIdx.x % per, rl = threadIdx.x / per;
     const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
     const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-    __shared__ float red[256][4];
-    for (int pb = 0; pb < pairs; pb += lanes) {
-        const int pair = pb + tl;
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (long long r = r0 + rl; r < r1; r += rpar) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(z + r * C + 2 * pair));
-            s0 += f.x; s1 += f.y;
-            q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
-        }
-        red[threadIdx.x][0] = s0; red[threadIdx.x][1] = s1; red[threadIdx.x][2] = q0; red[threadIdx.x][3] = q1;
-        __syncthreads();
-        if (rl == 0) {
-            double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-            for (int k = 0; k < rpar; ++k) {
-                const float* e = red[k * lanes + tl];
-                a0 += e[0]; a1 += e[1]; b0 += e[2]; b1 += e[3];
+    for (int gb = 0; gb < groups; gb += per) {
+        const int g = gb + gl;
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        const __half* col = z + 8 * g;
+        for (long long r = r0 + rl; r < r1; r += 4LL * rpar) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rpar;
+                v[u] = rr < r1 ? *reinterpret_cast<const uint4*>(col + rr * C) : make_uint4(0, 0, 0, 0);
             }
-            atomicAdd(sums + 2 * pair, a0);
-            atomicAdd(sums + 2 * pair + 1, a1);
-            atomicAdd(sums + C + 2 * pair, b0);
-            atomicAdd(sums + C + 2 * pair + 1, b1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                    acc[8 + 2 * j] = fmaf(f.x, f.x, acc[8 + 2 * j]);
+                    acc[8 + 2 * j + 1] = fmaf(f.y, f.y, acc[8 + 2 * j + 1]);
+                }
+            }
         }
+        col_reduce_tail<2>(acc, sums + 8 * gb, sums + C + 8 * gb, red, per, rpar, gl, rl);
         __syncthreads();
     }
 }
@@ -210,85 +235,111 @@ __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const __half* __restrict_
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        double* __restrict__ bsums, long long rows, int C, int rows_per_block) {
-    const int pairs = C >> 1;
-    const int lanes = pairs < 256 ? pairs : 256;
-    const int rpar = 256 / lanes;
-    const int tl = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+    extern __shared__ float red[];
+    const int groups = C >> 3, per = groups < 256 ? groups : 256, rpar = 256 / per;
+    const int gl = threadIdx.x % per, rl = threadIdx.x / per;
     const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
     const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-    __shared__ float red[256][4];
-    for (int pb = 0; pb < pairs; pb += lanes) {
-        const int pair = pb + tl, c = 2 * pair;
-        const float sc0 = scale[c], sc1 = scale[c + 1], sh0 = shift[c], sh1 = shift[c + 1];
-        const float m0 = mean[c], m1 = mean[c + 1], rs0 = rstd[c], rs1 = rstd[c + 1];
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        for (long long r = r0 + rl; r < r1; r += rpar) {
-            const float2 zf = __half22float2(*reinterpret_cast<const __half2*>(z + r * C + c));
-            const float2 df = __half22float2(*reinterpret_cast<const __half2*>(dy + r * C + c));
-            const float g0 = fmaf(zf.x, sc0, sh0) > 0.f ? df.x : 0.f;
-            const float g1 = fmaf(zf.y, sc1, sh1) > 0.f ? df.y : 0.f;
-            s0 += g0; s1 += g1;
-            q0 = fmaf(g0, (zf.x - m0) * rs0, q0);
-            q1 = fmaf(g1, (zf.y - m1) * rs1, q1);
+    for (int gb = 0; gb < groups; gb += per) {
+        const int g = gb + gl, c0 = 8 * g;
+        float sc[8], sh[8], mu[8], rs[8], acc[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = __ldg(scale + c0 + j);
+            sh[j] = __ldg(shift + c0 + j);
+            mu[j] = __ldg(mean + c0 + j);
+            rs[j] = __ldg(rstd + c0 + j);
+            acc[j] = acc[8 + j] = 0.f;
         }
-        red[threadIdx.x][0] = s0; red[threadIdx.x][1] = s1; red[threadIdx.x][2] = q0; red[threadIdx.x][3] = q1;
-        __syncthreads();
-        if (rl == 0) {
-            double a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-            for (int k = 0; k < rpar; ++k) {
-                const float* e = red[k * lanes + tl];
-                a0 += e[0]; a1 += e[1]; b0 += e[2]; b1 += e[3];
+        for (long long r = r0 + rl; r < r1; r += 2LL * rpar) {
+            uint4 zv[2], dv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rpar;
+                const bool in = rr < r1;
+                zv[u] = in ? *reinterpret_cast<const uint4*>(z + rr * C + c0) : make_uint4(0, 0, 0, 0);
+                dv[u] = in ? *reinterpret_cast<const uint4*>(dy + rr * C + c0) : make_uint4(0, 0, 0, 0);   // dy = 0: no contribution
             }
-            atomicAdd(bsums + c, a0);
-            atomicAdd(bsums + c + 1, a1);
-            atomicAdd(bsums + C + c, b0);
-            atomicAdd(bsums + C + c + 1, b1);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const __half2* zh = reinterpret_cast<const __half2*>(&zv[u]);
+                const __half2* dh = reinterpret_cast<const __half2*>(&dv[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 zf = __half22float2(zh[j]), df = __half22float2(dh[j]);
+                    const float g0 = fmaf(zf.x, sc[2 * j], sh[2 * j]) > 0.f ? df.x : 0.f;
+                    const float g1 = fmaf(zf.y, sc[2 * j + 1], sh[2 * j + 1]) > 0.f ? df.y : 0.f;
+                    acc[2 * j] += g0;
+                    acc[2 * j + 1] += g1;
+                    acc[8 + 2 * j] = fmaf(g0, (zf.x - mu[2 * j]) * rs[2 * j], acc[8 + 2 * j]);
+                    acc[8 + 2 * j + 1] = fmaf(g1, (zf.y - mu[2 * j + 1]) * rs[2 * j + 1], acc[8 + 2 * j + 1]);
+                }
+            }
         }
+        col_reduce_tail<2>(acc, bsums + 8 * gb, bsums + C + 8 * gb, red, per, rpar, gl, rl);
         __syncthreads();
     }
 }
 
 // dz = scale * (g - mean_rows(g) - xhat * mean_rows(g*xhat))  (fp16, dense);  block 0 also emits d_gamma, d_beta.
+// Same thread layout as the reductions: a thread keeps the per-channel constants of its 8 channels in registers and walks
+// the rows of its block.
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __half* __restrict__ dy, const __half* __restrict__ z,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
                                                       const double* __restrict__ bsums, __half* __restrict__ dz, float* __restrict__ g_gamma,
-                                                      float* __restrict__ g_beta, long long rows, int C, float inv_s) {
+                                                      float* __restrict__ g_beta, long long rows, int C, float inv_s, int rows_per_block) {
     if (blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += 256) {
             g_beta[c] += static_cast<float>(bsums[c] * inv_s);
             g_gamma[c] += static_cast<float>(bsums[C + c] * inv_s);
         }
     }
-    const int groups = C >> 3;
-    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (i >= rows * groups) return;
-    const long long r = i / groups;
-    const int c = static_cast<int>(i - r * groups) << 3;
-    const uint4 zv = *reinterpret_cast<const uint4*>(z + r * C + c);
-    const uint4 dv = *reinterpret_cast<const uint4*>(dy + r * C + c);
-    const __half2* zh = reinterpret_cast<const __half2*>(&zv);
-    const __half2* dh = reinterpret_cast<const __half2*>(&dv);
+    const int groups = C >> 3, per = groups < 256 ? groups : 256, rpar = 256 / per;
+    const int gl = threadIdx.x % per, rl = threadIdx.x / per;
+    const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+    const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
     const float inv_rows = 1.0f / static_cast<float>(rows);
-    float o[8];
+    for (int gb = 0; gb < groups; gb += per) {
+        const int c0 = 8 * (gb + gl);
+        float sc[8], sh[8], mu[8], rs[8], mg[8], mgx[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const float2 zf = __half22float2(zh[j]), df = __half22float2(dh[j]);
-        const float zz[2] = {zf.x, zf.y}, dd[2] = {df.x, df.y};
+        for (int j = 0; j < 8; ++j) {
+            sc[j] = __ldg(scale + c0 + j);
+            sh[j] = __ldg(shift + c0 + j);
+            mu[j] = __ldg(mean + c0 + j);
+            rs[j] = __ldg(rstd + c0 + j);
+            mg[j] = static_cast<float>(bsums[c0 + j]) * inv_rows;
+            mgx[j] = static_cast<float>(bsums[C + c0 + j]) * inv_rows;
+        }
+        for (long long r = r0 + rl; r < r1; r += 2LL * rpar) {
+            uint4 zv[2], dv[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int cc = c + 2 * j + e;
-            const float sc = __ldg(scale + cc), sh = __ldg(shift + cc);
-            const float g = fmaf(zz[e], sc, sh) > 0.f ? dd[e] : 0.f;
-            const float xh = (zz[e] - __ldg(mean + cc)) * __ldg(rstd + cc);
-            const float mg = static_cast<float>(bsums[cc]) * inv_rows, mgx = static_cast<float>(bsums[C + cc]) * inv_rows;
-            o[2 * j + e] = sc * (g - mg - xh * mgx);
+            for (int u = 0; u < 2; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rpar;
+                const bool in = rr < r1;
+                zv[u] = in ? *reinterpret_cast<const uint4*>(z + rr * C + c0) : make_uint4(0, 0, 0, 0);
+                dv[u] = in ? *reinterpret_cast<const uint4*>(dy + rr * C + c0) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rpar;
+                if (rr >= r1) break;
+                const __half2* zh = reinterpret_cast<const __half2*>(&zv[u]);
+                const __half2* dh = reinterpret_cast<const __half2*>(&dv[u]);
+                __half2 oh[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 zf = __half22float2(zh[j]), df = __half22float2(dh[j]);
+                    const float g0 = fmaf(zf.x, sc[2 * j], sh[2 * j]) > 0.f ? df.x : 0.f;
+                    const float g1 = fmaf(zf.y, sc[2 * j + 1], sh[2 * j + 1]) > 0.f ? df.y : 0.f;
+                    const float x0 = (zf.x - mu[2 * j]) * rs[2 * j], x1 = (zf.y - mu[2 * j + 1]) * rs[2 * j + 1];
+                    oh[j] = __floats2half2_rn(sc[2 * j] * (g0 - mg[2 * j] - x0 * mgx[2 * j]), sc[2 * j + 1] * (g1 - mg[2 * j + 1] - x1 * mgx[2 * j + 1]));
+                }
+                *reinterpret_cast<uint4*>(dz + rr * C + c0) = *reinterpret_cast<const uint4*>(oh);
+            }
         }
     }
-    __half2 oh[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(o[2 * j], o[2 * j + 1]);
-    *reinterpret_cast<uint4*>(dz + r * C + c) = *reinterpret_cast<const uint4*>(oh);
 }
 
 // ------------------------------------------------------------------------------------------------ max-pool backward + skip add
@@ -345,27 +396,39 @@ __global__ void __launch_bounds__(256) k_pool_bwd_add(const __half* __restrict__
 // out[c] += scale * sum_rows src[row*stride + off + c]
 __global__ void __launch_bounds__(256) k_colsum(const __half* __restrict__ src, long long rows, int C, int stride, int off,
                                                 float* __restrict__ out, float scale, int rows_per_block) {
-    const int pairs = C >> 1;
-    const int lanes = pairs < 256 ? pairs : 256;
-    const int rpar = 256 / lanes;
-    const int tl = threadIdx.x % lanes, rl = threadIdx.x / lanes;
+    extern __shared__ float red[];
+    const int groups = C >> 3, per = groups < 256 ? groups : 256, rpar = 256 / per;
+    const int gl = threadIdx.x % per, rl = threadIdx.x / per;
     const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
     const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-    __shared__ float red[256][2];
-    for (int pb = 0; pb < pairs; pb += lanes) {
-        const int pair = pb + tl;
-        float s0 = 0.f, s1 = 0.f;
-        for (long long r = r0 + rl; r < r1; r += rpar) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(src + r * stride + off + 2 * pair));
-            s0 += f.x; s1 += f.y;
+    for (int gb = 0; gb < groups; gb += per) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const __half* col = src + off + 8 * (gb + gl);
+        for (long long r = r0 + rl; r < r1; r += 4LL * rpar) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = r + static_cast<long long>(u) * rpar;
+                v[u] = rr < r1 ? *reinterpret_cast<const uint4*>(col + rr * stride) : make_uint4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    acc[2 * j] += f.x;
+                    acc[2 * j + 1] += f.y;
+                }
+            }
         }
-        red[threadIdx.x][0] = s0; red[threadIdx.x][1] = s1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(rl * per + gl) * 8 + j] = acc[j];
         __syncthreads();
-        if (rl == 0) {
-            float a0 = 0, a1 = 0;
-            for (int k = 0; k < rpar; ++k) { a0 += red[k * lanes + tl][0]; a1 += red[k * lanes + tl][1]; }
-            atomicAdd(out + 2 * pair, a0 * scale);
-            atomicAdd(out + 2 * pair + 1, a1 * scale);
+        for (int idx = threadIdx.x; idx < per * 8; idx += 256) {
+            float t = 0.f;
+            for (int k = 0; k < rpar; ++k) t += red[k * per * 8 + idx];
+            atomicAdd(out + 8 * gb + idx, t * scale);
         }
         __syncthreads();
     }
@@ -575,9 +638,18 @@ cudaError_t launch_stem_wgrad(const float* x, const __half* dz, float* gw, int N
     k_stem_wgrad<<<grid, 256, smem, s>>>(x, dz, gw, H, W, inv_s);
     return cudaGetLastError();
 }
+// rows per block of the column-reduction kernels: about four blocks per SM when the matrix is tall enough, never fewer rows
+// than one block covers in a single step of its row loop
+inline int reduce_rows_per_block(long long rows, int C, int unroll) {
+    const int groups = C >> 3, per = groups < 256 ? groups : 256, rpar = 256 / per;
+    long long rpb = (rows + 591) / 592;
+    const long long step = static_cast<long long>(unroll) * rpar;
+    rpb = ((rpb + step - 1) / step) * step;
+    return static_cast<int>(rpb < step ? step : rpb);
+}
 cudaError_t launch_bn_stats(const __half* z, double* sums, long long rows, int C, cudaStream_t s) {
-    const int rpb = 512;
-    k_bn_stats<<<blocks_for(rows, rpb), 256, 0, s>>>(z, sums, rows, C, rpb);
+    const int rpb = reduce_rows_per_block(rows, C, 4);
+    k_bn_stats<<<blocks_for(rows, rpb), 256, 256 * 16 * sizeof(float), s>>>(z, sums, rows, C, rpb);
     return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(const double* sums, const float* gamma, const float* beta, float* scale, float* shift, float* mean,
@@ -594,12 +666,11 @@ cudaError_t launch_bn_apply_relu(const __half* z, const float* scale, const floa
 }
 cudaError_t launch_bn_bwd(const __half* dy, const __half* z, const float* scale, const float* shift, const float* mean, const float* rstd,
                           double* bsums, __half* dz, float* g_gamma, float* g_beta, long long rows, int C, float inv_s, cudaStream_t s) {
-    const int rpb = 512;
-    k_bn_bwd_reduce<<<blocks_for(rows, rpb), 256, 0, s>>>(dy, z, scale, shift, mean, rstd, bsums, rows, C, rpb);
+    const int rpb = reduce_rows_per_block(rows, C, 2);
+    k_bn_bwd_reduce<<<blocks_for(rows, rpb), 256, 256 * 16 * sizeof(float), s>>>(dy, z, scale, shift, mean, rstd, bsums, rows, C, rpb);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_bn_bwd_apply<<<blocks_for(rows * (C / 8), 256), 256, 0, s>>>(dy, z, scale, shift, mean, rstd, bsums, dz, g_gamma, g_beta, rows, C,
-                                                                   inv_s);
+    k_bn_bwd_apply<<<blocks_for(rows, rpb), 256, 0, s>>>(dy, z, scale, shift, mean, rstd, bsums, dz, g_gamma, g_beta, rows, C, inv_s, rpb);
     return cudaGetLastError();
 }
 cudaError_t launch_pool_bwd_add(const __half* y, int y_stride, const __half* dskip, int ds_stride, const __half* dpool, __half* dy, int N,
@@ -609,8 +680,8 @@ cudaError_t launch_pool_bwd_add(const __half* y, int y_stride, const __half* dsk
     return cudaGetLastError();
 }
 cudaError_t launch_colsum(const __half* src, long long rows, int C, int stride, int off, float* out, float scale, cudaStream_t s) {
-    const int rpb = 1024;
-    k_colsum<<<blocks_for(rows, rpb), 256, 0, s>>>(src, rows, C, stride, off, out, scale, rpb);
+    const int rpb = reduce_rows_per_block(rows, C, 4);
+    k_colsum<<<blocks_for(rows, rpb), 256, 256 * 8 * sizeof(float), s>>>(src, rows, C, stride, off, out, scale, rpb);
     return cudaGetLastError();
 }
 cudaError_t launch_outc_fwd(const __half* y, const float* w, const float* b, float* logits, long long P, cudaStream_t s) {

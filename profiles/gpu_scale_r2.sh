@@ -8,7 +8,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 if [ "$N" = "1" ]; then TR="python"; fi
 timeout 600 $TR bench.py --gpus $N --steps 8 --warmup 3 --no-cpu-baseline --api-steps 1 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "pipeline N=$N exit $?"
 for B in 8 32; do
-  timeout 600 $TR bench.py --workload train --gpus $N --train-batch $B --steps 20 --warmup 3 > gpurun_out/train_n${N}_b$B.json 2> gpurun_out/train_n${N}_b$B.err; echo "train N=$N b=$B exit $?"
+  timeout 600 $TR bench.py --workload train --gpus $N --train-batch $B --steps $((B == 8 ? 300 : 120)) --warmup 5 > gpurun_out/train_n${N}_b$B.json 2> gpurun_out/train_n${N}_b$B.err; echo "train N=$N b=$B exit $?"
 done
 python - $N <<'PY'
 import json, sys
