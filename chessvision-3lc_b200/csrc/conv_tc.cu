@@ -26,12 +26,13 @@ namespace cvb {
 
 constexpr int kEpiConstBytes = 256 * 4 + 64 * 4;   // per-tile bias (<= 256 columns) + the 1x1 head weights
 
-template <int BLOCK_N>
+// PAIR = 1: the CTA pair form (cta_group::2, see common.cuh): a stage holds this CTA's 128 pixels of A and HALF of the weight tile
+template <int BLOCK_N, int PAIR = 0>
 struct ConvCfg {
     static constexpr int kABytes = 128 * 128;
-    static constexpr int kBBytes = BLOCK_N * 128;
+    static constexpr int kBBytes = BLOCK_N * 128 / (PAIR ? 2 : 1);
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4);
+    static constexpr int kStages = PAIR ? (BLOCK_N == 128 ? 8 : 6) : (BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4));
     static constexpr int kTmemCols = 2 * BLOCK_N;
     static constexpr int kOutBytes = 2 * 128 * 128;   // two staging buffers for the TMA tile store
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiConstBytes;
@@ -215,9 +216,9 @@ __device__ __forceinline__ void epilogue_consts(const ConvParams& p, int n_tile,
     named_bar_sync(1, 128);
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int PAIR = 0>
 __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BLOCK_N>;
+    using Cfg = ConvCfg<BLOCK_N, PAIR>;
     constexpr int S = Cfg::kStages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -234,6 +235,10 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // CTA pair: the even CTA of the cluster issues the MMAs for both; tile index and stride count clusters, not CTAs
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int sched0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int sched_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.b_map);
@@ -246,31 +251,39 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 128);
+            mbar_init(bar_tempty + 8 * i, PAIR ? 2 : 128);   // pair: one arrival per CTA (its epilogue warps sync first)
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    if (warp == 2) {
+        if constexpr (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), Cfg::kTmemCols);
+        else tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_launch();
     griddep_wait();   // everything above overlapped the previous kernel's tail (programmatic dependent launch)
 
+    // pair: a scheduled tile is two consecutive M tiles (this CTA takes 2 * pair + rank) x one N tile
     const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
-    const int total_tiles = m_tiles * p.n_tiles;
+    const int m_units = PAIR ? (m_tiles + 1) >> 1 : m_tiles;
+    const int total_tiles = m_units * p.n_tiles;
     const int k_steps = p.taps * p.c_chunks;
 
     if (warp == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        // transaction bytes of both CTAs are counted on the leader's barrier
+        const uint32_t full_sig = PAIR ? mapa_cluster(bar_full, 0) : bar_full;
+        for (int t = sched0; t < total_tiles; t += sched_step) {
             const int n_tile = t % p.n_tiles;
-            const int m_tile = t / p.n_tiles;
+            const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             const int w0 = (m_tile % p.tiles_w) * p.tw;
             const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.th;
-            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;
+            const int n0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tn;   // beyond the last image for the odd tile out: zero fill
             for (int tap = 0; tap < p.taps; ++tap) {
                 const CUtensorMap* amap = &p.a_map[p.tap_map[tap]];
                 const int hh = h0 + p.tap_dy[tap];
@@ -280,16 +293,23 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     if (elect_one()) {
                         const uint32_t a_dst = tiles_addr + stage * Cfg::kStageBytes;
                         const uint32_t b_dst = a_dst + Cfg::kABytes;
-                        mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
-                        tma_load_4d(a_dst, amap, bar_full + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
-                        tma_load_2d(b_dst, &p.b_map, bar_full + 8 * stage, (tap * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
+                        if constexpr (PAIR) {
+                            if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * Cfg::kStageBytes);
+                            tma_load_4d_pair(a_dst, amap, full_sig + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
+                            tma_load_2d_pair(b_dst, &p.b_map, full_sig + 8 * stage, (tap * p.c_chunks + kc) * 64,
+                                             n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * stage, Cfg::kStageBytes);
+                            tma_load_4d(a_dst, amap, bar_full + 8 * stage, p.a_c_off + kc * 64, ww, hh, n0);
+                            tma_load_2d(b_dst, &p.b_map, bar_full + 8 * stage, (tap * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
+                        }
                     }
                     __syncwarp();
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         // warp-uniform role loop, tcgen05 instructions predicated on one lane elected once; descriptor words are
         // base + stage * pitch (uniform registers), so a stage costs a handful of instructions besides its four MMAs
         const bool leader = elect_one();
@@ -299,7 +319,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+        for (int t = sched0; t < total_tiles; t += sched_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -312,11 +332,19 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
                     const uint32_t a_lo = a_lo0 + stage * (Cfg::kStageBytes >> 4);
                     const uint32_t b_lo = a_lo + (Cfg::kABytes >> 4);
                     // advance 16 elements (32 B) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-                    umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, kb != 0 ? 1u : 0u);
+                    if constexpr (PAIR) {
+                        umma_f16_pair(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int k = 1; k < 4; ++k) umma_f16(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, 1u);
-                    umma_commit(bar_empty + 8 * stage);
-                    if (kb == k_steps - 1) umma_commit(bar_tfull + 8 * acc);
+                        for (int k = 1; k < 4; ++k) umma_f16_pair(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, 1u);
+                        umma_commit_pair(bar_empty + 8 * stage);
+                        if (kb == k_steps - 1) umma_commit_pair(bar_tfull + 8 * acc);
+                    } else {
+                        umma_f16(d_tmem, desc_hi | a_lo, desc_hi | b_lo, idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) umma_f16(d_tmem, desc_hi | (a_lo + 2 * k), desc_hi | (b_lo + 2 * k), idesc, 1u);
+                        umma_commit(bar_empty + 8 * stage);
+                        if (kb == k_steps - 1) umma_commit(bar_tfull + 8 * acc);
+                    }
                 }
                 if (++stage == S) { stage = 0; phase ^= 1; }
             }
@@ -332,11 +360,12 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         int store_count = 0;
         float* s_outw = s_bias + 256;
         int iter = 0, cur_nt = -1;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
+        const uint32_t tempty_sig = PAIR ? mapa_cluster(bar_tempty, 0) : bar_tempty;
+        for (int t = sched0; t < total_tiles; t += sched_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int n_tile = t % p.n_tiles;
-            const int m_tile = t / p.n_tiles;
+            const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             if (n_tile != cur_nt) {
                 epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
                 cur_nt = n_tile;
@@ -354,16 +383,23 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n - rn, h - rh, w - rw, n, h, w, valid, n_tile, s_bias, s_outw, s_out,
                                         tiles_addr + S * Cfg::kStageBytes, store_count, threadIdx.x - 128, res0);
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
+            if constexpr (PAIR) {
+                named_bar_sync(1, 128);   // all four warps have read their lanes of the accumulator
+                if (threadIdx.x == 128) mbar_arrive_cluster(tempty_sig + 8 * acc);
+            } else {
+                mbar_arrive(bar_tempty + 8 * acc);
+            }
         }
         if (threadIdx.x == 128) bulk_wait_all();   // the staged tiles must have left shared memory before the CTA exits
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();   // neither CTA leaves while the other may still signal its barriers or read its B half
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -373,21 +409,22 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
 // up4.up, unet_parts.py:16-21,53).  Unfused, the 128-channel tensor is written to HBM (4 MB per board) only to be read back by a
 // transposed-convolution kernel that is bound by exactly that traffic.  Here the epilogue converts the accumulator tile
 // (128 pixels x 128 channels) to fp16 in the 128-byte-swizzled K-major layout -- the same bytes the unfused kernel would have
-// stored -- and leaves it in shared memory as the A operand of a second MMA against the resident transposed-conv weights
+// stored -- and leaves it in shared memory as the A operand of a second MMA against the transposed-conv weights
 // (N = 4 taps x 64 channels = 256, K = 128); its accumulator (256 TMEM columns next to the two 128-column main accumulators)
 // is drained, biased and scattered by the same four epilogue warps through the strided output views of EPI_CONVT.  The
 // results equal those of the two separate kernels (same fp16 rounding point, same accumulation order as conv3x3_vr_kernel).
-//   warp 0 TMA producer (transposed-conv weights once, then the main pipeline), warp 1 MMA issue (main K loop of tile i; the
-//   second MMA of tile i-1 is slipped in as soon as its A operand is ready), warp 2 TMEM, warps 4-11 epilogue (two groups).
+//   warp 0 TMA producer, warp 1 MMA issue (main K loop of tile i, then the second MMA of tile i-1, whose A operand the
+//   epilogue produced meanwhile), warp 2 TMEM, warps 4-11 epilogue (two groups).
 // ---------------------------------------------------------------------------------------------------------------------
 struct FusedCfg {
     // main loop in the vertical-reuse form (see conv3x3_vr_kernel): one activation box {64 ch, 8 w, 18 h} per (K chunk, dx)
-    // serves the three vertical taps, whose weight tiles flow through a ring of their own
-    static constexpr int kAStages = 2, kBStages = 5;
+    // serves the three vertical taps, whose weight tiles flow through a ring of their own.  The transposed-conv weights
+    // (64 KB) travel through the same ring as four more 16 KB tiles per output tile instead of staying resident: that buys
+    // a ring of nine tiles (2,300 tensor-clocks of look-ahead, what the TMA pipeline needs to cover the L2 latency).
+    static constexpr int kAStages = 2, kBStages = 9;
     static constexpr int kABytes = 18 * 1024, kBBytes = 128 * 128;
-    static constexpr int kW2Bytes = 2 * 256 * 128;   // two K blocks of [256 rows][64 k]
     static constexpr int kA2Bytes = 2 * 128 * 128;   // two K blocks of [128 pixels][64 k]; reused as the two store staging buffers
-    static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kW2Bytes + kA2Bytes + 1024 + 256 + (128 + 64) * 4;
+    static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kA2Bytes + 1024 + 256 + (128 + 64) * 4;
 };
 constexpr int kFusedThreads = 384;   // TMA, MMA, TMEM, idle warp + two epilogue groups of four warps
 
@@ -399,9 +436,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
     const uint32_t a_addr = (raw_addr + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (a_addr - raw_addr);
     const uint32_t b_addr = a_addr + SA * Cfg::kABytes;
-    const uint32_t w2_addr = b_addr + SB * Cfg::kBBytes;
-    const uint32_t a2_addr = w2_addr + Cfg::kW2Bytes;
-    uint8_t* a2_ptr = base_ptr + SA * Cfg::kABytes + SB * Cfg::kBBytes + Cfg::kW2Bytes;
+    const uint32_t a2_addr = b_addr + SB * Cfg::kBBytes;
+    uint8_t* a2_ptr = base_ptr + SA * Cfg::kABytes + SB * Cfg::kBBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(a2_ptr + Cfg::kA2Bytes);
     const uint32_t bar_afull = smem_u32(bars);
     const uint32_t bar_aempty = bar_afull + 8 * SA;
@@ -409,9 +445,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
     const uint32_t bar_bempty = bar_bfull + 8 * SB;
     const uint32_t bar_tfull = bar_bempty + 8 * SB;
     const uint32_t bar_tempty = bar_tfull + 16;
-    const uint32_t bar_w2 = bar_tfull + 32;
-    const uint32_t bar_a2full = bar_tfull + 40;
-    const uint32_t bar_d2full = bar_tfull + 48;
+    const uint32_t bar_a2full = bar_tfull + 32;
+    const uint32_t bar_d2full = bar_tfull + 40;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 8);
     float* s_bias = reinterpret_cast<float*>(a2_ptr + Cfg::kA2Bytes + 256);
     float* s_bias2 = s_bias + 128;
@@ -436,7 +471,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 256);
         }
-        mbar_init(bar_w2, 1);
         mbar_init(bar_a2full, 256);
         mbar_init(bar_d2full, 1);
         mbar_fence_init();
@@ -452,21 +486,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t d2_tmem = tmem_base + 256;
     griddep_launch();
-    if (warp != 0) griddep_wait();
+    griddep_wait();
 
     const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;   // one N tile: all 128 channels of a pixel in this CTA
+    // Order of the weight ring, identical in the producer and the MMA warp: the 18 tiles of the main loop of tile i, then
+    // (from the second tile on) the four transposed-conv tiles (row half rh, K block kb) for the second MMA of tile i-1;
+    // after the last tile four more for its own second MMA.
 
     if (warp == 0) {
-        if (elect_one()) {
-            mbar_expect_tx(bar_w2, Cfg::kW2Bytes);
-            tma_load_2d(w2_addr, &p.b2_map, bar_w2, 0, 0);
-            tma_load_2d(w2_addr + 256 * 128, &p.b2_map, bar_w2, 64, 0);
-        }
-        __syncwarp();
-        griddep_wait();
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        auto load_w2 = [&]() {
+            for (int j = 0; j < 4; ++j) {   // j = rh * 2 + kb: rows [128 rh, 128 rh + 128) of the 256 (dy,dx,co) rows, K block kb
+                mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_bfull + 8 * bs, Cfg::kBBytes);
+                    tma_load_2d(b_addr + bs * Cfg::kBBytes, &p.b2_map, bar_bfull + 8 * bs, (j & 1) * 64, (j >> 1) * 128);
+                }
+                __syncwarp();
+                if (++bs == SB) { bs = 0; bph ^= 1; }
+            }
+        };
+        int iter = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int w0 = (t % p.tiles_w) * 8;
             const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
             const int n0 = t / (p.tiles_w * p.tiles_h);
@@ -490,46 +532,47 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
                     }
                 }
             }
+            if (iter > 0) load_w2();
         }
+        if (iter > 0) load_w2();
     } else if (warp == 1) {
         const bool leader = elect_one();
         const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
         const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_sw128(0));
         const uint32_t a_lo0 = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
         const uint32_t b_lo0 = desc_lo0 + ((b_addr & 0x3FFFFu) >> 4);
-        const uint32_t w2_lo = desc_lo0 + ((w2_addr & 0x3FFFFu) >> 4);
         const uint32_t a2_lo = desc_lo0 + ((a2_addr & 0x3FFFFu) >> 4);
-        const uint32_t idesc = umma_idesc_f16(128, 128, 0), idesc2 = umma_idesc_f16(128, 256, 0);
-        // second MMA of one tile: D2[128 px][(dy,dx,co)] = A2[128 px][128 ci] . W2^T, two K blocks of four K = 16 steps
-        auto mma2 = [&]() {
-            tc_fence_after();
-            if (leader) {
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(d2_tmem, desc_hi | (a2_lo + kb * (128 * 128 >> 4) + 2 * k), desc_hi | (w2_lo + kb * (256 * 128 >> 4) + 2 * k), idesc2,
-                                 (kb | k) != 0 ? 1u : 0u);
-                umma_commit(bar_d2full);
-            }
-            __syncwarp();
-        };
-        mbar_wait(bar_w2, 0);
+        const uint32_t idesc = umma_idesc_f16(128, 128, 0);
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
+        // second MMA of tile j: D2[128 px][(dy,dx,co)] = A2[128 px][128 ci] . W2^T as four N = 128 pieces (row half rh of W2,
+        // K block kb), each fed by one tile of the weight ring
+        auto mma2 = [&](int j) {
+            mbar_wait(bar_a2full, j & 1);
+            for (int q = 0; q < 4; ++q) {
+                mbar_wait(bar_bfull + 8 * bs, bph);
+                tc_fence_after();
+                if (leader) {
+                    const int rh = q >> 1, kb = q & 1;
+                    const uint32_t b_lo = b_lo0 + bs * (Cfg::kBBytes >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(d2_tmem + rh * 128, desc_hi | (a2_lo + kb * (128 * 128 >> 4) + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(bar_bempty + 8 * bs);
+                    if (q == 3) umma_commit(bar_d2full);
+                }
+                __syncwarp();
+                if (++bs == SB) { bs = 0; bph ^= 1; }
+            }
+        };
         int iter = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
             const int acc = iter & 1;
             mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 128;
-            bool pending2 = iter > 0;   // the previous tile's second MMA: issued as soon as the epilogue has produced its A operand
             for (int kc = 0; kc < p.c_chunks; ++kc) {
                 for (int dxi = 0; dxi < 3; ++dxi) {
-                    if (pending2 && mbar_try_wait(bar_a2full, (iter - 1) & 1)) {
-                        mma2();
-                        pending2 = false;
-                    }
                     mbar_wait(bar_afull + 8 * as, aph);
                     const uint32_t a_lo = a_lo0 + as * (Cfg::kABytes >> 4);
                     for (int dy = 0; dy < 3; ++dy) {
@@ -553,15 +596,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
                     if (++as == SA) { as = 0; aph ^= 1; }
                 }
             }
-            if (pending2) {
-                mbar_wait(bar_a2full, (iter - 1) & 1);
-                mma2();
-            }
+            if (iter > 0) mma2(iter - 1);
         }
-        if (iter > 0) {
-            mbar_wait(bar_a2full, (iter - 1) & 1);
-            mma2();
-        }
+        if (iter > 0) mma2(iter - 1);
     } else if (warp >= 4) {
         // Two epilogue groups (warps 4-7 / 8-11) work on the SAME tile: group g converts channels 64g .. 64g+63 of the
         // accumulator into K block g of the A operand, then drains taps q = 2g, 2g+1 of the transposed-conv accumulator and
@@ -1214,6 +1251,8 @@ int tmap_act(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv, in
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+static int g_pair_clusters = 0;   // see configure_pair
+
 int tmap_weights(CUtensorMap* m, const void* base, int K_total, int rows, int block_n) {
     if (tmap_init()) return -1;
     cuuint64_t dims[2] = {(cuuint64_t)K_total, (cuuint64_t)rows};
@@ -1306,7 +1345,18 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
         rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
         if (rc) return rc;
     }
-    return 0;
+    return conv_try_pair(L, w, K, rows);
+}
+
+// Generic kernel, BLOCK_N = 128 / 256, plain or transposed-conv store: run it as CTA pairs (each CTA then loads half of the
+// weight tile: the weight view gets a box of BLOCK_N / 2 rows).
+int conv_try_pair(ConvLaunch& L, const __half* w, int K, int rows) {
+    if (g_pair_clusters <= 0 || L.variant != 0 || (L.block_n != 128 && L.block_n != 256)) return 0;
+    if (L.epilogue != EPI_STORE && L.epilogue != EPI_CONVT) return 0;
+    const char* only = getenv("CVB_PAIR_MIN_N");   // A/B: pair form only from this BLOCK_N up
+    if (only && L.block_n < atoi(only)) return 0;
+    L.pair = 1;
+    return tmap_weights(&L.p.b_map, w, K, rows, L.block_n / 2);
 }
 
 // "Convolution" with kernel 2x2, stride 2, no padding over an NHWC buffer [Nmax, 2*Ho, 2*Wo, in_c_stride]: tap q = (dy,dx)
@@ -1346,7 +1396,7 @@ int conv_build_k2s2(ConvLaunch& L, const __half* in, int Nmax, int Ho, int Wo, i
     L.epilogue = EPI_STORE;
     L.n_max = Nmax;
     L.pdl = 1;
-    return 0;
+    return conv_try_pair(L, w, K, rows);
 }
 
 // Output side of a launch: NHWC fp16 buffer with `out_c_stride` channels per pixel, first output channel `out_c_off`.
@@ -1381,8 +1431,8 @@ int conv_set_fused_convt(ConvLaunch& L, const __half* w2, const float* bias2, in
     ConvParams& p = L.p;
     if (L.epilogue != EPI_FUSED_CONVT || L.block_n != 128 || p.n_tiles != 1 || cout2 != 64) return -5;
     if (tmap_init()) return -1;
-    // transposed-conv weights [4 * cout2 rows][128 k]: box {64 k, 256 rows}
-    int rc = tmap_weights(&p.b2_map, w2, 128, 4 * cout2, 256);
+    // transposed-conv weights [4 * cout2 rows][128 k]: box {64 k, 128 rows} (one tile of the weight ring)
+    int rc = tmap_weights(&p.b2_map, w2, 128, 4 * cout2, 128);
     if (rc) return rc;
     p.bias2 = bias2;
     p.convt_cout = cout2;
@@ -1409,6 +1459,32 @@ static cudaError_t configure_one() {
     return cudaFuncSetAttribute(conv_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::kSmemBytes);
 }
 
+// CTA-pair form of the generic kernel: clusters of two CTAs.  g_pair_clusters = how many such clusters the device runs at once
+// (74 on a B200: one per TPC); 0 turns the pair form off (CVB_NO_PAIR=1, or a device that cannot co-schedule them).
+template <int BN, int EPI>
+static cudaError_t configure_pair() {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, 1>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = ConvCfg<BN, 1>::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, EPI, 1>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (n < g_pair_clusters) g_pair_clusters = n;
+    return cudaSuccess;
+}
+
+int conv_pair_clusters() { return g_pair_clusters; }
+
 cudaError_t conv_configure() {
     cudaError_t e;
     if ((e = configure_one<64, EPI_STORE>()) != cudaSuccess) return e;
@@ -1419,6 +1495,17 @@ cudaError_t conv_configure() {
     if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::kSmemBytes)) != cudaSuccess) return e;
+    {
+        const char* off = getenv("CVB_NO_PAIR");
+        g_pair_clusters = off && off[0] == '1' ? 0 : 1 << 20;
+        if (g_pair_clusters) {
+            if ((e = configure_pair<256, EPI_STORE>()) != cudaSuccess) return e;
+            if ((e = configure_pair<128, EPI_STORE>()) != cudaSuccess) return e;
+            if ((e = configure_pair<256, EPI_CONVT>()) != cudaSuccess) return e;
+            if ((e = configure_pair<128, EPI_CONVT>()) != cudaSuccess) return e;
+            if (g_pair_clusters == 1 << 20) g_pair_clusters = 0;
+        }
+    }
     if ((e = configure_vr<64, EPI_STORE, true>()) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_STORE, false>()) != cudaSuccess) return e;
     if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
@@ -1436,6 +1523,10 @@ cudaError_t conv_configure() {
 template <int BN, int EPI>
 static cudaError_t launch_one(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
     return launch_k(conv_tc_kernel<BN, EPI>, grid, 256, ConvCfg<BN>::kSmemBytes, s, pdl, p);
+}
+template <int BN, int EPI>
+static cudaError_t launch_pair(const ConvParams& p, int clusters, cudaStream_t s, bool pdl) {
+    return launch_kc(conv_tc_kernel<BN, EPI, 1>, 2 * clusters, 256, ConvCfg<BN, 1>::kSmemBytes, s, pdl, 2, p);
 }
 
 // Decide whether the vertical-reuse kernel applies to this launch and size its pipeline.
@@ -1538,6 +1629,20 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
         if (L.epilogue == EPI_OUTC) return launch_vr<64, EPI_OUTC, true>(p, grid, stream, pdl);
         if (L.block_n == 64) return ws ? launch_vr<64, EPI_STORE, true>(p, grid, stream, pdl) : launch_vr<64, EPI_STORE, false>(p, grid, stream, pdl);
         return ws ? launch_vr<128, EPI_STORE, true>(p, grid, stream, pdl) : launch_vr<128, EPI_STORE, false>(p, grid, stream, pdl);
+    }
+    if (L.pair) {
+        if (g_pair_clusters <= 0) return cudaErrorInvalidValue;
+        const long long m_tiles = 1LL * p.tiles_n * p.tiles_h * p.tiles_w;
+        const long long units = ((m_tiles + 1) / 2) * p.n_tiles;
+        const int clusters = (int)(units < g_pair_clusters ? units : g_pair_clusters);
+        p.idesc = umma_idesc_f16(256, L.block_n, 0);
+        switch (L.epilogue * 1000 + L.block_n) {
+            case EPI_STORE * 1000 + 128: return launch_pair<128, EPI_STORE>(p, clusters, stream, pdl);
+            case EPI_STORE * 1000 + 256: return launch_pair<256, EPI_STORE>(p, clusters, stream, pdl);
+            case EPI_CONVT * 1000 + 128: return launch_pair<128, EPI_CONVT>(p, clusters, stream, pdl);
+            case EPI_CONVT * 1000 + 256: return launch_pair<256, EPI_CONVT>(p, clusters, stream, pdl);
+            default: return cudaErrorInvalidValue;
+        }
     }
     switch (L.epilogue * 1000 + L.block_n) {
         case EPI_STORE * 1000 + 64: return launch_one<64, EPI_STORE>(p, grid, stream, pdl);

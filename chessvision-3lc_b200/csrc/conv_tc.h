@@ -20,7 +20,7 @@ struct alignas(64) ConvParams {
     CUtensorMap a_map[4];  // activation views, 4-D {C, W, H, N}, box {64, tw, th, tn}, 128-byte swizzle
     CUtensorMap b_map;     // packed weights, 2-D {K_total, Cout_total}, box {64, BLOCK_N}, 128-byte swizzle
     CUtensorMap o_map[4];  // output views for the TMA tile store, box {64, tw, th, tn}; convT: one strided view per (dy,dx)
-    CUtensorMap b2_map;    // EPI_FUSED_CONVT: packed transposed-conv weights, 2-D {Cin2 = 128, 4 * Cout2 = 256}, box {64, 256}
+    CUtensorMap b2_map;    // EPI_FUSED_CONVT: packed transposed-conv weights, 2-D {Cin2 = 128, 4 * Cout2 = 256}, box {64, 128}
     const float* bias2;    // EPI_FUSED_CONVT: [Cout2] bias of the transposed convolution
     int out_bufs;          // 16 KB staging buffers for the store (0: EPI_OUTC, 1 or 2 otherwise)
     // K loop: taps x (Cin/64) chunks.  Tap t reads view tap_map[t] at spatial offset (tap_dy[t], tap_dx[t]).
@@ -65,6 +65,7 @@ struct ConvLaunch {
     int epilogue;  // ConvEpilogue
     int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel, 2 row-streaming 3x3 kernel (Cout = 64)
     int n_max;     // images the activation / output views were built for
+    int pair;      // generic kernel as CTA pairs (cta_group::2, M = 256 per MMA; each CTA loads half of the weight tile)
     int pdl;       // launch with programmatic stream serialization (resident weights are then requested before the previous
                    // kernel has finished: only for launches whose weights no kernel in the stream writes, i.e. inference)
 };
@@ -82,6 +83,10 @@ int tmap_act_vr(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int Nv,
 bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin);
 // Row-streaming 3x3 kernel (Cout = 64, W % 128 == 0): views with boxes {64, 128, 1, 1} and {64, 130, 1, 1}.
 bool conv_try_rs(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin);
+// Generic kernel with BLOCK_N = 128 / 256: switch the launch to the CTA-pair form when the device runs clusters of two
+// (conv_configure decides; CVB_NO_PAIR=1 turns it off).  Returns 0 or a tensor-map error.
+int conv_try_pair(ConvLaunch& L, const __half* w, int K, int rows);
+int conv_pair_clusters();
 
 // Host-side construction of a launch (api.cu / train.cu).  Return 0, -5 (shape not supported) or a tensor-map error.
 int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int in_c_stride, int in_c_off, int Cin, const __half* w,

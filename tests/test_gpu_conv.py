@@ -51,6 +51,13 @@ CASES = [
     (64, 16, 16, 64, 64, 3, 1, True, True),      # one board of squares, residual (BasicBlock conv2)
     (203, 16, 16, 64, 64, 3, 1, True, False),    # ragged: 203 = 25 * 8 + 3 squares
     (1500, 16, 16, 64, 64, 3, 1, False, True),   # more strips than SMs
+    # generic kernel as CTA pairs (cta_group::2, BLOCK_N 128 / 256): many units per cluster (ring and both accumulators wrap),
+    # an odd number of M tiles (the last pair's second CTA computes a tile beyond the batch), two N tiles, residual
+    (37, 32, 32, 512, 512, 3, 1, True, False),
+    (41, 8, 8, 256, 256, 3, 1, True, True),
+    (300, 4, 4, 256, 512, 3, 1, True, True),
+    (75, 8, 8, 128, 128, 3, 1, False, True),
+    (21, 16, 16, 128, 256, 3, 2, True, False),
 ]
 
 
