@@ -131,7 +131,7 @@ int pack_stem(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv
 // descriptor expects (16-byte chunk j of row r at r*128 + ((j ^ (r & 7)) << 4)); k = ky*ky_stride + kx*kx_stride + ci,
 // every other k is zero.  BN scale and the 256/255 factor (inputs enter as v/256, the reference divides by 255) folded.
 int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& conv, const std::string& bn_prefix, int Cin, int k,
-                 int ky_stride, int kx_stride, int bias_k, void** d_w) {
+                 int ky_stride, int kx_stride, int bias_k, void** d_w, int neg_k = -1) {
     const cvb_tensor* w = find(sd, n, conv + ".weight");
     if (!w || numel(w) != 64LL * Cin * k * k) return fail(ctx, -4, "missing/bad '%s.weight'", conv.c_str());
     Bn bn;
@@ -160,6 +160,11 @@ int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& c
             img[byte / 2] = parts[j];
         }
     }
+    // K column neg_k: -30000 for every channel.  An im2col row with 1.0 there (a max-pool window position outside the conv
+    // image) loses every maximum it takes part in (k_resnet_stem_tc).
+    if (neg_k >= 0)
+        for (int co = 0; co < 64; ++co)
+            img[(static_cast<size_t>(co) * 128 + (((neg_k >> 3) ^ (co & 7)) << 4) + (neg_k & 7) * 2) / 2] = __float2half_rn(-30000.f);
     __half* d = nullptr;
     if (dalloc(ctx, &d, img.size())) return -3;
     CK(cudaMemcpy(d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -735,7 +740,7 @@ int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     if (ctx->resnet_loaded) return fail(ctx, -8, "classifier weights already loaded");
     const int S = ctx->max_batch * 64;
     if (pack_stem(ctx, sd, n, "conv1", "bn1", 1, 7, &ctx->rstem_w, &ctx->rstem_b)) return -4;
-    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, 56, &ctx->rstem_wsw)) return -4;
+    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, 56, &ctx->rstem_wsw, 58)) return -4;
     const cvb_tensor* fw = find(sd, n, "fc.weight");
     const cvb_tensor* fb = find(sd, n, "fc.bias");
     if (!fw || !fb || numel(fw) != 13 * 512 || numel(fb) != 13) return fail(ctx, -4, "missing/bad fc tensors");

@@ -33,7 +33,8 @@ struct ConvCfg {
     static constexpr int kBBytes = BLOCK_N * 128 / (PAIR ? 2 : 1);
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = PAIR ? (BLOCK_N == 128 ? 8 : 6) : (BLOCK_N == 64 ? 8 : (BLOCK_N == 128 ? 6 : 4));
-    static constexpr int kTmemCols = 2 * BLOCK_N;
+    static constexpr int kAcc = PAIR && BLOCK_N <= 128 ? 4 : 2;   // accumulator ring (see conv3x3_vr_kernel for the four-deep pair form)
+    static constexpr int kTmemCols = kAcc * BLOCK_N;
     static constexpr int kOutBytes = 2 * 128 * 128;   // two staging buffers for the TMA tile store
     static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*alignment slack*/ + 256 /*barriers*/ + kEpiConstBytes;
 };
@@ -230,8 +231,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * S;
     const uint32_t bar_tfull = bar_full + 16 * S;
-    const uint32_t bar_tempty = bar_tfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    constexpr int kAcc = Cfg::kAcc;
+    const uint32_t bar_tempty = bar_tfull + 8 * kAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2 * kAcc);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kAcc; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, PAIR ? 2 : 128);   // pair: one arrival per CTA (its epilogue warps sync first)
         }
@@ -320,8 +322,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         uint32_t phase = 0;
         int iter = 0;
         for (int t = sched0; t < total_tiles; t += sched_step, ++iter) {
-            const int acc = iter & 1;
-            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int acc = iter % kAcc;
+            const uint32_t acc_phase = (iter / kAcc) & 1;
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -362,8 +364,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         int iter = 0, cur_nt = -1;
         const uint32_t tempty_sig = PAIR ? mapa_cluster(bar_tempty, 0) : bar_tempty;
         for (int t = sched0; t < total_tiles; t += sched_step, ++iter) {
-            const int acc = iter & 1;
-            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int acc = iter % kAcc;
+            const uint32_t acc_phase = (iter / kAcc) & 1;
             const int n_tile = t % p.n_tiles;
             const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             if (n_tile != cur_nt) {
@@ -692,12 +694,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
 // (9*Cin*Cout*2 B) fit beside the pipeline they are loaded once per CTA and stay in shared memory.
 // L2->SM bytes per 128x64 output tile, Cin = 64:  generic 216 KB  ->  54 KB.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI, bool W_STAT>
+template <int BLOCK_N, int EPI, bool W_STAT, int PAIR = 0>
 __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constant__ ConvParams p) {
+    // PAIR = 1: CTA pair (cta_group::2, see conv_tc_kernel): two 16 x 8 output tiles per MMA, each CTA holds half of every
+    // weight tile (BLOCK_N / 2 rows), so an MMA reads 4 KB of A + 2 KB of B per SM instead of 4 + 4 (the N = 128 layers are
+    // bound by exactly that shared-memory operand bandwidth) and twice the input channels fit as resident weights.
     constexpr int kABytes = 18 * 1024;
-    constexpr int kBBytes = BLOCK_N * 128;
+    constexpr int kBBytes = BLOCK_N * 128 / (PAIR ? 2 : 1);
     constexpr int kStageBytes = kABytes + (W_STAT ? 0 : 3 * kBBytes);
-    constexpr int kTmemCols = 2 * BLOCK_N;
+    // accumulator ring: four deep for a pair (the cross-CTA hand-over of an accumulator -- multicast commit, remote arrive --
+    // takes longer than a short K loop; two buffers left the MMA waiting on tiles with Cin = 64)
+    constexpr int kAcc = PAIR && BLOCK_N <= 128 ? 4 : 2;
+    constexpr int kTmemCols = kAcc * BLOCK_N;
     const int S = p.vr_stages;
 
     extern __shared__ uint8_t smem_raw[];
@@ -712,12 +720,15 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * S;
     const uint32_t bar_tfull = bar_full + 16 * S;
-    const uint32_t bar_tempty = bar_tfull + 16;
-    const uint32_t bar_w = bar_tfull + 32;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+    const uint32_t bar_tempty = bar_tfull + 8 * kAcc;
+    const uint32_t bar_w = bar_tfull + 16 * kAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 2 * kAcc + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int sched0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int sched_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.b_map);
@@ -728,35 +739,50 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kAcc; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 128);
+            mbar_init(bar_tempty + 8 * i, PAIR ? 2 : 128);
         }
         mbar_init(bar_w, 1);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == 2) {
+        if constexpr (PAIR) tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
+        else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     griddep_launch();
     if (warp != 0) griddep_wait();   // warp 0 first requests the resident weights (no kernel writes them)
 
-    const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int m_units = PAIR ? (m_tiles + 1) >> 1 : m_tiles;
+    const int total_tiles = m_units * p.n_tiles;
 
     if (warp == 0) {
+        // pair: the bytes of both CTAs are counted on the leader's barriers (its MMA warp is the only consumer)
+        const uint32_t full_sig = PAIR ? mapa_cluster(bar_full, 0) : bar_full;
         if (W_STAT && elect_one()) {
-            mbar_expect_tx(bar_w, w_bytes);
-            for (int i = 0; i < 9 * p.c_chunks; ++i) tma_load_2d(base_addr + i * kBBytes, &p.b_map, bar_w, i * 64, 0);
+            if constexpr (PAIR) {
+                const uint32_t w_sig = mapa_cluster(bar_w, 0);
+                if (rank == 0) mbar_expect_tx(bar_w, 2 * w_bytes);
+                for (int i = 0; i < 9 * p.c_chunks; ++i)
+                    tma_load_2d_pair(base_addr + i * kBBytes, &p.b_map, w_sig, i * 64, static_cast<int>(rank) * (BLOCK_N / 2));
+            } else {
+                mbar_expect_tx(bar_w, w_bytes);
+                for (int i = 0; i < 9 * p.c_chunks; ++i) tma_load_2d(base_addr + i * kBBytes, &p.b_map, bar_w, i * 64, 0);
+            }
         }
         __syncwarp();
         griddep_wait();
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = sched0; t < total_tiles; t += sched_step) {
             const int n_tile = t % p.n_tiles;
-            const int m_tile = t / p.n_tiles;
+            const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             const int w0 = (m_tile % p.tiles_w) * 8;
             const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * 16;
             const int n0 = m_tile / (p.tiles_w * p.tiles_h);
@@ -765,13 +791,25 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     if (elect_one()) {
                         const uint32_t a_dst = stages_addr + stage * kStageBytes;
-                        mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
-                        tma_load_4d(a_dst, &p.a_map[0], bar_full + 8 * stage, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
-                        if (!W_STAT) {
+                        if constexpr (PAIR) {
+                            if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * kStageBytes);
+                            tma_load_4d_pair(a_dst, &p.a_map[0], full_sig + 8 * stage, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
+                            if (!W_STAT) {
 #pragma unroll
-                            for (int dy = 0; dy < 3; ++dy)
-                                tma_load_2d(a_dst + kABytes + dy * kBBytes, &p.b_map, bar_full + 8 * stage,
-                                            ((dy * 3 + dxi) * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
+                                for (int dy = 0; dy < 3; ++dy)
+                                    tma_load_2d_pair(a_dst + kABytes + dy * kBBytes, &p.b_map, full_sig + 8 * stage,
+                                                     ((dy * 3 + dxi) * p.c_chunks + kc) * 64,
+                                                     n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+                            }
+                        } else {
+                            mbar_expect_tx(bar_full + 8 * stage, kStageBytes);
+                            tma_load_4d(a_dst, &p.a_map[0], bar_full + 8 * stage, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
+                            if (!W_STAT) {
+#pragma unroll
+                                for (int dy = 0; dy < 3; ++dy)
+                                    tma_load_2d(a_dst + kABytes + dy * kBBytes, &p.b_map, bar_full + 8 * stage,
+                                                ((dy * 3 + dxi) * p.c_chunks + kc) * 64, n_tile * BLOCK_N);
+                            }
                         }
                     }
                     __syncwarp();
@@ -779,7 +817,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 && rank == 0) {
         const bool leader = elect_one();   // warp-uniform loop, tcgen05 instructions predicated on one lane (see conv_tc_kernel)
         if (W_STAT) {
             mbar_wait(bar_w, 0);
@@ -795,9 +833,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         int iter = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-            const int acc = iter & 1;
-            const uint32_t acc_phase = (iter >> 1) & 1;
+        for (int t = sched0; t < total_tiles; t += sched_step, ++iter) {
+            const int acc = iter % kAcc;
+            const uint32_t acc_phase = (iter / kAcc) & 1;
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -811,12 +849,22 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_f16(d_tmem, desc_hi | (a_lo + dy * 64 + 2 * k), desc_hi | (b_lo + dy * b_step + 2 * k), idesc,
-                                         (kc | dxi | dy | k) != 0 ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                if constexpr (PAIR)
+                                    umma_f16_pair(d_tmem, desc_hi | (a_lo + dy * 64 + 2 * k), desc_hi | (b_lo + dy * b_step + 2 * k), idesc,
+                                                  (kc | dxi | dy | k) != 0 ? 1u : 0u);
+                                else
+                                    umma_f16(d_tmem, desc_hi | (a_lo + dy * 64 + 2 * k), desc_hi | (b_lo + dy * b_step + 2 * k), idesc,
+                                             (kc | dxi | dy | k) != 0 ? 1u : 0u);
+                            }
                         }
-                        umma_commit(bar_empty + 8 * stage);
-                        if (kc == p.c_chunks - 1 && dxi == 2) umma_commit(bar_tfull + 8 * acc);
+                        if constexpr (PAIR) {
+                            umma_commit_pair(bar_empty + 8 * stage);
+                            if (kc == p.c_chunks - 1 && dxi == 2) umma_commit_pair(bar_tfull + 8 * acc);
+                        } else {
+                            umma_commit(bar_empty + 8 * stage);
+                            if (kc == p.c_chunks - 1 && dxi == 2) umma_commit(bar_tfull + 8 * acc);
+                        }
                     }
                     if (++stage == S) { stage = 0; phase ^= 1; }
                 }
@@ -831,11 +879,12 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
         int store_count = 0;
         float* s_outw = s_bias + 256;
         int iter = 0, cur_nt = -1;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++iter) {
-            const int acc = iter & 1;
-            const uint32_t acc_phase = (iter >> 1) & 1;
+        const uint32_t tempty_sig = PAIR ? mapa_cluster(bar_tempty, 0) : bar_tempty;
+        for (int t = sched0; t < total_tiles; t += sched_step, ++iter) {
+            const int acc = iter % kAcc;
+            const uint32_t acc_phase = (iter / kAcc) & 1;
             const int n_tile = t % p.n_tiles;
-            const int m_tile = t / p.n_tiles;
+            const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             if (n_tile != cur_nt) {
                 epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
                 cur_nt = n_tile;
@@ -852,16 +901,23 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n, h - rh, w - rw, n, h, w, n < p.N, n_tile, s_bias, s_outw, s_out,
                                         stages_addr + S * kStageBytes, store_count, threadIdx.x - 128, res0);
             tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * acc);
+            if constexpr (PAIR) {
+                named_bar_sync(1, 128);
+                if (threadIdx.x == 128) mbar_arrive_cluster(tempty_sig + 8 * acc);
+            } else {
+                mbar_arrive(bar_tempty + 8 * acc);
+            }
         }
         if (threadIdx.x == 128) bulk_wait_all();
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -1343,6 +1399,7 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
         if (rc) return rc;
     } else if (use_vr && conv_try_vr(L, ksize, stride, Ho, Wo, Cin)) {
         rc = tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);
+        if (!rc && L.pair) rc = tmap_weights(&p.b_map, w, K, rows, L.block_n / 2);
         if (rc) return rc;
     }
     return conv_try_pair(L, w, K, rows);
@@ -1353,8 +1410,13 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
 int conv_try_pair(ConvLaunch& L, const __half* w, int K, int rows) {
     if (g_pair_clusters <= 0 || L.variant != 0 || (L.block_n != 128 && L.block_n != 256)) return 0;
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_CONVT) return 0;
-    const char* only = getenv("CVB_PAIR_MIN_N");   // A/B: pair form only from this BLOCK_N up
-    if (only && L.block_n < atoi(only)) return 0;
+    // Measured (profiles/README.md, round 2): the pair form wins 7-14 % on N = 256 tiles with long K loops and loses on short
+    // ones (1x1 downsamples, transposed convs with Cin <= 512: the epilogue is the bottleneck there and two CTAs in lock step
+    // wait for the slower of the two) and on N = 128 tiles.  CVB_PAIR_MIN_N / CVB_PAIR_MIN_K override the thresholds (A/B runs).
+    const char* min_n = getenv("CVB_PAIR_MIN_N");
+    const char* min_k = getenv("CVB_PAIR_MIN_K");
+    if (L.block_n < (min_n ? atoi(min_n) : 256)) return 0;
+    if (L.p.taps * L.p.c_chunks < (min_k ? atoi(min_k) : 16)) return 0;
     L.pair = 1;
     return tmap_weights(&L.p.b_map, w, K, rows, L.block_n / 2);
 }
@@ -1511,6 +1573,8 @@ cudaError_t conv_configure() {
     if ((e = configure_vr<128, EPI_STORE, true>()) != cudaSuccess) return e;
     if ((e = configure_vr<128, EPI_STORE, false>()) != cudaSuccess) return e;
     if ((e = configure_vr<64, EPI_OUTC, true>()) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
@@ -1535,7 +1599,12 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     if (ksize != 3 || stride != 1 || Ho % 16 || Wo % 8) return false;
     if (L.block_n != 64 && L.block_n != 128) return false;
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
-    const int b_bytes = L.block_n * 128;
+    // N = 128 with a plain store: CTA pairs (half of each weight tile per CTA); CVB_NO_PAIR_VR=1 keeps the single-CTA form
+    const char* no_pair = getenv("CVB_NO_PAIR_VR");
+    const char* min_cc = getenv("CVB_PAIR_VR_MIN_CC");   // A/B: pair form only from this many 64-channel input chunks up
+    const bool pair = g_pair_clusters > 0 && L.block_n == 128 && L.epilogue == EPI_STORE && !(no_pair && no_pair[0] == '1') &&
+                      Cin / 64 >= (min_cc ? atoi(min_cc) : 2);
+    const int b_bytes = L.block_n * 128 / (pair ? 2 : 1);
     const int w_bytes = 9 * (Cin / 64) * b_bytes;
     const int out_bytes = L.epilogue == EPI_OUTC ? 0 : kOutBufBytes;
     const int budget = kVrMaxSmem - 1024 - 256 - kEpiConstBytes - out_bytes;
@@ -1553,6 +1622,7 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     p.tiles_w = Wo / 8;
     p.tiles_h = Ho / 16;
     L.variant = 1;
+    L.pair = pair ? 1 : 0;
     return true;
 }
 
@@ -1595,6 +1665,10 @@ template <int BN, int EPI, bool WS>
 static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
     return launch_k(conv3x3_vr_kernel<BN, EPI, WS>, grid, 256, p.smem_bytes, s, pdl, p);
 }
+template <bool WS>
+static cudaError_t launch_vr_pair(const ConvParams& p, int clusters, cudaStream_t s, bool pdl) {
+    return launch_kc(conv3x3_vr_kernel<128, EPI_STORE, WS, 1>, 2 * clusters, 256, p.smem_bytes, s, pdl, 2, p);
+}
 
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream) {
     ConvParams& p = L.p;
@@ -1623,6 +1697,13 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
             else e = launch_k(conv3x3_rs_kernel<EPI_STORE, 1, false>, grid, kRsThreads, p.smem_bytes, stream, pdl, p);
         }
         return e;
+    }
+    if (L.variant == 1 && L.pair) {
+        if (g_pair_clusters <= 0 || L.block_n != 128 || L.epilogue != EPI_STORE) return cudaErrorInvalidValue;
+        const long long units = ((1LL * p.tiles_n * p.tiles_h * p.tiles_w + 1) / 2) * p.n_tiles;
+        const int clusters = (int)(units < g_pair_clusters ? units : g_pair_clusters);
+        p.idesc = umma_idesc_f16(256, L.block_n, 0);
+        return p.w_stationary ? launch_vr_pair<true>(p, clusters, stream, pdl) : launch_vr_pair<false>(p, clusters, stream, pdl);
     }
     if (L.variant == 1) {
         const bool ws = p.w_stationary != 0;

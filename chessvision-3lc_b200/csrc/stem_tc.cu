@@ -22,7 +22,7 @@ namespace cvb {
 namespace {
 
 constexpr int kThreads = 416;      // UNet stem: 4 producer + 2 x 4 epilogue (alternate tiles) + 1 MMA warps
-constexpr int kRsThreads = 416;    // ResNet stem: 4 producer + 8 epilogue + 1 MMA warps
+constexpr int kRsThreads = 544;    // ResNet stem: 2 x 4 producer + 8 epilogue + 1 MMA warps
 constexpr int kStages = 4;
 constexpr int kABytes = 128 * 128;   // 128 im2col rows x 64 fp16
 constexpr int kBBytes = 64 * 128;    // 64 output channels x 64 fp16
@@ -89,44 +89,83 @@ __device__ __forceinline__ void mma_tile(uint32_t a_addr, uint32_t b_addr, uint3
 }
 
 // =====================================================================================================================
-// ResNet-18 stem
+// ResNet-18 stem.  The 3x3 / stride-2 max-pool is folded into the GEMM's row order: an M tile is 8 x 16 POOLED pixels (half a
+// square) and is multiplied nine times, once per window position (dy, dx), with the im2col rows of conv pixel
+// (2py + dy - 1, 2px + dx - 1).  The nine accumulators of a pooled pixel then sit in the SAME TMEM lane, so the pool is a
+// per-thread running maximum (3-input FMNMX3) over accumulator blocks: no shuffles, no shared-memory row ring, no named
+// barriers, and ReLU + the fp16 conversion are applied once per pooled pixel instead of once per conv pixel (max commutes
+// with the monotone conversion, so the bytes equal pool(relu(conv))).
+// The im2col rows never touch shared memory: the producer thread of row p writes its 64 fp16 (32 registers) straight into
+// tensor memory (tcgen05.st) and the MMA takes its A operand from there; only the 8 KB weight tile is read from shared
+// memory, so the N = 64 MMAs run at the tensor rate instead of the shared-memory operand rate (52 instead of 32 clocks each
+// for an A operand in shared memory, and writing + reading 16 KB per tile kept the first version of this kernel bound by
+// shared-memory bandwidth).
+// A window position outside the 32 x 32 conv image (dy = 0 at py = 0, dx = 0 at px = 0) must lose the maximum: its im2col row
+// is zero except for a 1.0 in K column 58, whose weight row holds -30000 for every channel.
+// Pipeline: a "batch" is the three tiles dy = 0..2 of one dx (their im2col chunks overlap: chunk ky of tile dy is row 2dy + ky
+// of an 11-row column strip, loaded once).  TMEM: two sets of three 64-column accumulators (columns 0..383) and a ring of
+// four A tiles of 32 columns (384..511).
 // =====================================================================================================================
 constexpr int kRsInHalfs = 70 * 72;                      // staged square: s_in[r][c] = px(r-3, c-3) / 256
 constexpr int kRsInBytes = ((kRsInHalfs * 2 + 1023) / 1024) * 1024;
-constexpr int kRsOffA = kBBytes;
-constexpr int kRsOffIn = kRsOffA + kStages * kABytes;
-constexpr int kRsOffH = kRsOffIn + 2 * kRsInBytes;       // ring of 16 horizontally pooled conv rows [16 px][64 ch]
-constexpr int kRsOffBias = kRsOffH + 16 * 2048;
-constexpr int kRsOffBars = kRsOffBias + 256;
+constexpr int kRsASlots = 4;
+constexpr int kRsOffIn = kBBytes;                        // 2 buffers x 2 copies (the second one word to the left)
+constexpr int kRsOffBars = kRsOffIn + 4 * kRsInBytes;
 constexpr int kRsSmem = kRsOffBars + 256 + 1024;
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t* __restrict__ board, const uint4* __restrict__ wsw,
-                                                               const float* __restrict__ bias, __half* __restrict__ out,
-                                                               int n_squares) {
+                                                               __half* __restrict__ out, int n_squares) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
     uint8_t* base = smem_raw + (base_addr - raw_addr);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + kRsOffBars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kRsASlots, bar_tfull = bar_empty + 8 * kRsASlots,
+                   bar_tempty = bar_tfull + 16;
 
     for (int i = tid; i < kBBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
-    for (int i = tid; i < 2 * kRsInBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base + kRsOffIn)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < kStages * 128; i += kRsThreads)   // the padding chunk (K columns 56..63) is written once: columns 56, 57 = 1.0
-        *reinterpret_cast<uint4*>(base + kRsOffA + (i >> 7) * kABytes + sw128(i & 127, 7)) = make_uint4(0x3C003C00u, 0, 0, 0);   // x (bias_hi, bias_lo) rows of B
-    if (tid < 64) reinterpret_cast<float*>(base + kRsOffBias)[tid] = __ldg(bias + tid);
-    Bars b;
-    const uint32_t tmem_base = setup<12, 256, 2>(bars, tmem_slot, b, warp, lane);
+    for (int i = tid; i < 4 * kRsInBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base + kRsOffIn)[i] = make_uint4(0, 0, 0, 0);
+    if (warp == 16) {
+        if (lane == 0) {
+            for (int i = 0; i < kRsASlots; ++i) {
+                mbar_init(bar_full + 8 * i, 128);
+                mbar_init(bar_empty + 8 * i, 1);
+            }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(bar_tfull + 8 * i, 1);
+                mbar_init(bar_tempty + 8 * i, 256);
+            }
+            mbar_fence_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_slot), 512);
+    }
+    fence_proxy_async();   // the weight tile written with ordinary stores is read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_a = tmem_base + 384;
     griddep_launch();
     griddep_wait();   // weights, zero padding, barriers and TMEM were set up under the previous kernel's tail
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ------------------------------------------------------------------------------------------------ producers
-        const int p = tid;                 // im2col row of every tile; also (row, half) of the staged square
-        const int row = p >> 1, half = p & 1;
-        int stage = 0, buf = 0;
-        uint32_t phase = 0;
+        // Two groups of four warps (a warp writes the TMEM lane quadrant warp % 4) take alternate tiles: the chain
+        // wait for the slot -> tcgen05.st -> wait::st -> arrive is latency-bound, two of them in flight keep the MMA fed.
+        const int pg = warp >> 2;
+        const int p = tid & 127;           // M row of every tile = TMEM lane = pooled pixel (p >> 4, p & 15) of the half square;
+        const int row = p >> 1, half = p & 1;   // also (row, half) of the staged square (group 0 stages it)
+        const uint32_t a_lane = tmem_a + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        int tile = 0, buf = 0;             // running tile index: slot = tile % 4, taken by group tile % 2
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
         auto fetch = [&](int sq) {
             const int n = sq >> 6, q = sq & 63;
@@ -136,10 +175,14 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
             r1 = __ldg(src + 1);
         };
         int sq = blockIdx.x;
-        if (sq < n_squares) fetch(sq);
+        if (pg == 0 && sq < n_squares) fetch(sq);
         for (; sq < n_squares; sq += gridDim.x) {
-            // 32 pixels of one row -> fp16/256, written at element offset 3 (the 7x7 window of output x starts at 2x-3)
-            __half* in = reinterpret_cast<__half*>(base + kRsOffIn + buf * kRsInBytes);
+            // 32 pixels of one row -> fp16/256, written at element offset 3 (the 7x7 window of conv column x starts at 2x-3);
+            // copy 1 holds the same words one position to the left, so that every 4-word window starts on an 8-byte boundary
+            // in one of the two copies
+            uint32_t* in0 = reinterpret_cast<uint32_t*>(base + kRsOffIn + (2 * buf) * kRsInBytes);
+            uint32_t* in1 = reinterpret_cast<uint32_t*>(base + kRsOffIn + (2 * buf + 1) * kRsInBytes);
+          if (pg == 0) {
             const uint32_t wsrc[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             __half2 h[16];   // h[k] = (x_2k, x_2k+1)
 #pragma unroll
@@ -150,111 +193,137 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
             // words of the staged row hold (x_odd, x_even): shift the pair stream by one pixel
             const uint32_t last = h2_bits(h[15]) >> 16;                                  // x_31
             const uint32_t left = __shfl_up_sync(0xffffffffu, last, 1);                  // x_31 of the left half-row
-            uint32_t* dst = reinterpret_cast<uint32_t*>(in) + (row + 3) * 36 + 1 + 16 * half;
+            const int w0 = (row + 3) * 36 + 1 + 16 * half;
             uint32_t prev = half ? left : 0u;
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
                 const uint32_t cur = h2_bits(h[k]);
-                dst[k] = prev | (cur << 16);
+                const uint32_t v = prev | (cur << 16);
+                in0[w0 + k] = v;
+                in1[w0 + k - 1] = v;
                 prev = cur >> 16;
             }
-            if (half) dst[16] = prev;                                                    // (x_63, 0)
+            if (half) {                                                                  // (x_63, 0)
+                in0[w0 + 16] = prev;
+                in1[w0 + 15] = prev;
+            }
             const int nsq = sq + gridDim.x;
             if (nsq < n_squares) fetch(nsq);
-            named_bar(1, 128);
-            const int x = p & 31, yq = p >> 5;
-            for (int t = 0; t < 8; ++t) {
-                mbar_wait(b.empty + 8 * stage, phase ^ 1);
-                uint8_t* a = base + kRsOffA + stage * kABytes;
-                const uint32_t* src = reinterpret_cast<const uint32_t*>(in) + (2 * (4 * t + yq)) * 36 + x;
+          }
+            named_bar(1, 256);
+            const int px = p & 15;
+            for (int T = 0; T < 2; ++T) {
+                const int py = 8 * T + (p >> 4);
+                for (int dx = 0; dx < 3; ++dx) {
+                    // column strip of conv column cx = 2px + dx - 1: words cx .. cx+3 of staged rows 4py - 2 + j, j = 0..10
+                    const int cx = 2 * px + dx - 1;
+                    const bool x_ok = cx >= 0;
+                    const uint32_t* src = ((cx & 1) ? in1 + (cx - 1) : in0 + cx) + (4 * py - 2) * 36;
+                    uint32_t R[44];
 #pragma unroll
-                for (int ky = 0; ky < 7; ++ky) {
-                    const uint32_t* s = src + ky * 36;
-                    *reinterpret_cast<uint4*>(a + sw128(p, ky)) = make_uint4(s[0], s[1], s[2], s[3]);
+                    for (int j = 0; j < 11; ++j) {
+                        if (x_ok && (j >= 2 || py > 0)) {
+                            const uint2 a = *reinterpret_cast<const uint2*>(src + j * 36);
+                            const uint2 c = *reinterpret_cast<const uint2*>(src + j * 36 + 2);
+                            R[4 * j] = a.x; R[4 * j + 1] = a.y; R[4 * j + 2] = c.x; R[4 * j + 3] = c.y;
+                        } else {
+                            R[4 * j] = R[4 * j + 1] = R[4 * j + 2] = R[4 * j + 3] = 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy, ++tile) {
+                        if ((tile & 1) != pg) continue;
+                        const int slot = tile & 3;
+                        const uint32_t phase = (tile >> 2) & 1;
+                        const bool ok = x_ok && (dy > 0 || py > 0);
+                        uint32_t v[32];
+#pragma unroll
+                        for (int i = 0; i < 28; ++i) v[i] = (dy > 0 || py > 0) ? R[8 * dy + i] : 0u;
+                        // K columns 56, 57 = 1.0 (x the two bias rows of B) for a conv pixel, column 58 = 1.0 (x -30000) outside the image
+                        v[28] = ok ? 0x3C003C00u : 0u;
+                        v[29] = ok ? 0u : 0x00003C00u;
+                        v[30] = v[31] = 0u;
+                        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+                        tc_fence_after();
+                        tmem_st_32x32(a_lane + 32 * slot, v);
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(bar_full + 8 * slot);
+                    }
                 }
-                fence_proxy_async();
-                mbar_arrive(b.full + 8 * stage);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             buf ^= 1;
         }
-    } else if (warp < 12) {
+    } else if (warp < 16) {
         // ------------------------------------------------------------------------------------------------ epilogue
-        // warpgroup g (warps 4-7 / 8-11) owns channels 32g .. 32g+31 of every conv pixel
-        const int e = warp & 3, g = (warp - 4) >> 2, etid = (tid - 128) & 127;
-        uint8_t* sH = base + kRsOffH;
-        int iter = 0;
+        // warpgroup g (warps 8-11 / 12-15) owns channels 32g .. 32g+31; thread <-> TMEM lane <-> pooled pixel of the half square
+        const int e = warp & 3, g = (warp - 8) >> 2;
+        const int prow = e * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(e * 32) << 16) + g * 32;
+        int batch = 0;
         for (int sq = blockIdx.x; sq < n_squares; sq += gridDim.x) {
-            for (int t = 0; t < 8; ++t, ++iter) {
-                const int acc = iter & 1;
-                mbar_wait(b.tfull + 8 * acc, (iter >> 1) & 1);
-                tc_fence_after();
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + acc * 64 + g * 32, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(b.tempty + 8 * acc);
-                // conv pixel (y = 4t + e, x = lane): bias + ReLU -> fp16, then the horizontal half of the 3x3 max pool
-                uint32_t hv[16];
+            for (int T = 0; T < 2; ++T) {
+                float run[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i)   // the bias is part of the accumulator (two K columns of ones x bias_hi, bias_lo)
-                    hv[i] = pack_h2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                for (int dx = 0; dx < 3; ++dx, ++batch) {
+                    const int bb = batch & 1;
+                    mbar_wait(bar_tfull + 8 * bb, (batch >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32(lane_addr + bb * 192, v0);
+                    tmem_ld_32x32(lane_addr + bb * 192 + 64, v1);
+                    tmem_ld_wait();
+                    float t[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, hv[i], 1);       // lane 0 keeps its own value
-                    const uint32_t dn = __shfl_down_sync(0xffffffffu, hv[i], 1);
-                    hv[i] = h2_bits(__hmax2(bits_h2(hv[i]), __hmax2(bits_h2(up), bits_h2(dn))));
-                }
-                if ((lane & 1) == 0) {
-                    const int px = lane >> 1;
-                    uint8_t* dst = sH + ((iter * 4 + e) & 15) * 2048 + px * 128;
+                    for (int i = 0; i < 32; ++i) t[i] = fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i]));
+                    tmem_ld_32x32(lane_addr + bb * 192 + 128, v0);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8 * bb);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4*>(dst + (((4 * g + c) ^ (px & 7)) << 4)) = make_uint4(hv[4 * c], hv[4 * c + 1], hv[4 * c + 2], hv[4 * c + 3]);
+                    for (int i = 0; i < 32; ++i)
+                        run[i] = dx == 0 ? fmaxf(t[i], __uint_as_float(v0[i])) : fmax3(run[i], t[i], __uint_as_float(v0[i]));
                 }
-                named_bar(2 + g, 128);
-                // vertical half: pooled rows 2t (conv rows 4t-1..4t+1) and 2t+1 (conv rows 4t+1..4t+3); one 16-byte item per thread
-                {
-                    const int k = etid >> 6, px = (etid >> 2) & 15, c = 4 * g + (etid & 3);
-                    const int first = k ? 1 : (t == 0 ? 0 : -1);
-                    uint4 m = make_uint4(0, 0, 0, 0);   // activations are >= 0, so 0 is the identity of max
-                    for (int dy = first; dy <= (k ? 3 : 1); ++dy) {
-                        const uint4 r = *reinterpret_cast<const uint4*>(sH + ((iter * 4 + dy) & 15) * 2048 + px * 128 + ((c ^ (px & 7)) << 4));
-                        m.x = h2_bits(__hmax2(bits_h2(m.x), bits_h2(r.x)));
-                        m.y = h2_bits(__hmax2(bits_h2(m.y), bits_h2(r.y)));
-                        m.z = h2_bits(__hmax2(bits_h2(m.z), bits_h2(r.z)));
-                        m.w = h2_bits(__hmax2(bits_h2(m.w), bits_h2(r.w)));
-                    }
-                    *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(sq) * 16 + 2 * t + k) * 16 + px) * 64 + c * 8) = m;
-                }
+                uint32_t o[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[i] = pack_h2_relu(run[2 * i], run[2 * i + 1]);   // the bias is part of the accumulator
+                __half* dst = out + ((static_cast<size_t>(sq) * 16 + 8 * T + (prow >> 4)) * 16 + (prow & 15)) * 64 + 32 * g;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
             }
         }
     } else {
         // ------------------------------------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_f16(128, 64, 0);
-        int stage = 0, iter = 0;
+        const uint64_t b_desc = umma_desc_sw128(base_addr);
+        const bool leader = elect_one();
+        int slot = 0, batch = 0;
         uint32_t phase = 0;
         for (int sq = blockIdx.x; sq < n_squares; sq += gridDim.x) {
-            for (int t = 0; t < 8; ++t, ++iter) {
-                const int acc = iter & 1;
-                mbar_wait(b.tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
-                mbar_wait(b.full + 8 * stage, phase);
-                tc_fence_after();
-                if (elect_one()) {
-                    mma_tile(base_addr + kRsOffA + stage * kABytes, base_addr, tmem_base + acc * 64, idesc);
-                    umma_commit(b.empty + 8 * stage);
-                    umma_commit(b.tfull + 8 * acc);
+            for (int b6 = 0; b6 < 6; ++b6, ++batch) {
+                const int bb = batch & 1;
+                mbar_wait(bar_tempty + 8 * bb, ((batch >> 1) & 1) ^ 1);
+                for (int dy = 0; dy < 3; ++dy) {
+                    mbar_wait(bar_full + 8 * slot, phase);
+                    tc_fence_after();
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16_ts(tmem_base + bb * 192 + dy * 64, tmem_a + 32 * slot + 8 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
+                        umma_commit(bar_empty + 8 * slot);
+                        if (dy == 2) umma_commit(bar_tfull + 8 * bb);
+                    }
+                    __syncwarp();
+                    if (++slot == kRsASlots) { slot = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == 16) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 128);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -438,7 +507,8 @@ cudaError_t launch_resnet_stem_tc(const uint8_t* board, const void* wsw, const f
                                   cudaStream_t s) {
     const int n_squares = n_boards * 64;
     if (n_squares == 0) return cudaSuccess;
-    return launch_k(k_resnet_stem_tc, n_squares < sm_count ? n_squares : sm_count, kRsThreads, kRsSmem, s, true, board, static_cast<const uint4*>(wsw), bias,
+    (void)bias;   // part of the packed weight tile (two K columns of ones x bias_hi, bias_lo)
+    return launch_k(k_resnet_stem_tc, n_squares < sm_count ? n_squares : sm_count, kRsThreads, kRsSmem, s, true, board, static_cast<const uint4*>(wsw),
                     out, n_squares);
 }
 

@@ -1,0 +1,22 @@
+#!/usr/bin/env bash
+# CTA-pair form of the generic conv kernel + weight-ring form of conv_convt_kernel: parity, A/B bench, per-layer launch list.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_conv.py tests/test_gpu_nets.py tests/test_gpu_pipeline.py -m gpu -q -x > gpurun_out/pytest_j.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/pytest_j.log | cut -c1-300
+run() {
+  env $2 timeout 300 python bench.py --no-cpu-baseline --steps 6 --warmup 3 --api-steps 1 > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err; echo "bench $1 exit $?"
+  python - "$1" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(f"gpurun_out/bench_{sys.argv[1]}.json").read().strip().splitlines()[-1])
+    print(sys.argv[1], round(d["value"], 1), "boards/s  e2e", round(d["e2e"]["value"], 1), "ms/step", round(d["ms_per_step"], 2),
+          {k: round(v, 2) for k, v in d["stage_ms_per_step"].items()}, d["clocks"])
+except Exception as e:
+    print(sys.argv[1], "failed", e)
+PY
+}
+run j_default CVB_X=1
+run j_novrpair CVB_NO_PAIR_VR=1
+run j_default2 CVB_X=2
+P="python profiles/prof_step.py --boards 148 --warmup 1 --steps 1"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_j.csv $P > gpurun_out/prof_launches_j.log 2>&1
+python profiles/launch_table.py gpurun_out/launches_j.csv gpurun_out/launches_pair.csv 148 2>&1 | tail -60 | cut -c1-200
