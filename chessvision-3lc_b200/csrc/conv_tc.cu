@@ -702,9 +702,9 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     constexpr int kABytes = 18 * 1024;
     constexpr int kBBytes = BLOCK_N * 128 / (PAIR ? 2 : 1);
     constexpr int kStageBytes = kABytes + (W_STAT ? 0 : 3 * kBBytes);
-    // accumulator ring: four deep for a pair (the cross-CTA hand-over of an accumulator -- multicast commit, remote arrive --
-    // takes longer than a short K loop; two buffers left the MMA waiting on tiles with Cin = 64)
-    constexpr int kAcc = PAIR && BLOCK_N <= 128 ? 4 : 2;
+    // accumulator ring (a four-deep ring for N = 128 pairs was measured: no gain on Cin >= 128, and Cin = 64 -- where the
+    // cross-CTA hand-over of an accumulator outlasts the short K loop -- stays slower than the single-CTA form either way)
+    constexpr int kAcc = 2;
     constexpr int kTmemCols = kAcc * BLOCK_N;
     const int S = p.vr_stages;
 
@@ -1575,6 +1575,7 @@ cudaError_t conv_configure() {
     if ((e = configure_vr<64, EPI_OUTC, true>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<256, EPI_STORE, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
@@ -1597,18 +1598,23 @@ static cudaError_t launch_pair(const ConvParams& p, int clusters, cudaStream_t s
 bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) {
     ConvParams& p = L.p;
     if (ksize != 3 || stride != 1 || Ho % 16 || Wo % 8) return false;
-    if (L.block_n != 64 && L.block_n != 128) return false;
+    // N = 256 (the deep UNet levels): only as a CTA pair, where a stage (one activation box + three half weight tiles) is 66 KB
+    // and three of them fit; against the generic pair kernel that is a third less L2 -> SM traffic (the activations are fetched
+    // once per horizontal tap instead of once per tap).  CVB_VR256=0 keeps those layers on the generic kernel.
+    const char* vr256 = getenv("CVB_VR256");
+    const bool wide = L.block_n == 256 && L.epilogue == EPI_STORE && g_pair_clusters > 0 && !(vr256 && vr256[0] == '0');
+    if (L.block_n != 64 && L.block_n != 128 && !wide) return false;
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_OUTC) return false;
     // N = 128 with a plain store: CTA pairs (half of each weight tile per CTA); CVB_NO_PAIR_VR=1 keeps the single-CTA form
     const char* no_pair = getenv("CVB_NO_PAIR_VR");
     const char* min_cc = getenv("CVB_PAIR_VR_MIN_CC");   // A/B: pair form only from this many 64-channel input chunks up
-    const bool pair = g_pair_clusters > 0 && L.block_n == 128 && L.epilogue == EPI_STORE && !(no_pair && no_pair[0] == '1') &&
-                      Cin / 64 >= (min_cc ? atoi(min_cc) : 2);
+    const bool pair = wide || (g_pair_clusters > 0 && L.block_n == 128 && L.epilogue == EPI_STORE && !(no_pair && no_pair[0] == '1') &&
+                               Cin / 64 >= (min_cc ? atoi(min_cc) : 2));
     const int b_bytes = L.block_n * 128 / (pair ? 2 : 1);
     const int w_bytes = 9 * (Cin / 64) * b_bytes;
     const int out_bytes = L.epilogue == EPI_OUTC ? 0 : kOutBufBytes;
     const int budget = kVrMaxSmem - 1024 - 256 - kEpiConstBytes - out_bytes;
-    const bool ws = p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
+    const bool ws = !wide && p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
     if (L.epilogue == EPI_OUTC && !ws) return false;
     const int stage = 18 * 1024 + (ws ? 0 : 3 * b_bytes);
     int stages = (budget - (ws ? w_bytes : 0)) / stage;
@@ -1665,9 +1671,9 @@ template <int BN, int EPI, bool WS>
 static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
     return launch_k(conv3x3_vr_kernel<BN, EPI, WS>, grid, 256, p.smem_bytes, s, pdl, p);
 }
-template <bool WS>
+template <int BN, bool WS>
 static cudaError_t launch_vr_pair(const ConvParams& p, int clusters, cudaStream_t s, bool pdl) {
-    return launch_kc(conv3x3_vr_kernel<128, EPI_STORE, WS, 1>, 2 * clusters, 256, p.smem_bytes, s, pdl, 2, p);
+    return launch_kc(conv3x3_vr_kernel<BN, EPI_STORE, WS, 1>, 2 * clusters, 256, p.smem_bytes, s, pdl, 2, p);
 }
 
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream) {
@@ -1699,11 +1705,12 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
         return e;
     }
     if (L.variant == 1 && L.pair) {
-        if (g_pair_clusters <= 0 || L.block_n != 128 || L.epilogue != EPI_STORE) return cudaErrorInvalidValue;
+        if (g_pair_clusters <= 0 || (L.block_n != 128 && L.block_n != 256) || L.epilogue != EPI_STORE) return cudaErrorInvalidValue;
         const long long units = ((1LL * p.tiles_n * p.tiles_h * p.tiles_w + 1) / 2) * p.n_tiles;
         const int clusters = (int)(units < g_pair_clusters ? units : g_pair_clusters);
         p.idesc = umma_idesc_f16(256, L.block_n, 0);
-        return p.w_stationary ? launch_vr_pair<true>(p, clusters, stream, pdl) : launch_vr_pair<false>(p, clusters, stream, pdl);
+        if (L.block_n == 256) return p.w_stationary ? cudaErrorInvalidValue : launch_vr_pair<256, false>(p, clusters, stream, pdl);
+        return p.w_stationary ? launch_vr_pair<128, true>(p, clusters, stream, pdl) : launch_vr_pair<128, false>(p, clusters, stream, pdl);
     }
     if (L.variant == 1) {
         const bool ws = p.w_stationary != 0;

@@ -1192,14 +1192,12 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
     }
     __syncthreads();
     const int xq = t & 15, yq = t >> 4;
-    double c0[4], c3[4], c6[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double xx = static_cast<double>(4 * xq + i);
-        c0[i] = m0 * xx;
-        c3[i] = m3 * xx;
-        c6[i] = (m6 * xx) * 0.03125;
-    }
+    // Fast path of the coordinates (only has to land within the 2^-13 guard band of the exact value, which is 2^-27 relative):
+    // numerators and denominator advance by one destination pixel with one addition each, the quotient is one MUFU reciprocal
+    // (2^-22) refined by a single Newton step in float64 (2^-43), and the product is formed by the FMA that also adds the
+    // rounding constant.
+    const double xs = static_cast<double>(4 * xq);
+    const double m6s = m6 * 0.03125;   // exact scaling
     const unsigned lim_x = static_cast<unsigned>(ncol16 * 16 - 1), lim_y = static_cast<unsigned>(nrows - 1);
     constexpr double kMagic = 103079215104.0;   // 1.5 * 2^36: the low word of (v + kMagic) is rint(v * 2^16)
     constexpr int kMagicHi = 0x42380000;        // high word of kMagic
@@ -1207,16 +1205,18 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
     for (int j = 0; j < 4; ++j) {
         const int ry = yq + 16 * j;
         const double X0 = rowtab[ry * 3], Y0 = rowtab[ry * 3 + 1], W0s = rowtab[ry * 3 + 2];
+        double Xn = fma(m0, xs, X0), Yn = fma(m3, xs, Y0), ws = fma(m6s, xs, W0s);
         uint32_t packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double Xn = X0 + c0[i], Yn = Y0 + c3[i], ws = W0s + c6[i];
-            double r = static_cast<double>(__frcp_rn(__double2float_rn(ws)));
-            double e = fma(-ws, r, 1.0);
-            r = fma(r, e, r);
-            e = fma(-ws, r, 1.0);
-            r = fma(r, e, r);
-            const double tx = Xn * r + kMagic, ty = Yn * r + kMagic;
+            float rf;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(ws)));
+            double r = static_cast<double>(rf);
+            r = fma(r, fma(-ws, r, 1.0), r);
+            const double tx = fma(Xn, r, kMagic), ty = fma(Yn, r, kMagic);
+            Xn += m0;
+            Yn += m3;
+            ws += m6s;
             const int vx = __double2loint(tx), vy = __double2loint(ty);
             // in range (|v| < 2^15): the high word is kMagicHi, minus one when the low word borrowed
             bool ok = fits && (__double2hiint(tx) - (vx >> 31)) == kMagicHi && (__double2hiint(ty) - (vy >> 31)) == kMagicHi;
