@@ -136,35 +136,32 @@ int pack_stem_tc(cvb_ctx* ctx, const cvb_tensor* sd, int n, const std::string& c
     if (!w || numel(w) != 64LL * Cin * k * k) return fail(ctx, -4, "missing/bad '%s.weight'", conv.c_str());
     Bn bn;
     if (load_bn(ctx, sd, n, bn_prefix, 64, bn)) return -4;
-    std::vector<__half> img(64 * 64, __float2half_rn(0.f));
+    // one or two swizzled [64 co][64 K] tiles: K index kk lives in tile kk / 64
+    const int tiles = (bias_k + 1 >= 64 || neg_k >= 64) ? 2 : 1;
+    std::vector<__half> img(static_cast<size_t>(tiles) * 64 * 64, __float2half_rn(0.f));
+    auto at = [&](int co, int kk) -> __half& {
+        const int t = kk >> 6, c = kk & 63;
+        return img[static_cast<size_t>(t) * 4096 + (static_cast<size_t>(co) * 128 + (((c >> 3) ^ (co & 7)) << 4) + (c & 7) * 2) / 2];
+    };
     for (int co = 0; co < 64; ++co)
         for (int ci = 0; ci < Cin; ++ci)
             for (int r = 0; r < k; ++r)
                 for (int s = 0; s < k; ++s) {
-                    const int kk = r * ky_stride + s * kx_stride + ci;
                     const double v = static_cast<double>(w->data[((static_cast<size_t>(co) * Cin + ci) * k + r) * k + s]) *
                                      static_cast<double>(bn.scale[co]) * (256.0 / 255.0);
-                    const size_t byte = static_cast<size_t>(co) * 128 + (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2;
-                    img[byte / 2] = __float2half_rn(static_cast<float>(v));
+                    at(co, r * ky_stride + s * kx_stride + ci) = __float2half_rn(static_cast<float>(v));
                 }
     // The folded BatchNorm shift rides along as two more K columns (the kernels keep 1.0 in columns bias_k, bias_k + 1 of every
     // im2col row): bias = hi + lo in fp16, exact to 2^-22 of its magnitude, accumulated in fp32 by the MMA itself.
     for (int co = 0; co < 64; ++co) {
         const float b = bn.shift[co];
         const __half hi = __float2half_rn(b);
-        const __half lo = __float2half_rn(b - __half2float(hi));
-        const __half parts[2] = {hi, lo};
-        for (int j = 0; j < 2; ++j) {
-            const int kk = bias_k + j;
-            const size_t byte = static_cast<size_t>(co) * 128 + (((kk >> 3) ^ (co & 7)) << 4) + (kk & 7) * 2;
-            img[byte / 2] = parts[j];
-        }
+        at(co, bias_k) = hi;
+        at(co, bias_k + 1) = __float2half_rn(b - __half2float(hi));
+        // K column neg_k: -30000 for every channel.  An im2col row with 1.0 there (a max-pool window position outside the conv
+        // image) loses every maximum it takes part in (k_resnet_stem_tc).
+        if (neg_k >= 0) at(co, neg_k) = __float2half_rn(-30000.f);
     }
-    // K column neg_k: -30000 for every channel.  An im2col row with 1.0 there (a max-pool window position outside the conv
-    // image) loses every maximum it takes part in (k_resnet_stem_tc).
-    if (neg_k >= 0)
-        for (int co = 0; co < 64; ++co)
-            img[(static_cast<size_t>(co) * 128 + (((neg_k >> 3) ^ (co & 7)) << 4) + (neg_k & 7) * 2) / 2] = __float2half_rn(-30000.f);
     __half* d = nullptr;
     if (dalloc(ctx, &d, img.size())) return -3;
     CK(cudaMemcpy(d, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -740,7 +737,7 @@ int cvb_load_resnet18(cvb_ctx* ctx, const cvb_tensor* sd, int n) {
     if (ctx->resnet_loaded) return fail(ctx, -8, "classifier weights already loaded");
     const int S = ctx->max_batch * 64;
     if (pack_stem(ctx, sd, n, "conv1", "bn1", 1, 7, &ctx->rstem_w, &ctx->rstem_b)) return -4;
-    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, 56, &ctx->rstem_wsw, 58)) return -4;
+    if (pack_stem_tc(ctx, sd, n, "conv1", "bn1", 1, 7, 8, 1, 64, &ctx->rstem_wsw, 66)) return -4;
     const cvb_tensor* fw = find(sd, n, "fc.weight");
     const cvb_tensor* fb = find(sd, n, "fc.bias");
     if (!fw || !fb || numel(fw) != 13 * 512 || numel(fb) != 13) return fail(ctx, -4, "missing/bad fc tensors");

@@ -686,6 +686,279 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
 
 
 // ---------------------------------------------------------------------------------------------------------------------
+// conv_convt_kernel as a CTA pair (cta_group::2): two 16 x 8 tiles per MMA, each CTA holds its own activation boxes, its own
+// A operand of the second MMA, and HALF of every weight tile (64 of the 128 rows; the transposed-conv pieces likewise).  The
+// single-CTA form pulls 66 KB per 768 tensor-clocks from L2 into every SM (~19 TB/s over the chip -- the limit; its MMA warp
+// spent half of its time waiting for weight tiles, ncu r02); here it is 42 KB, and an MMA reads 4 + 2 KB of operands from
+// shared memory instead of 4 + 4.  Barriers the leader's MMA warp waits on (afull, bfull, a2full, tempty) live in the leader
+// and are signalled by both CTAs; barriers the two CTAs' producers / epilogues wait on are signalled by multicast commits.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FusedPairCfg {
+    static constexpr int kAStages = 3, kBStages = 16;
+    static constexpr int kABytes = 18 * 1024, kBBytes = 64 * 128;
+    static constexpr int kA2Bytes = 2 * 128 * 128;
+    static constexpr int kBarBytes = 512;
+    static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kA2Bytes + 1024 + kBarBytes + (128 + 64) * 4;
+};
+
+__global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_pair_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = FusedPairCfg;
+    constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    const uint32_t a_addr = (raw_addr + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (a_addr - raw_addr);
+    const uint32_t b_addr = a_addr + SA * Cfg::kABytes;
+    const uint32_t a2_addr = b_addr + SB * Cfg::kBBytes;
+    uint8_t* a2_ptr = base_ptr + SA * Cfg::kABytes + SB * Cfg::kBBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(a2_ptr + Cfg::kA2Bytes);
+    const uint32_t bar_afull = smem_u32(bars);
+    const uint32_t bar_aempty = bar_afull + 8 * SA;
+    const uint32_t bar_bfull = bar_aempty + 8 * SA;
+    const uint32_t bar_bempty = bar_bfull + 8 * SB;
+    const uint32_t bar_tfull = bar_bempty + 8 * SB;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_a2full = bar_tfull + 32;
+    const uint32_t bar_d2full = bar_tfull + 40;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 8);
+    float* s_bias = reinterpret_cast<float*>(a2_ptr + Cfg::kA2Bytes + Cfg::kBarBytes);
+    float* s_bias2 = s_bias + 128;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.b_map);
+        tma_prefetch_desc(&p.b2_map);
+        tma_prefetch_desc(&p.a_map[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < SA; ++i) {
+            mbar_init(bar_afull + 8 * i, 1);
+            mbar_init(bar_aempty + 8 * i, 1);
+        }
+        for (int i = 0; i < SB; ++i) {
+            mbar_init(bar_bfull + 8 * i, 1);
+            mbar_init(bar_bempty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 512);   // the 256 epilogue threads of both CTAs
+        }
+        mbar_init(bar_a2full, 512);
+        mbar_init(bar_d2full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    if (warp == 3) {
+        for (int i = lane; i < 128; i += 32) s_bias[i] = __ldg(p.bias + i);
+        for (int i = lane; i < 64; i += 32) s_bias2[i] = __ldg(p.bias2 + i);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t d2_tmem = tmem_base + 256;
+    griddep_launch();
+    griddep_wait();
+
+    const int total_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int total_units = (total_tiles + 1) >> 1;
+    const int unit0 = static_cast<int>(blockIdx.x >> 1), unit_step = static_cast<int>(gridDim.x >> 1);
+
+    if (warp == 0) {
+        const uint32_t afull_sig = mapa_cluster(bar_afull, 0), bfull_sig = mapa_cluster(bar_bfull, 0);
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        auto load_w2 = [&]() {
+            for (int j = 0; j < 4; ++j) {   // j = rh * 2 + kb: this CTA's 64 of the rows [128 rh, 128 rh + 128) of W2, K block kb
+                mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(bar_bfull + 8 * bs, 2 * Cfg::kBBytes);
+                    tma_load_2d_pair(b_addr + bs * Cfg::kBBytes, &p.b2_map, bfull_sig + 8 * bs, (j & 1) * 64, (j >> 1) * 128 + static_cast<int>(rank) * 64);
+                }
+                __syncwarp();
+                if (++bs == SB) { bs = 0; bph ^= 1; }
+            }
+        };
+        int iter = 0;
+        for (int u = unit0; u < total_units; u += unit_step, ++iter) {
+            const int t = 2 * u + static_cast<int>(rank);
+            const int w0 = (t % p.tiles_w) * 8;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
+            const int n0 = t / (p.tiles_w * p.tiles_h);
+            for (int kc = 0; kc < p.c_chunks; ++kc) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(bar_afull + 8 * as, 2 * Cfg::kABytes);
+                        tma_load_4d_pair(a_addr + as * Cfg::kABytes, &p.a_map[0], afull_sig + 8 * as, p.a_c_off + kc * 64, w0 + dxi - 1, h0 - 1, n0);
+                    }
+                    __syncwarp();
+                    if (++as == SA) { as = 0; aph ^= 1; }
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+                        if (elect_one()) {
+                            if (rank == 0) mbar_expect_tx(bar_bfull + 8 * bs, 2 * Cfg::kBBytes);
+                            tma_load_2d_pair(b_addr + bs * Cfg::kBBytes, &p.b_map, bfull_sig + 8 * bs, ((dy * 3 + dxi) * p.c_chunks + kc) * 64,
+                                             static_cast<int>(rank) * 64);
+                        }
+                        __syncwarp();
+                        if (++bs == SB) { bs = 0; bph ^= 1; }
+                    }
+                }
+            }
+            if (iter > 0) load_w2();
+        }
+        if (iter > 0) load_w2();
+    } else if (warp == 1 && rank == 0) {
+        const bool leader = elect_one();
+        const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_sw128(0));
+        const uint32_t a_lo0 = desc_lo0 + ((a_addr & 0x3FFFFu) >> 4);
+        const uint32_t b_lo0 = desc_lo0 + ((b_addr & 0x3FFFFu) >> 4);
+        const uint32_t a2_lo = desc_lo0 + ((a2_addr & 0x3FFFFu) >> 4);
+        const uint32_t idesc = umma_idesc_f16(256, 128, 0);
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        // second MMA of unit j: D2[256 px][(dy,dx,co)] = A2[256 px][128 ci] . W2^T as four N = 128 pieces (row half rh of W2,
+        // K block kb), each fed by one tile of the weight ring (64 rows per CTA)
+        auto mma2 = [&](int j) {
+            mbar_wait_cluster(bar_a2full, j & 1);
+            for (int q = 0; q < 4; ++q) {
+                mbar_wait(bar_bfull + 8 * bs, bph);
+                tc_fence_after();
+                if (leader) {
+                    const int rh = q >> 1, kb = q & 1;
+                    const uint32_t b_lo = b_lo0 + bs * (Cfg::kBBytes >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_pair(d2_tmem + rh * 128, desc_hi | (a2_lo + kb * (128 * 128 >> 4) + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(bar_bempty + 8 * bs);
+                    if (q == 3) umma_commit_pair(bar_d2full);
+                }
+                __syncwarp();
+                if (++bs == SB) { bs = 0; bph ^= 1; }
+            }
+        };
+        int iter = 0;
+        for (int u = unit0; u < total_units; u += unit_step, ++iter) {
+            const int acc = iter & 1;
+            mbar_wait(bar_tempty + 8 * acc, ((iter >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 128;
+            for (int kc = 0; kc < p.c_chunks; ++kc) {
+                for (int dxi = 0; dxi < 3; ++dxi) {
+                    mbar_wait(bar_afull + 8 * as, aph);
+                    const uint32_t a_lo = a_lo0 + as * (Cfg::kABytes >> 4);
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(bar_bfull + 8 * bs, bph);
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t b_lo = b_lo0 + bs * (Cfg::kBBytes >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)   // tap dy: the same box one 8-row swizzle group (1024 B) further
+                                umma_f16_pair(d_tmem, desc_hi | (a_lo + dy * 64 + 2 * k), desc_hi | (b_lo + 2 * k), idesc, (kc | dxi | dy | k) != 0 ? 1u : 0u);
+                            umma_commit_pair(bar_bempty + 8 * bs);
+                        }
+                        __syncwarp();
+                        if (++bs == SB) { bs = 0; bph ^= 1; }
+                    }
+                    if (leader) {
+                        umma_commit_pair(bar_aempty + 8 * as);
+                        if (kc == p.c_chunks - 1 && dxi == 2) umma_commit_pair(bar_tfull + 8 * acc);
+                    }
+                    __syncwarp();
+                    if (++as == SA) { as = 0; aph ^= 1; }
+                }
+            }
+            if (iter > 0) mma2(iter - 1);
+        }
+        if (iter > 0) mma2(iter - 1);
+    } else if (warp >= 4) {
+        // Two epilogue groups (warps 4-7 / 8-11) work on this CTA's tile exactly as in conv_convt_kernel.
+        const int quarter = warp & 3, g = (warp - 4) >> 2, etid = (threadIdx.x - 128) & 127;
+        const int row = quarter * 32 + lane;   // = 8 * (row of the 16 x 8 tile) + column
+        const uint32_t no_res[32] = {0};
+        uint8_t* my_buf = a2_ptr + g * (128 * 128);
+        const uint32_t my_buf_addr = a2_addr + g * (128 * 128);
+        const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+        const uint32_t tempty_sig = mapa_cluster(bar_tempty, 0), a2full_sig = mapa_cluster(bar_a2full, 0);
+        int iter = 0;
+        for (int u = unit0; u < total_units; u += unit_step, ++iter) {
+            const int acc = iter & 1;
+            const int t = 2 * u + static_cast<int>(rank);
+            const int w0 = (t % p.tiles_w) * 8;
+            const int h0 = ((t / p.tiles_w) % p.tiles_h) * 16;
+            const int n0 = t / (p.tiles_w * p.tiles_h);
+            mbar_wait(bar_tfull + 8 * acc, (iter >> 1) & 1);
+            tc_fence_after();
+            // ---- part 1: accumulator -> bias + ReLU -> fp16 -> K block g of the second MMA's A operand
+            if (etid == 0) bulk_wait_read<0>();   // this group's stores of the previous tile have finished reading the block
+            named_bar_sync(1 + g, 128);
+            {
+                uint32_t va[32], vb[32], o[32];
+                tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + g * 64, va);
+                tmem_ld_32x32(tmem_base + lane_addr + acc * 128 + g * 64 + 32, vb);
+                tmem_ld_wait(va);
+                pack_chunk<0>(va, s_bias + g * 64, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                tmem_ld_wait(vb);
+                tc_fence_before();
+                mbar_arrive_cluster(tempty_sig + 8 * acc);          // the accumulator half is in registers: release it early
+                pack_chunk<16>(vb, s_bias + g * 64 + 32, no_res, false, true, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                uint8_t* dst = my_buf + row * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive_cluster(a2full_sig);
+            // ---- part 2: taps q = 2g, 2g+1 of the transposed-conv accumulator -> + bias -> fp16 -> strided tile stores
+            mbar_wait(bar_d2full, iter & 1);
+            tc_fence_after();
+            {
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(d2_tmem + lane_addr + (2 * g) * 64, va);
+#pragma unroll
+                for (int qq = 0; qq < 2; ++qq) {
+                    const int q = 2 * g + qq;
+                    uint32_t o[32];
+                    tmem_ld_wait(va);
+                    tmem_ld_32x32(d2_tmem + lane_addr + q * 64 + 32, vb);
+                    pack_chunk<0>(va, s_bias2, no_res, false, false, reinterpret_cast<uint32_t(&)[16]>(o[0]));
+                    tmem_ld_wait(vb);
+                    if (qq == 0) tmem_ld_32x32(d2_tmem + lane_addr + (q + 1) * 64, va);
+                    pack_chunk<16>(vb, s_bias2 + 32, no_res, false, false, reinterpret_cast<uint32_t(&)[16]>(o[16]));
+                    // block free: qq = 0 -> the second MMA has consumed it (d2full); qq = 1 -> this group's first store has read it
+                    if (qq == 1 && etid == 0) bulk_wait_read<0>();
+                    named_bar_sync(1 + g, 128);
+                    uint8_t* dst = my_buf + row * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + g, 128);
+                    if (etid == 0) {
+                        tma_store_4d(&p.o_map[q], my_buf_addr, p.out_c_off, w0, h0, n0);
+                        bulk_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+        if (etid == 0) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
 // 3x3 / stride 1 variant with vertical-tap reuse (and optionally stationary weights) for the wide, shallow layers
 // (Cout = 64 or 128 at 256^2 / 128^2), which are L2->SM bandwidth bound in the generic kernel: every tap re-fetches
 // the same activations.  Here one TMA box {64 ch, 8 w, 18 h} (18 swizzle groups of 1024 B) per horizontal offset dx
@@ -1391,6 +1664,9 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
         p.tn = 1; p.th = 16; p.tw = 8;   // the vertical-reuse tile: 16 rows x 8 columns, activation box {64, 8, 18, 1}
         p.tiles_w = Wo / 8;
         p.tiles_h = Ho / 16;
+        const char* np = getenv("CVB_NO_PAIR_CONVT");
+        L.pair = g_pair_clusters > 0 && !(np && np[0] == '1') ? 1 : 0;   // conv_convt_pair_kernel: 64 weight rows per CTA
+        if (L.pair && (rc = tmap_weights(&p.b_map, w, K, rows, 64))) return rc;
         return tmap_act_vr(&p.a_map[0], in, in_c_stride, Win, Hin, Nmax, sW, sH, sN);   // conv_set_fused_convt completes the launch
     }
     if (use_vr && conv_try_rs(L, ksize, stride, Ho, Wo, Cin)) {
@@ -1494,7 +1770,7 @@ int conv_set_fused_convt(ConvLaunch& L, const __half* w2, const float* bias2, in
     if (L.epilogue != EPI_FUSED_CONVT || L.block_n != 128 || p.n_tiles != 1 || cout2 != 64) return -5;
     if (tmap_init()) return -1;
     // transposed-conv weights [4 * cout2 rows][128 k]: box {64 k, 128 rows} (one tile of the weight ring)
-    int rc = tmap_weights(&p.b2_map, w2, 128, 4 * cout2, 128);
+    int rc = tmap_weights(&p.b2_map, w2, 128, 4 * cout2, L.pair ? 64 : 128);
     if (rc) return rc;
     p.bias2 = bias2;
     p.convt_cout = cout2;
@@ -1557,6 +1833,7 @@ cudaError_t conv_configure() {
     if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::kSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_convt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedPairCfg::kSmemBytes)) != cudaSuccess) return e;
     {
         const char* off = getenv("CVB_NO_PAIR");
         g_pair_clusters = off && off[0] == '1' ? 0 : 1 << 20;
@@ -1687,6 +1964,12 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
     const bool pdl = L.pdl != 0;
     if (L.epilogue == EPI_FUSED_CONVT) {
         if (L.variant != 0 || L.block_n != 128 || p.n_tiles != 1 || p.bias2 == nullptr) return cudaErrorInvalidValue;
+        if (L.pair) {
+            if (g_pair_clusters <= 0) return cudaErrorInvalidValue;
+            const long long units = (total + 1) / 2;
+            const int clusters = (int)(units < g_pair_clusters ? units : g_pair_clusters);
+            return launch_kc(conv_convt_pair_kernel, 2 * clusters, kFusedThreads, FusedPairCfg::kSmemBytes, stream, pdl, 2, p);
+        }
         return launch_k(conv_convt_kernel, grid, kFusedThreads, FusedCfg::kSmemBytes, stream, pdl, p);
     }
     if (L.variant == 2) {

@@ -95,23 +95,27 @@ __device__ __forceinline__ void mma_tile(uint32_t a_addr, uint32_t b_addr, uint3
 // per-thread running maximum (3-input FMNMX3) over accumulator blocks: no shuffles, no shared-memory row ring, no named
 // barriers, and ReLU + the fp16 conversion are applied once per pooled pixel instead of once per conv pixel (max commutes
 // with the monotone conversion, so the bytes equal pool(relu(conv))).
-// The im2col rows never touch shared memory: the producer thread of row p writes its 64 fp16 (32 registers) straight into
-// tensor memory (tcgen05.st) and the MMA takes its A operand from there; only the 8 KB weight tile is read from shared
-// memory, so the N = 64 MMAs run at the tensor rate instead of the shared-memory operand rate (52 instead of 32 clocks each
-// for an A operand in shared memory, and writing + reading 16 KB per tile kept the first version of this kernel bound by
-// shared-memory bandwidth).
-// A window position outside the 32 x 32 conv image (dy = 0 at py = 0, dx = 0 at px = 0) must lose the maximum: its im2col row
-// is zero except for a 1.0 in K column 58, whose weight row holds -30000 for every channel.
-// Pipeline: a "batch" is the three tiles dy = 0..2 of one dx (their im2col chunks overlap: chunk ky of tile dy is row 2dy + ky
-// of an 11-row column strip, loaded once).  TMEM: two sets of three 64-column accumulators (columns 0..383) and a ring of
-// four A tiles of 32 columns (384..511).
+// The im2col rows never touch shared memory: the A operand lives in tensor memory, written by tcgen05.st from the producer
+// thread that owns the lane; only the 8 KB weight tile is read from shared memory, so the N = 64 MMAs run at the tensor rate
+// (32 clocks; 52 with an A operand in shared memory, and writing + reading 16 KB per tile kept the first version of this
+// kernel bound by shared-memory bandwidth).
+// Unit of the pipeline = one "batch": the three window rows dy = 0..2 of one window column dx.  Their im2col rows overlap:
+// with K laid out as 7 input rows x 8 columns, K step i of tile dy is K step dy + i of an 11-row column strip -- so the
+// producers write ONE strip of 48 TMEM columns per batch and the three tiles read it at column offsets 8 dy.  (K columns
+// 56..63 of a tile are then the next input row of the strip; their weights are zero.)  Bias and validity ride in a fifth K
+// step against a second weight tile: its A operand is one of four constant 8-column blocks (written once), rows
+// (1, 1, 0, ..) for a conv pixel -> + bias_hi + bias_lo, rows (0, 0, 1, ..) for a window position outside the 32 x 32 conv
+// image (dy = 0 at py = 0, dx = 0 at px = 0) -> -30000, which loses every maximum it takes part in.
+// TMEM: two sets of three 64-column accumulators (columns 0..383), the four marker blocks (384..415), two strips (416..511).
+// Two producer groups fill the two strips alternately; the hand-over latencies (tcgen05.st -> wait -> arrive -> MMA issue ->
+// commit) are per batch of 15 MMAs, not per tile of 4 as in the previous version, which they bounded.
 // =====================================================================================================================
 constexpr int kRsInHalfs = 70 * 72;                      // staged square: s_in[r][c] = px(r-3, c-3) / 256
 constexpr int kRsInBytes = ((kRsInHalfs * 2 + 1023) / 1024) * 1024;
-constexpr int kRsASlots = 4;
-constexpr int kRsOffIn = kBBytes;                        // 2 buffers x 2 copies (the second one word to the left)
+constexpr int kRsOffIn = 2 * kBBytes;                    // after the two weight tiles: 2 buffers x 2 copies (the second one word to the left)
 constexpr int kRsOffBars = kRsOffIn + 4 * kRsInBytes;
 constexpr int kRsSmem = kRsOffBars + 256 + 1024;
+constexpr uint32_t kRsColMarker = 384, kRsColStrip = 416, kRsStripCols = 48;
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
     float r;
@@ -128,18 +132,15 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + kRsOffBars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kRsASlots, bar_tfull = bar_empty + 8 * kRsASlots,
-                   bar_tempty = bar_tfull + 16;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 16, bar_tfull = bar_full + 32, bar_tempty = bar_full + 48;
 
-    for (int i = tid; i < kBBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
+    for (int i = tid; i < 2 * kBBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base)[i] = __ldg(wsw + i);
     for (int i = tid; i < 4 * kRsInBytes / 16; i += kRsThreads) reinterpret_cast<uint4*>(base + kRsOffIn)[i] = make_uint4(0, 0, 0, 0);
     if (warp == 16) {
         if (lane == 0) {
-            for (int i = 0; i < kRsASlots; ++i) {
+            for (int i = 0; i < 2; ++i) {
                 mbar_init(bar_full + 8 * i, 128);
                 mbar_init(bar_empty + 8 * i, 1);
-            }
-            for (int i = 0; i < 2; ++i) {
                 mbar_init(bar_tfull + 8 * i, 1);
                 mbar_init(bar_tempty + 8 * i, 256);
             }
@@ -148,24 +149,40 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), 512);
     }
-    fence_proxy_async();   // the weight tile written with ordinary stores is read by the tensor core
+    fence_proxy_async();   // the weight tiles written with ordinary stores are read by the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_a = tmem_base + 384;
+    if (warp < 4) {
+        // marker blocks (constant): variant v = (dy == 0 && upper half square) + 2 * (dx == 0); lane = pooled pixel (tid >> 4, tid & 15)
+        uint32_t mk[32];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const bool bad = ((v & 1) && tid < 16) || ((v & 2) && (tid & 15) == 0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mk[8 * v + i] = 0u;
+            mk[8 * v] = bad ? 0u : 0x3C003C00u;        // K columns 0, 1 = 1.0: + bias_hi + bias_lo
+            mk[8 * v + 1] = bad ? 0x00003C00u : 0u;    // K column 2 = 1.0: - 30000
+        }
+        tmem_st_32x32(tmem_base + kRsColMarker + (static_cast<uint32_t>(warp * 32) << 16), mk);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     griddep_launch();
     griddep_wait();   // weights, zero padding, barriers and TMEM were set up under the previous kernel's tail
 
     if (warp < 8) {
         // ------------------------------------------------------------------------------------------------ producers
-        // Two groups of four warps (a warp writes the TMEM lane quadrant warp % 4) take alternate tiles: the chain
-        // wait for the slot -> tcgen05.st -> wait::st -> arrive is latency-bound, two of them in flight keep the MMA fed.
+        // Two groups of four warps (a warp writes the TMEM lane quadrant warp % 4); group pg fills strip pg for the batches
+        // of its parity.  Group 0 also stages the square.
         const int pg = warp >> 2;
-        const int p = tid & 127;           // M row of every tile = TMEM lane = pooled pixel (p >> 4, p & 15) of the half square;
-        const int row = p >> 1, half = p & 1;   // also (row, half) of the staged square (group 0 stages it)
-        const uint32_t a_lane = tmem_a + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        int tile = 0, buf = 0;             // running tile index: slot = tile % 4, taken by group tile % 2
+        const int p = tid & 127;           // TMEM lane = pooled pixel (p >> 4, p & 15) of the half square;
+        const int row = p >> 1, half = p & 1;   // also (row, half) of the staged square
+        const uint32_t strip = tmem_base + kRsColStrip + kRsStripCols * pg + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        int batch = 0, buf = 0;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
         auto fetch = [&](int sq) {
             const int n = sq >> 6, q = sq & 63;
@@ -182,44 +199,45 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
             // in one of the two copies
             uint32_t* in0 = reinterpret_cast<uint32_t*>(base + kRsOffIn + (2 * buf) * kRsInBytes);
             uint32_t* in1 = reinterpret_cast<uint32_t*>(base + kRsOffIn + (2 * buf + 1) * kRsInBytes);
-          if (pg == 0) {
-            const uint32_t wsrc[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            __half2 h[16];   // h[k] = (x_2k, x_2k+1)
+            if (pg == 0) {
+                const uint32_t wsrc[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                __half2 h[16];   // h[k] = (x_2k, x_2k+1)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                h[2 * k] = bytes_to_h2(wsrc[k], 0x4140);
-                h[2 * k + 1] = bytes_to_h2(wsrc[k], 0x4342);
-            }
-            // words of the staged row hold (x_odd, x_even): shift the pair stream by one pixel
-            const uint32_t last = h2_bits(h[15]) >> 16;                                  // x_31
-            const uint32_t left = __shfl_up_sync(0xffffffffu, last, 1);                  // x_31 of the left half-row
-            const int w0 = (row + 3) * 36 + 1 + 16 * half;
-            uint32_t prev = half ? left : 0u;
+                for (int k = 0; k < 8; ++k) {
+                    h[2 * k] = bytes_to_h2(wsrc[k], 0x4140);
+                    h[2 * k + 1] = bytes_to_h2(wsrc[k], 0x4342);
+                }
+                // words of the staged row hold (x_odd, x_even): shift the pair stream by one pixel
+                const uint32_t last = h2_bits(h[15]) >> 16;                                  // x_31
+                const uint32_t left = __shfl_up_sync(0xffffffffu, last, 1);                  // x_31 of the left half-row
+                const int w0 = (row + 3) * 36 + 1 + 16 * half;
+                uint32_t prev = half ? left : 0u;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                const uint32_t cur = h2_bits(h[k]);
-                const uint32_t v = prev | (cur << 16);
-                in0[w0 + k] = v;
-                in1[w0 + k - 1] = v;
-                prev = cur >> 16;
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t cur = h2_bits(h[k]);
+                    const uint32_t v = prev | (cur << 16);
+                    in0[w0 + k] = v;
+                    in1[w0 + k - 1] = v;
+                    prev = cur >> 16;
+                }
+                if (half) {                                                                  // (x_63, 0)
+                    in0[w0 + 16] = prev;
+                    in1[w0 + 15] = prev;
+                }
+                const int nsq = sq + gridDim.x;
+                if (nsq < n_squares) fetch(nsq);
             }
-            if (half) {                                                                  // (x_63, 0)
-                in0[w0 + 16] = prev;
-                in1[w0 + 15] = prev;
-            }
-            const int nsq = sq + gridDim.x;
-            if (nsq < n_squares) fetch(nsq);
-          }
             named_bar(1, 256);
             const int px = p & 15;
             for (int T = 0; T < 2; ++T) {
                 const int py = 8 * T + (p >> 4);
-                for (int dx = 0; dx < 3; ++dx) {
+                for (int dx = 0; dx < 3; ++dx, ++batch) {
+                    if ((batch & 1) != pg) continue;
                     // column strip of conv column cx = 2px + dx - 1: words cx .. cx+3 of staged rows 4py - 2 + j, j = 0..10
                     const int cx = 2 * px + dx - 1;
                     const bool x_ok = cx >= 0;
                     const uint32_t* src = ((cx & 1) ? in1 + (cx - 1) : in0 + cx) + (4 * py - 2) * 36;
-                    uint32_t R[44];
+                    uint32_t R[48];
 #pragma unroll
                     for (int j = 0; j < 11; ++j) {
                         if (x_ok && (j >= 2 || py > 0)) {
@@ -230,26 +248,14 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
                             R[4 * j] = R[4 * j + 1] = R[4 * j + 2] = R[4 * j + 3] = 0u;
                         }
                     }
-#pragma unroll
-                    for (int dy = 0; dy < 3; ++dy, ++tile) {
-                        if ((tile & 1) != pg) continue;
-                        const int slot = tile & 3;
-                        const uint32_t phase = (tile >> 2) & 1;
-                        const bool ok = x_ok && (dy > 0 || py > 0);
-                        uint32_t v[32];
-#pragma unroll
-                        for (int i = 0; i < 28; ++i) v[i] = (dy > 0 || py > 0) ? R[8 * dy + i] : 0u;
-                        // K columns 56, 57 = 1.0 (x the two bias rows of B) for a conv pixel, column 58 = 1.0 (x -30000) outside the image
-                        v[28] = ok ? 0x3C003C00u : 0u;
-                        v[29] = ok ? 0u : 0x00003C00u;
-                        v[30] = v[31] = 0u;
-                        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-                        tc_fence_after();
-                        tmem_st_32x32(a_lane + 32 * slot, v);
-                        tmem_st_wait();
-                        tc_fence_before();
-                        mbar_arrive(bar_full + 8 * slot);
-                    }
+                    R[44] = R[45] = R[46] = R[47] = 0u;
+                    mbar_wait(bar_empty + 8 * pg, ((batch >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    tmem_st_32x32(strip, reinterpret_cast<const uint32_t(&)[32]>(R[0]));
+                    tmem_st_32x16(strip + 32, R + 32);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(bar_full + 8 * pg);
                 }
             }
             buf ^= 1;
@@ -295,26 +301,31 @@ __global__ void __launch_bounds__(kRsThreads, 1) k_resnet_stem_tc(const uint8_t*
     } else {
         // ------------------------------------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = umma_idesc_f16(128, 64, 0);
-        const uint64_t b_desc = umma_desc_sw128(base_addr);
+        const uint64_t b_desc = umma_desc_sw128(base_addr), bm_desc = umma_desc_sw128(base_addr + kBBytes);
         const bool leader = elect_one();
-        int slot = 0, batch = 0;
-        uint32_t phase = 0;
+        int batch = 0;
         for (int sq = blockIdx.x; sq < n_squares; sq += gridDim.x) {
-            for (int b6 = 0; b6 < 6; ++b6, ++batch) {
-                const int bb = batch & 1;
-                mbar_wait(bar_tempty + 8 * bb, ((batch >> 1) & 1) ^ 1);
-                for (int dy = 0; dy < 3; ++dy) {
-                    mbar_wait(bar_full + 8 * slot, phase);
+            for (int T = 0; T < 2; ++T) {
+                for (int dx = 0; dx < 3; ++dx, ++batch) {
+                    const int bb = batch & 1;
+                    const uint32_t ph = (batch >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * bb, ph ^ 1);
+                    mbar_wait(bar_full + 8 * bb, ph);
                     tc_fence_after();
                     if (leader) {
+                        const uint32_t strip = tmem_base + kRsColStrip + kRsStripCols * bb;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16_ts(tmem_base + bb * 192 + dy * 64, tmem_a + 32 * slot + 8 * k, b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
-                        umma_commit(bar_empty + 8 * slot);
-                        if (dy == 2) umma_commit(bar_tfull + 8 * bb);
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t acc = tmem_base + bb * 192 + dy * 64;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) umma_f16_ts(acc, strip + 8 * (dy + k), b_desc + 2 * k, idesc, k != 0 ? 1u : 0u);
+                            const uint32_t variant = (dy == 0 && T == 0 ? 1u : 0u) + (dx == 0 ? 2u : 0u);
+                            umma_f16_ts(acc, tmem_base + kRsColMarker + 8 * variant, bm_desc, idesc, 1u);
+                        }
+                        umma_commit(bar_empty + 8 * bb);
+                        umma_commit(bar_tfull + 8 * bb);
                     }
                     __syncwarp();
-                    if (++slot == kRsASlots) { slot = 0; phase ^= 1; }
                 }
             }
         }
