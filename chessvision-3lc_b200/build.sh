@@ -14,8 +14,9 @@ $NVCC $FLAGS -c csrc/wgrad_tc.cu -o build/wgrad_tc.o &
 $NVCC $FLAGS -c csrc/train_kernels.cu -o build/train_kernels.o &
 $NVCC $FLAGS -c csrc/train.cu -o build/train.o &
 $NVCC $FLAGS -c csrc/consumers.cu -o build/consumers.o &
+$NVCC $FLAGS -c csrc/train_cls.cu -o build/train_cls.o &
 $NVCC $FLAGS -c csrc/jpeg.cu -o build/jpeg.o &
 # a failed compile must fail the build (a bare `wait` returns 0 and the link would reuse a stale object)
 for job in $(jobs -p); do wait "$job"; done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o build/wgrad_tc.o build/train_kernels.o build/train.o build/consumers.o build/jpeg.o -lpthread
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o libchessvision_b200.so build/conv_tc.o build/stem.o build/stem_tc.o build/geometry.o build/api.o build/wgrad_tc.o build/train_kernels.o build/train.o build/consumers.o build/train_cls.o build/jpeg.o -lpthread
 echo "built $(pwd)/libchessvision_b200.so"

@@ -37,6 +37,13 @@ class TrainConfig(C.Structure):
     _fields_ = [("batch", C.c_int32), ("loss_scale", C.c_float), ("momentum", C.c_float), ("alpha", C.c_float), ("eps", C.c_float),
                 ("weight_decay", C.c_float), ("max_grad_norm", C.c_float), ("bn_momentum", C.c_float), ("bn_eps", C.c_float)]
 
+class ClsTrainConfig(C.Structure):
+    """cvb_cls_train_config (include/chessvision_b200.h); defaults = torch.optim.Adam / nn.BatchNorm2d defaults
+    (scripts/train/train_classifier.py:218-221 of the reference)."""
+    _fields_ = [("batch", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("bn_momentum", C.c_float), ("bn_eps", C.c_float)]
+
+
 # every symbol include/chessvision_b200.h declares: name -> (restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int, C.c_float
 SYMBOLS = {
@@ -74,6 +81,15 @@ SYMBOLS = {
     "cvb_train_optimizer_step": (_I, [_P, _F, _F, _P]),
     "cvb_train_step": (_I, [_P, _P, _P, _F, _P, _P]),
     "cvb_train_export": (_I, [_P, _I, C.POINTER(_Tensor), _I]),
+    "cvb_cls_train_default_config": (_I, [C.POINTER(ClsTrainConfig)]),
+    "cvb_cls_train_create": (_I, [_P, C.POINTER(_Tensor), _I, C.POINTER(ClsTrainConfig)]),
+    "cvb_cls_train_forward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P]),
+    "cvb_cls_train_forward_backward": (_I, [_P, _P, _P, _P, _P, _P]),
+    "cvb_cls_train_grads": (_I, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "cvb_cls_train_optimizer_step": (_I, [_P, _F, _F, _P]),
+    "cvb_cls_train_step": (_I, [_P, _P, _P, _F, _P, _P, _P]),
+    "cvb_cls_train_export": (_I, [_P, _I, C.POINTER(_Tensor), _I]),
+    "cvb_cls_train_steps": (C.c_int64, [_P]),
     "cvb_wgrad3x3_f16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "cvb_eval_metrics": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "cvb_quality_scores": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
@@ -404,6 +420,85 @@ class Engine:
         arr = (_Tensor * len(items))(*items)
         self._ck(self.lib.cvb_train_export(self.h, 1 if grads else 0, arr, len(items)), "cvb_train_export")
         return {k: torch.from_numpy(v) for k, v in out.items()}
+
+    # ---- piece-classifier training step (cvb_cls_train_*)
+    def cls_train_create(self, state_dict, batch=64, **overrides):
+        """model.train() state of resnet18(num_classes=13, in_chans=1) + Adam from a state_dict; overrides: fields of ClsTrainConfig."""
+        cfg = ClsTrainConfig()
+        self._ck(self.lib.cvb_cls_train_default_config(C.byref(cfg)), "cvb_cls_train_default_config")
+        cfg.batch = batch
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown training option '{k}'")
+            setattr(cfg, k, v)
+        arr, keep = _state_dict_array(state_dict)
+        self._ck(self.lib.cvb_cls_train_create(self.h, arr, len(arr), C.byref(cfg)), "cvb_cls_train_create")
+        self.cls_cfg = cfg
+        self._cls_shapes = {k: tuple(v.shape) for k, v in state_dict.items() if torch.is_tensor(v) and v.is_floating_point()}
+        self._cls_loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._cls_correct = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return cfg
+
+    def _cls_check(self, data, target):
+        b = self.cls_cfg.batch
+        assert data.is_cuda and data.dtype == torch.float32 and data.numel() == b * 4096 and data.is_contiguous(), \
+            f"data must be a contiguous fp32 CUDA tensor [{b},1,64,64]"
+        if target is not None:
+            assert target.is_cuda and target.dtype == torch.int32 and target.numel() == b and target.is_contiguous()
+
+    def cls_train_forward(self, data, target=None, training=False):
+        """logits fp32 [B,13] (+ loss / correct when target is given) in model.train() or model.eval() state."""
+        self._cls_check(data, target)
+        logits = torch.empty((self.cls_cfg.batch, 13), dtype=torch.float32, device=self.device)
+        self._ck(self.lib.cvb_cls_train_forward(self.h, _ptr(data), _ptr(target) if target is not None else None, 1 if training else 0,
+                                                _ptr(self._cls_loss), _ptr(self._cls_correct), _ptr(logits), _stream()), "cvb_cls_train_forward")
+        return logits, self._cls_loss, self._cls_correct
+
+    def cls_train_forward_backward(self, data, target):
+        self._cls_check(data, target)
+        self._ck(self.lib.cvb_cls_train_forward_backward(self.h, _ptr(data), _ptr(target), _ptr(self._cls_loss), _ptr(self._cls_correct), _stream()),
+                 "cvb_cls_train_forward_backward")
+        return self._cls_loss, self._cls_correct
+
+    def cls_train_grads(self):
+        ptr, cnt = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.cvb_cls_train_grads(self.h, C.byref(ptr), C.byref(cnt)), "cvb_cls_train_grads")
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (cnt.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 3, "strides": None}
+
+        return torch.as_tensor(_Alias(), device=self.device)
+
+    def cls_train_optimizer_step(self, lr, grad_scale=1.0):
+        self._ck(self.lib.cvb_cls_train_optimizer_step(self.h, lr, grad_scale, _stream()), "cvb_cls_train_optimizer_step")
+
+    def cls_train_step(self, data, target, lr):
+        self._cls_check(data, target)
+        self._ck(self.lib.cvb_cls_train_step(self.h, _ptr(data), _ptr(target), lr, _ptr(self._cls_loss), _ptr(self._cls_correct), _stream()),
+                 "cvb_cls_train_step")
+        return self._cls_loss, self._cls_correct
+
+    def cls_train_export(self, what=0):
+        """what = 0: parameters + running statistics, 1: gradients, 2 / 3: Adam exp_avg / exp_avg_sq; CPU tensors, torch layout."""
+        out, items = {}, []
+        for k, shape in self._cls_shapes.items():
+            if what != 0 and "running_" in k:
+                continue
+            a = np.zeros(shape, np.float32)
+            out[k] = a
+            t = _Tensor()
+            t.name = k.encode()
+            t.data = a.ctypes.data
+            t.ndim = a.ndim
+            for i in range(4):
+                t.shape[i] = a.shape[i] if i < a.ndim else 1
+            items.append(t)
+        arr = (_Tensor * len(items))(*items)
+        self._ck(self.lib.cvb_cls_train_export(self.h, what, arr, len(items)), "cvb_cls_train_export")
+        return {k: torch.from_numpy(v) for k, v in out.items()}
+
+    def cls_train_steps(self) -> int:
+        return int(self.lib.cvb_cls_train_steps(self.h))
 
     def wgrad3x3_f16(self, dz, x, scale=1.0):
         n, h, w, cout = dz.shape

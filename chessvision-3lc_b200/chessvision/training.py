@@ -123,3 +123,83 @@ class UNetTrainer:
     def close(self):
         if self._own_engine:
             self.engine.close()
+
+
+class ClassifierTrainer:
+    """timm resnet18(num_classes=13, in_chans=1) in training on one GPU: the reference's ``train`` / ``validate`` loops and its
+    optimizer / scheduler (``scripts/train/train_classifier.py:63-113,218-221``: CrossEntropyLoss, Adam(lr=1e-3), StepLR(step_size=4,
+    gamma=0.1)) behind the C ABI (``cvb_cls_train_*``, fp32 CUDA kernels in ``csrc/train_cls.cu``).
+
+    ``step(data, target)`` is the loop body ``optimizer.zero_grad(); output = model(data); loss = criterion(output, target);
+    loss.backward(); optimizer.step()`` and returns ``(loss, correct)`` as device tensors; ``epoch_end()`` is ``scheduler.step()``;
+    ``evaluate(data, target)`` is the body of ``validate`` (``model.eval()``).  Data parallel: as for ``UNetTrainer`` the flat
+    gradient buffer is all-reduced over the process group before the optimizer step."""
+
+    def __init__(self, state_dict, batch_size: int = 64, learning_rate: float = 1e-3, step_size: int = 4, gamma: float = 0.1, device: int = 0,
+                 engine: "_native.Engine | None" = None, process_group=None, **train_options):
+        self.engine = engine if engine is not None else _native.Engine(device, max_batch=1)
+        self._own_engine = engine is None
+        self.engine.cls_train_create(state_dict, batch=batch_size, **train_options)
+        self.batch_size = batch_size
+        self.base_lr = learning_rate
+        self.step_size, self.gamma = step_size, gamma
+        self.epoch = 0
+        self.process_group = process_group
+        self._grads = self.engine.cls_train_grads()
+        self._int_keys = {k: v.clone() for k, v in state_dict.items() if torch.is_tensor(v) and not v.is_floating_point()}
+
+    @property
+    def learning_rate(self) -> float:
+        """StepLR: base_lr * gamma ** (epoch // step_size)."""
+        return self.base_lr * self.gamma ** (self.epoch // self.step_size)
+
+    def epoch_end(self):
+        self.epoch += 1
+
+    def _prep(self, data, target):
+        data = data.to(device=self.engine.device, dtype=torch.float32).contiguous()
+        target = target.to(device=self.engine.device, dtype=torch.int32).contiguous() if target is not None else None
+        return data, target
+
+    def step(self, data: torch.Tensor, target: torch.Tensor):
+        data, target = self._prep(data, target)
+        loss, correct = self.engine.cls_train_forward_backward(data, target)
+        scale = allreduce_gradients(self._grads, self.process_group)
+        self.engine.cls_train_optimizer_step(self.learning_rate, scale)
+        return loss, correct
+
+    def forward_backward(self, data, target):
+        data, target = self._prep(data, target)
+        return self.engine.cls_train_forward_backward(data, target)
+
+    def evaluate(self, data, target=None):
+        """``model.eval()`` forward: (logits [B,13], loss, correct)."""
+        data, target = self._prep(data, target)
+        return self.engine.cls_train_forward(data, target, training=False)
+
+    def gradients(self):
+        return self.engine.cls_train_export(1)
+
+    def state_dict(self):
+        """Parameters + BatchNorm buffers, CPU tensors in the layout ``utils.get_classifier_model().load_state_dict`` /
+        ``cvb_load_resnet18`` take (``num_batches_tracked`` counted up by the steps taken here)."""
+        sd = self.engine.cls_train_export(0)
+        steps = self.engine.cls_train_steps()
+        for k, v in self._int_keys.items():
+            sd[k] = v + steps if k.endswith("num_batches_tracked") else v
+        return sd
+
+    def optimizer_state_dict(self, names=None):
+        """torch.optim.Adam's ``state_dict()`` layout (``state``: index -> step / exp_avg / exp_avg_sq; one param group), so that
+        ``save_classifier_checkpoint`` (train_classifier.py:116-126) writes a checkpoint ``strip_optimizer`` understands."""
+        m, v = self.engine.cls_train_export(2), self.engine.cls_train_export(3)
+        names = list(names) if names is not None else [k for k in m if "running_" not in k]
+        step = torch.tensor(float(self.engine.cls_train_steps()))
+        state = {i: {"step": step.clone(), "exp_avg": m[k], "exp_avg_sq": v[k]} for i, k in enumerate(names)}
+        group = {"lr": self.learning_rate, "betas": (self.engine.cls_cfg.beta1, self.engine.cls_cfg.beta2), "eps": self.engine.cls_cfg.eps,
+                 "weight_decay": self.engine.cls_cfg.weight_decay, "amsgrad": False, "params": list(range(len(names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def close(self):
+        if self._own_engine:
+            self.engine.close()

@@ -633,6 +633,7 @@ void cvb_destroy(cvb_ctx* ctx) {
     if (ctx->s_comp) cudaStreamDestroy(ctx->s_comp);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->trainer) cvb_trainer_free(ctx->trainer);
+    if (ctx->cls_trainer) cvb_cls_trainer_free(ctx->cls_trainer);
     if (ctx->jpeg) cvb_jpeg_free(ctx->jpeg);
     for (void* q : {static_cast<void*>(ctx->gs_xofs), static_cast<void*>(ctx->gs_xsi), static_cast<void*>(ctx->gs_xa), static_cast<void*>(ctx->gs_yofs),
                     static_cast<void*>(ctx->gs_ysi), static_cast<void*>(ctx->gs_ya), static_cast<void*>(ctx->gs_small), static_cast<void*>(ctx->gs_big),

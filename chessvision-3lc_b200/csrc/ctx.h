@@ -14,6 +14,8 @@
 
 struct cvb_trainer;   // train.cu
 void cvb_trainer_free(cvb_trainer* t);
+struct cvb_cls_trainer;   // train_cls.cu
+void cvb_cls_trainer_free(cvb_cls_trainer* t);
 struct cvb_jpeg_state;   // jpeg.cu: staging buffers of the JPEG decode front-end
 void cvb_jpeg_free(cvb_jpeg_state* s);
 
@@ -98,6 +100,7 @@ struct cvb_ctx {
 
     // ---- UNet training step (train.cu); owned, destroyed with the context
     cvb_trainer* trainer = nullptr;
+    cvb_cls_trainer* cls_trainer = nullptr;            // piece-classifier training step (train_cls.cu); owned
     cvb_jpeg_state* jpeg = nullptr;
 
     // ---- CUDA graphs of single-chunk pipeline passes (the latency path: process_image on one board is ~50 launches)

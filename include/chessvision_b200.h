@@ -189,6 +189,41 @@ CVB_API int cvb_wgrad3x3_f16(cvb_ctx* ctx, const void* dz, const void* x, int N,
                              float* dw, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
+ * Piece-classifier training step (reference scripts/train/train_classifier.py:63-126,218-221):
+ * timm resnet18(num_classes=13, in_chans=1) on 64x64 squares, CrossEntropyLoss, torch.optim.Adam; fp32 throughout, BatchNorm
+ * with batch statistics in training mode and running statistics in eval mode (the validation loop, :91-113).
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct cvb_cls_train_config {
+    int32_t batch;        /* squares per step on this GPU (fixed at creation)                    */
+    float beta1, beta2;   /* Adam (0.9, 0.999), eps 1e-8, weight_decay 0: torch.optim.Adam's defaults, train_classifier.py:219 */
+    float eps;
+    float weight_decay;
+    float bn_momentum;    /* nn.BatchNorm2d defaults 0.1 / 1e-5                                   */
+    float bn_eps;
+} cvb_cls_train_config;
+
+CVB_API int cvb_cls_train_default_config(cvb_cls_train_config* cfg);
+/* Model + optimizer state from a state_dict (the tensors cvb_load_resnet18 takes); cfg NULL = defaults with batch 64. */
+CVB_API int cvb_cls_train_create(cvb_ctx* ctx, const cvb_tensor* state_dict, int n_tensors, const cvb_cls_train_config* cfg);
+/* output = model(data) [+ loss, number of correct predictions]: data fp32 [B,1,64,64], target i32 [B] (may be NULL: no loss),
+ * training != 0 = model.train() (batch statistics, running statistics updated), 0 = model.eval().  loss (1 float), correct
+ * (1 int32), logits ([B,13]) are device pointers and may be NULL. */
+CVB_API int cvb_cls_train_forward(cvb_ctx* ctx, const float* data, const int32_t* target, int training, float* loss, int32_t* correct,
+                                  float* logits, void* stream);
+/* forward in training mode + loss.backward() (train_classifier.py:77-80): the gradients land in the flat buffer below. */
+CVB_API int cvb_cls_train_forward_backward(cvb_ctx* ctx, const float* data, const int32_t* target, float* loss, int32_t* correct, void* stream);
+/* The flat fp32 gradient buffer (for a data-parallel all-reduce; conv weights are stored [co][r][q][ci]). */
+CVB_API int cvb_cls_train_grads(cvb_ctx* ctx, float** grads, int64_t* count);
+/* optimizer.step() (Adam) on grads * grad_scale with learning rate lr (the caller applies StepLR, train_classifier.py:220). */
+CVB_API int cvb_cls_train_optimizer_step(cvb_ctx* ctx, float lr, float grad_scale, void* stream);
+/* forward_backward + optimizer_step(grad_scale 1): the body of the reference's loop for one batch. */
+CVB_API int cvb_cls_train_step(cvb_ctx* ctx, const float* data, const int32_t* target, float lr, float* loss, int32_t* correct, void* stream);
+/* what = 0: parameters + BatchNorm running statistics, 1: gradients, 2 / 3: Adam exp_avg / exp_avg_sq -- in torch state_dict
+ * layout; out[i].name / shape select the tensor, out[i].data must point to WRITABLE host memory. */
+CVB_API int cvb_cls_train_export(cvb_ctx* ctx, int what, const cvb_tensor* out, int n_tensors);
+CVB_API int64_t cvb_cls_train_steps(const cvb_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------------------------
  * Consumers of the per-board outputs, computed on the device buffers the pipeline wrote.
  * ------------------------------------------------------------------------------------------------------------------- */
 /* scripts/eval/evaluate.py:37-52,109-140 for N boards.  probs f32 [N,64,13]; labels / labels_valid u8 [N,64] (either may
