@@ -74,6 +74,11 @@ def test_product_path_fails_loudly_without_gpu():
         cvm.process_image(np.zeros((512, 512, 3), np.uint8))
     with pytest.raises(_native.NativeError):
         ChessVision._find_quadrangle(np.zeros((256, 256), np.uint8))
+    from chessvision.training import ClassifierTrainer, UNetTrainer
+    with pytest.raises(_native.NativeError):
+        ClassifierTrainer({}, batch_size=4)
+    with pytest.raises(_native.NativeError):
+        UNetTrainer({}, batch_size=1)
 
 
 def test_product_package_never_imports_the_oracle():
