@@ -16,7 +16,15 @@ pytestmark = pytest.mark.gpu
 FILES = sorted((GOLDEN / "data_test").glob("*/*"))
 
 
-def test_data_test_images_byte_identical(engine):
+@pytest.fixture(params=["host", "device"])
+def huffman_path(request, monkeypatch):
+    """Entropy decoding on the host threads (small batches) or on the device (one warp per image; batches >= 256 by default):
+    CVB_JPEG_DEVICE_MIN forces either for any batch size."""
+    monkeypatch.setenv("CVB_JPEG_DEVICE_MIN", "1" if request.param == "device" else "0")
+    return request.param
+
+
+def test_data_test_images_byte_identical(engine, huffman_path):
     man = {e["file"]: e["image_sha1"] for e in json.load(open(GOLDEN / "manifest.json"))["images"]}
     streams = [f.read_bytes() for f in FILES]
     got = engine.decode_jpeg(streams).cpu().numpy()
@@ -28,7 +36,7 @@ def test_data_test_images_byte_identical(engine):
 
 @pytest.mark.parametrize("h,w,quality,rst,n", [(16, 16, 90, 0, 3), (48, 32, 50, 0, 5), (512, 512, 100, 0, 2), (768, 1024, 75, 7, 2),
                                                (64, 64, 10, 1, 70), (256, 256, 95, 16, 9)])
-def test_reencoded_synthetic_images(engine, h, w, quality, rst, n):
+def test_reencoded_synthetic_images(engine, huffman_path, h, w, quality, rst, n):
     rng = np.random.default_rng(h * 7 + w + quality)
     streams, want = [], []
     for i in range(n):
@@ -72,3 +80,43 @@ def test_decode_then_image_to_fen_equals_the_cv2_front_end():
         if a.position is not None:
             assert a.position.fen == b.position.fen and a.position.original_fen == b.position.original_fen
         assert np.array_equal(a.board_extraction.binary_mask, b.board_extraction.binary_mask)
+
+
+def test_device_huffman_equals_host_huffman_on_damaged_streams(engine, monkeypatch):
+    """Truncated and bit-flipped entropy-coded segments: the device decoder takes the same decisions as the host decoder
+    (same pixels, or both refuse the batch), and a large batch takes the device path by default."""
+    from chessvision import _native
+    rng = np.random.default_rng(3)
+    base = [f.read_bytes() for f in FILES[:8]]
+    streams = []
+    for k in range(48):
+        b = bytearray(base[k % len(base)])
+        if k % 3 == 0:
+            b = b[: len(b) - int(rng.integers(1, len(b) // 2))]                  # cut inside the scan
+        else:
+            start = len(b) // 3
+            for _ in range(int(rng.integers(1, 6))):
+                i = int(rng.integers(start, len(b) - 2))
+                b[i] ^= 1 << int(rng.integers(0, 8))
+        streams.append(bytes(b))
+
+    def run(mode, items):
+        monkeypatch.setenv("CVB_JPEG_DEVICE_MIN", mode)
+        try:
+            return engine.decode_jpeg(items).cpu().numpy()
+        except _native.NativeError:
+            return None
+
+    agree = 0
+    for s_ in streams:
+        host, dev = run("0", [s_]), run("1", [s_])
+        assert (host is None) == (dev is None)
+        if host is not None:
+            assert np.array_equal(host, dev)
+            agree += 1
+    assert agree > 0
+    monkeypatch.delenv("CVB_JPEG_DEVICE_MIN")
+    many = [base[i % len(base)] for i in range(300)]                             # >= 256: device path by default
+    got = engine.decode_jpeg(many).cpu().numpy()
+    for i in (0, 7, 299):
+        assert np.array_equal(got[i], cv2.imdecode(np.frombuffer(many[i], np.uint8), cv2.IMREAD_COLOR))
