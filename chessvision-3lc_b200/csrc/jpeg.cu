@@ -551,12 +551,12 @@ __global__ void __launch_bounds__(kHuffWarps * 32) k_jpeg_huffman(const uint8_t*
     br.acc = 0;
     br.bits = 0;
     const int restart = meta[img].restart;
-    int pred[3] = {0, 0, 0};
+    int pred0 = 0, pred1 = 0, pred2 = 0;   // scalars: an array indexed by the component would live in local memory
     int bad = 0;
     for (int mcu = 0; mcu < mh * mw && !bad; ++mcu) {
         if (lane == 0 && restart && mcu && mcu % restart == 0) {
             br.restart();
-            pred[0] = pred[1] = pred[2] = 0;
+            pred0 = pred1 = pred2 = 0;
         }
         const int my = mcu / mw, mx = mcu - my * mw;
         for (int b = 0; b < 6 && !bad; ++b) {
@@ -570,11 +570,16 @@ __global__ void __launch_bounds__(kHuffWarps * 32) k_jpeg_huffman(const uint8_t*
                 if (s < 0 || s > 15) {
                     bad = 1;
                 } else {
+                    int diff = 0;
                     if (s) {
                         const int v = static_cast<int>(br.get(s));
-                        pred[c] += v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+                        diff = v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
                     }
-                    out[0] = static_cast<int16_t>(pred[c]);
+                    int dcv;
+                    if (c == 0) dcv = (pred0 += diff);
+                    else if (c == 1) dcv = (pred1 += diff);
+                    else dcv = (pred2 += diff);
+                    out[0] = static_cast<int16_t>(dcv);
                     for (int k = 1; k < 64;) {
                         if (br.bits < 32) br.refill();
                         const int rs = dev_decode_symbol(br, act);
@@ -673,11 +678,13 @@ int cvb_jpeg_coefficients(const uint8_t* data, int64_t nbytes, int16_t* coef, ui
     return cvb::decode_scan(data, static_cast<size_t>(nbytes), H, coef);
 }
 
-// Batches of at least this many images are entropy-decoded on the device (one warp per image: ~15 ms for any batch that fits
-// the GPU, against ~1.2 ms per image and host thread); CVB_JPEG_DEVICE_MIN overrides (1 = always, 0 = never).
+// Batches of at least this many images are entropy-decoded on the device.  One warp per image walks ~120 k symbols at ~540
+// clocks each (a single dependent instruction chain: ncu, profiles/README.md), i.e. ~50 ms for ANY batch that fits the GPU's
+// 9,472 warp slots, against ~1.2 ms per image and host thread: the device wins from about a thousand images per call.
+// CVB_JPEG_DEVICE_MIN overrides (1 = always, 0 = never).
 static int jpeg_device_min() {
     const char* e = getenv("CVB_JPEG_DEVICE_MIN");
-    if (!e) return 256;
+    if (!e) return 1024;
     const int v = atoi(e);
     return v <= 0 ? 0x7fffffff : v;
 }
@@ -704,7 +711,7 @@ static void run_threads(int n, const std::function<void(int)>& fn) {
 // Device path of cvb_decode_jpeg: the host only parses the headers, derives the Huffman tables and packs the entropy-coded
 // segments; k_jpeg_huffman produces the coefficients the two existing kernels consume.
 static int decode_jpeg_device(cvb_ctx* ctx, const uint8_t* const* data, const int64_t* nbytes, int N, int H, int W, uint8_t* img, cudaStream_t s) {
-    constexpr int kChunk = 1024;
+    constexpr int kChunk = 4096;
     const size_t px = static_cast<size_t>(H) * W;
     const size_t coef_per_image = px * 3 / 2;
     if (!ctx->jpeg) ctx->jpeg = new cvb_jpeg_state();

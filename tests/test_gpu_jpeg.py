@@ -18,7 +18,7 @@ FILES = sorted((GOLDEN / "data_test").glob("*/*"))
 
 @pytest.fixture(params=["host", "device"])
 def huffman_path(request, monkeypatch):
-    """Entropy decoding on the host threads (small batches) or on the device (one warp per image; batches >= 256 by default):
+    """Entropy decoding on the host threads (small batches) or on the device (one warp per image; batches >= 1024 by default):
     CVB_JPEG_DEVICE_MIN forces either for any batch size."""
     monkeypatch.setenv("CVB_JPEG_DEVICE_MIN", "1" if request.param == "device" else "0")
     return request.param
@@ -116,7 +116,7 @@ def test_device_huffman_equals_host_huffman_on_damaged_streams(engine, monkeypat
             agree += 1
     assert agree > 0
     monkeypatch.delenv("CVB_JPEG_DEVICE_MIN")
-    many = [base[i % len(base)] for i in range(300)]                             # >= 256: device path by default
+    many = [base[i % len(base)] for i in range(1100)]                            # >= 1024: device path by default
     got = engine.decode_jpeg(many).cpu().numpy()
-    for i in (0, 7, 299):
+    for i in (0, 7, 1099):
         assert np.array_equal(got[i], cv2.imdecode(np.frombuffer(many[i], np.uint8), cv2.IMREAD_COLOR))
