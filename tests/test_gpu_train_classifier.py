@@ -185,7 +185,7 @@ def test_ten_step_trajectory_with_steplr(start_state):
             l = F.cross_entropy(ref(data.cuda()), target.cuda())
             l.backward()
             opt.step()
-            theirs.append(float(l))
+            theirs.append(float(l.detach()))
             loss, _ = tr.step(data, target)
             ours.append(float(loss))
             if step % 2 == 1:          # an "epoch" of two batches
