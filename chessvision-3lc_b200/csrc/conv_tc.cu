@@ -95,11 +95,15 @@ __device__ __forceinline__ void pack_chunk(const uint32_t (&v)[32], const float*
 //   layout and written by one TMA tile store (full 128-byte lines; the pixel-shuffle of the transposed convolution is a
 //   strided output view per (dy,dx)).  EPI_OUTC: fused 1x1 head, one logit + mask byte per pixel.
 //   The TMEM load of chunk c+1 is in flight while chunk c is processed.
-template <int BLOCK_N, int EPI>
+// COLS / col_base / bar_id: an epilogue group of four warps may own only the columns [col_base, col_base + COLS) of the tile
+// (taddr, s_out and s_out_addr then point at that group's columns / staging buffer, bar_id is its named barrier).
+template <int BLOCK_N, int EPI, int COLS = BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr, int row, int n0, int h0, int w0, int n, int h, int w,
                                               bool valid, int n_tile, const float* s_bias, const float* s_outw, uint8_t* s_out,
-                                              uint32_t s_out_addr, int& store_count, int etid, const uint32_t (&res0)[32]) {
-    constexpr int NC = BLOCK_N / 32;
+                                              uint32_t s_out_addr, int& store_count, int etid, const uint32_t (&res0)[32], int col_base = 0,
+                                              int bar_id = 1) {
+    constexpr int NC = COLS / 32;
+    s_bias += col_base;
     const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
     uint32_t va[32], vb[32];
     tmem_ld_32x32(taddr, va);
@@ -138,7 +142,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
     } else {
         const bool relu = p.relu != 0;
         const bool has_res = EPI == EPI_STORE && p.res != nullptr && valid;
-        const __half* res_px = has_res ? p.res + pix * p.res_c_stride + n_tile * BLOCK_N : nullptr;
+        const __half* res_px = has_res ? p.res + pix * p.res_c_stride + n_tile * BLOCK_N + col_base : nullptr;
         uint32_t rcur[32], rnext[32];
         if (has_res) {
 #pragma unroll
@@ -146,7 +150,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
         }
 #pragma unroll
         for (int c = 0; c < NC; c += 2) {
-            const int col0 = n_tile * BLOCK_N + c * 32;   // first of the 64 columns of this store group
+            const int col0 = n_tile * BLOCK_N + col_base + c * 32;   // first of the 64 columns of this store group
             if (c + 2 < NC && has_res) res_load64(res_px + (c + 2) * 32, rnext);   // one group ahead
             uint32_t o[32];
             tmem_ld_wait(va);
@@ -183,13 +187,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
             if (etid == 0) {
                 if (p.out_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(bar_id, 128);
             uint8_t* dst = s_out + buf * kOutBufBytes + row * 128;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 *reinterpret_cast<uint4*>(dst + ((j ^ (row & 7)) << 4)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(bar_id, 128);
             if (etid == 0) {
                 if constexpr (EPI == EPI_CONVT) {
                     const int q = col0 / p.convt_cout;
@@ -693,16 +697,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_kernel(const __gr
 // shared memory instead of 4 + 4.  Barriers the leader's MMA warp waits on (afull, bfull, a2full, tempty) live in the leader
 // and are signalled by both CTAs; barriers the two CTAs' producers / epilogues wait on are signalled by multicast commits.
 // ---------------------------------------------------------------------------------------------------------------------
+template <int SA_, int SB_>
 struct FusedPairCfg {
-    static constexpr int kAStages = 3, kBStages = 16;
+    static constexpr int kAStages = SA_, kBStages = SB_;
     static constexpr int kABytes = 18 * 1024, kBBytes = 64 * 128;
     static constexpr int kA2Bytes = 2 * 128 * 128;
     static constexpr int kBarBytes = 512;
     static constexpr int kSmemBytes = kAStages * kABytes + kBStages * kBBytes + kA2Bytes + 1024 + kBarBytes + (128 + 64) * 4;
 };
 
+template <int SA_, int SB_>
 __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_pair_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = FusedPairCfg;
+    using Cfg = FusedPairCfg<SA_, SB_>;
     constexpr int SA = Cfg::kAStages, SB = Cfg::kBStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
@@ -967,8 +973,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) conv_convt_pair_kernel(const
 // (9*Cin*Cout*2 B) fit beside the pipeline they are loaded once per CTA and stay in shared memory.
 // L2->SM bytes per 128x64 output tile, Cin = 64:  generic 216 KB  ->  54 KB.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BLOCK_N, int EPI, bool W_STAT, int PAIR = 0>
-__global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constant__ ConvParams p) {
+// EPG = 2 (N = 128): two epilogue groups of four warps, each draining 64 of the 128 columns of every tile through its own
+// staging buffer.  With a short K loop (Cin <= 128) one group cannot drain a 128-column tile in the time the MMAs need for
+// the next one (3,360 clocks per tile against 2,304 of MMA work at Cin = 64; 6,700 with the fused max-pool at Cin = 128).
+template <int BLOCK_N, int EPI, bool W_STAT, int PAIR = 0, int EPG = 1>
+__global__ void __launch_bounds__(128 + 128 * EPG, 1) conv3x3_vr_kernel(const __grid_constant__ ConvParams p) {
     // PAIR = 1: CTA pair (cta_group::2, see conv_tc_kernel): two 16 x 8 output tiles per MMA, each CTA holds half of every
     // weight tile (BLOCK_N / 2 rows), so an MMA reads 4 KB of A + 2 KB of B per SM instead of 4 + 4 (the N = 128 layers are
     // bound by exactly that shared-memory operand bandwidth) and twice the input channels fit as resident weights.
@@ -988,7 +997,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
     const uint32_t w_bytes = W_STAT ? 9u * p.c_chunks * kBBytes : 0u;
     const uint32_t stages_addr = base_addr + w_bytes;
     uint8_t* s_out = base_ptr + w_bytes + S * kStageBytes;
-    const uint32_t out_bytes = EPI == EPI_OUTC ? 0u : static_cast<uint32_t>(kOutBufBytes);
+    const uint32_t out_bytes = EPI == EPI_OUTC ? 0u : static_cast<uint32_t>(EPG * kOutBufBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + out_bytes);
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * S;
@@ -1014,7 +1023,7 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
         }
         for (int i = 0; i < kAcc; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, PAIR ? 2 : 128);
+            mbar_init(bar_tempty + 8 * i, PAIR ? 2 * EPG : 128 * EPG);
         }
         mbar_init(bar_w, 1);
         mbar_fence_init();
@@ -1146,6 +1155,8 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
         __syncwarp();
     } else if (warp >= 4) {
         const int quarter = warp & 3;
+        const int g = EPG == 2 ? (warp - 4) >> 2 : 0;          // epilogue group: columns [64 g, 64 g + 64) when there are two
+        const int etid = (threadIdx.x - 128) & 127;
         const int row = quarter * 32 + lane;
         const int rh = row >> 3, rw = row & 7;
         float* s_bias = reinterpret_cast<float*>(s_out + out_bytes + 256);
@@ -1159,7 +1170,13 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             const int n_tile = t % p.n_tiles;
             const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             if (n_tile != cur_nt) {
-                epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
+                if constexpr (EPG == 2) {   // both groups share the per-column constants
+                    named_bar_sync(3, 256);
+                    for (int i = threadIdx.x - 128; i < BLOCK_N; i += 256) s_bias[i] = __ldg(p.bias + n_tile * BLOCK_N + i);
+                    named_bar_sync(3, 256);
+                } else {
+                    epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
+                }
                 cur_nt = n_tile;
             }
             const int w = (m_tile % p.tiles_w) * 8 + rw;
@@ -1167,21 +1184,25 @@ __global__ void __launch_bounds__(256, 1) conv3x3_vr_kernel(const __grid_constan
             const int n = m_tile / (p.tiles_w * p.tiles_h);
             uint32_t res0[32];
             if (EPI == EPI_STORE && p.res != nullptr && n < p.N)
-                res_load64(p.res + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.res_c_stride + n_tile * BLOCK_N, res0);
+                res_load64(p.res + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.res_c_stride + n_tile * BLOCK_N + 64 * g, res0);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n, h - rh, w - rw, n, h, w, n < p.N, n_tile, s_bias, s_outw, s_out,
-                                        stages_addr + S * kStageBytes, store_count, threadIdx.x - 128, res0);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + 64 * g;
+            if constexpr (EPG == 2)
+                epilogue_tile<BLOCK_N, EPI, 64>(p, taddr, row, n, h - rh, w - rw, n, h, w, n < p.N, n_tile, s_bias, s_outw, s_out + g * kOutBufBytes,
+                                                stages_addr + S * kStageBytes + g * kOutBufBytes, store_count, etid, res0, 64 * g, 1 + g);
+            else
+                epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n, h - rh, w - rw, n, h, w, n < p.N, n_tile, s_bias, s_outw, s_out,
+                                            stages_addr + S * kStageBytes, store_count, etid, res0);
             tc_fence_before();
             if constexpr (PAIR) {
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 128) mbar_arrive_cluster(tempty_sig + 8 * acc);
+                named_bar_sync(1 + g, 128);
+                if (etid == 0) mbar_arrive_cluster(tempty_sig + 8 * acc);
             } else {
                 mbar_arrive(bar_tempty + 8 * acc);
             }
         }
-        if (threadIdx.x == 128) bulk_wait_all();
+        if (etid == 0) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -1833,7 +1854,8 @@ cudaError_t conv_configure() {
     if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::kSmemBytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(conv_convt_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedPairCfg::kSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_convt_pair_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedPairCfg<3, 16>::kSmemBytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv_convt_pair_kernel<4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedPairCfg<4, 12>::kSmemBytes)) != cudaSuccess) return e;
     {
         const char* off = getenv("CVB_NO_PAIR");
         g_pair_clusters = off && off[0] == '1' ? 0 : 1 << 20;
@@ -1853,6 +1875,10 @@ cudaError_t conv_configure() {
     if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<256, EPI_STORE, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, true, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(conv3x3_vr_kernel<128, EPI_STORE, false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv3x3_rs_kernel<EPI_STORE, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kVrMaxSmem)) != cudaSuccess) return e;
@@ -1885,13 +1911,22 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     // N = 128 with a plain store: CTA pairs (half of each weight tile per CTA); CVB_NO_PAIR_VR=1 keeps the single-CTA form
     const char* no_pair = getenv("CVB_NO_PAIR_VR");
     const char* min_cc = getenv("CVB_PAIR_VR_MIN_CC");   // A/B: pair form only from this many 64-channel input chunks up
+    const char* epg2_ = getenv("CVB_VR_EPG2");
+    const bool groups2 = L.block_n == 128 && L.epilogue == EPI_STORE && Cin <= 128 && epg2_ && epg2_[0] == '1';
     const bool pair = wide || (g_pair_clusters > 0 && L.block_n == 128 && L.epilogue == EPI_STORE && !(no_pair && no_pair[0] == '1') &&
-                               Cin / 64 >= (min_cc ? atoi(min_cc) : 2));
+                               Cin / 64 >= (min_cc ? atoi(min_cc) : (groups2 ? 1 : 2)));
     const int b_bytes = L.block_n * 128 / (pair ? 2 : 1);
     const int w_bytes = 9 * (Cin / 64) * b_bytes;
-    const int out_bytes = L.epilogue == EPI_OUTC ? 0 : kOutBufBytes;
+    // CVB_VR_EPG2=1 (A/B only): two epilogue groups for N = 128 with at most two input chunks.  Measured (profiles/README.md,
+    // round 2): no gain -- down1.conv3 539 -> 526 us, and down1.conv0, which then has to run as a pair to fit the second
+    // staging buffer, 280 -> 348 us: the epilogue is not what holds these layers at 69 % tensor activity.
+    const bool two_groups = groups2;
+    const int out_bytes = L.epilogue == EPI_OUTC ? 0 : (two_groups ? 2 : 1) * kOutBufBytes;
     const int budget = kVrMaxSmem - 1024 - 256 - kEpiConstBytes - out_bytes;
-    const bool ws = !wide && p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
+    // A/B: CVB_VR_PAIR_STREAM=1 streams the weights of a pair launch even when their halves would fit resident (resident
+    // weights leave room for only three activation stages when Cin = 128)
+    const char* pstream = getenv("CVB_VR_PAIR_STREAM");
+    const bool ws = !wide && !(pair && pstream && pstream[0] == '1') && p.n_tiles == 1 && w_bytes + 3 * 18 * 1024 <= budget;
     if (L.epilogue == EPI_OUTC && !ws) return false;
     const int stage = 18 * 1024 + (ws ? 0 : 3 * b_bytes);
     int stages = (budget - (ws ? w_bytes : 0)) / stage;
@@ -1906,6 +1941,7 @@ bool conv_try_vr(ConvLaunch& L, int ksize, int stride, int Ho, int Wo, int Cin) 
     p.tiles_h = Ho / 16;
     L.variant = 1;
     L.pair = pair ? 1 : 0;
+    L.vr_epg = two_groups ? 2 : 1;
     return true;
 }
 
@@ -1948,9 +1984,9 @@ template <int BN, int EPI, bool WS>
 static cudaError_t launch_vr(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
     return launch_k(conv3x3_vr_kernel<BN, EPI, WS>, grid, 256, p.smem_bytes, s, pdl, p);
 }
-template <int BN, bool WS>
+template <int BN, bool WS, int EPG = 1>
 static cudaError_t launch_vr_pair(const ConvParams& p, int clusters, cudaStream_t s, bool pdl) {
-    return launch_kc(conv3x3_vr_kernel<BN, EPI_STORE, WS, 1>, 2 * clusters, 256, p.smem_bytes, s, pdl, 2, p);
+    return launch_kc(conv3x3_vr_kernel<BN, EPI_STORE, WS, 1, EPG>, 2 * clusters, 128 + 128 * EPG, p.smem_bytes, s, pdl, 2, p);
 }
 
 cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t stream) {
@@ -1968,7 +2004,9 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
             if (g_pair_clusters <= 0) return cudaErrorInvalidValue;
             const long long units = (total + 1) / 2;
             const int clusters = (int)(units < g_pair_clusters ? units : g_pair_clusters);
-            return launch_kc(conv_convt_pair_kernel, 2 * clusters, kFusedThreads, FusedPairCfg::kSmemBytes, stream, pdl, 2, p);
+            static const bool deep_a = [] { const char* e = getenv("CVB_CONVT_DEEP_A"); return e && e[0] == '1'; }();   // A/B: 4 activation stages + 12 weight tiles
+            if (deep_a) return launch_kc(conv_convt_pair_kernel<4, 12>, 2 * clusters, kFusedThreads, FusedPairCfg<4, 12>::kSmemBytes, stream, pdl, 2, p);
+            return launch_kc(conv_convt_pair_kernel<3, 16>, 2 * clusters, kFusedThreads, FusedPairCfg<3, 16>::kSmemBytes, stream, pdl, 2, p);
         }
         return launch_k(conv_convt_kernel, grid, kFusedThreads, FusedCfg::kSmemBytes, stream, pdl, p);
     }
@@ -1993,12 +2031,16 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
         const int clusters = (int)(units < g_pair_clusters ? units : g_pair_clusters);
         p.idesc = umma_idesc_f16(256, L.block_n, 0);
         if (L.block_n == 256) return p.w_stationary ? cudaErrorInvalidValue : launch_vr_pair<256, false>(p, clusters, stream, pdl);
+        if (L.vr_epg == 2) return p.w_stationary ? launch_vr_pair<128, true, 2>(p, clusters, stream, pdl) : launch_vr_pair<128, false, 2>(p, clusters, stream, pdl);
         return p.w_stationary ? launch_vr_pair<128, true>(p, clusters, stream, pdl) : launch_vr_pair<128, false>(p, clusters, stream, pdl);
     }
     if (L.variant == 1) {
         const bool ws = p.w_stationary != 0;
         if (L.epilogue == EPI_OUTC) return launch_vr<64, EPI_OUTC, true>(p, grid, stream, pdl);
         if (L.block_n == 64) return ws ? launch_vr<64, EPI_STORE, true>(p, grid, stream, pdl) : launch_vr<64, EPI_STORE, false>(p, grid, stream, pdl);
+        if (L.vr_epg == 2)
+            return ws ? launch_k(conv3x3_vr_kernel<128, EPI_STORE, true, 0, 2>, grid, 384, p.smem_bytes, stream, pdl, p)
+                      : launch_k(conv3x3_vr_kernel<128, EPI_STORE, false, 0, 2>, grid, 384, p.smem_bytes, stream, pdl, p);
         return ws ? launch_vr<128, EPI_STORE, true>(p, grid, stream, pdl) : launch_vr<128, EPI_STORE, false>(p, grid, stream, pdl);
     }
     if (L.pair) {
