@@ -221,8 +221,10 @@ __device__ __forceinline__ void epilogue_consts(const ConvParams& p, int n_tile,
     named_bar_sync(1, 128);
 }
 
-template <int BLOCK_N, int EPI, int PAIR = 0>
-__global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+// EPG = 2: two epilogue groups of four warps, each draining half of the tile's columns through its own staging buffer (for
+// launches whose K loop is shorter than the epilogue of a whole tile: transposed convolutions, 1x1 downsamples).
+template <int BLOCK_N, int EPI, int PAIR = 0, int EPG = 1>
+__global__ void __launch_bounds__(128 + 128 * EPG, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
     using Cfg = ConvCfg<BLOCK_N, PAIR>;
     constexpr int S = Cfg::kStages;
 
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         }
         for (int i = 0; i < kAcc; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, PAIR ? 2 : 128);   // pair: one arrival per CTA (its epilogue warps sync first)
+            mbar_init(bar_tempty + 8 * i, PAIR ? 2 * EPG : 128 * EPG);   // pair: one arrival per CTA and group (its warps sync first)
         }
         mbar_fence_init();
     }
@@ -358,6 +360,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
         __syncwarp();
     } else if (warp >= 4) {
         const int quarter = warp & 3;
+        const int g = EPG == 2 ? (warp - 4) >> 2 : 0;          // epilogue group: columns [g * BLOCK_N / 2, (g + 1) * BLOCK_N / 2) when there are two
+        constexpr int kGroupCols = BLOCK_N / EPG;
+        const int etid = (threadIdx.x - 128) & 127;
         const int row = quarter * 32 + lane;
         const int rn = row / (p.th * p.tw);
         const int rh = (row / p.tw) % p.th;
@@ -373,7 +378,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             const int n_tile = t % p.n_tiles;
             const int m_tile = PAIR ? 2 * (t / p.n_tiles) + static_cast<int>(rank) : t / p.n_tiles;
             if (n_tile != cur_nt) {
-                epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
+                if constexpr (EPG == 2) {   // both groups share the per-column constants
+                    named_bar_sync(3, 256);
+                    for (int i = threadIdx.x - 128; i < BLOCK_N; i += 256)
+                        s_bias[i] = __ldg(p.bias + (EPI == EPI_CONVT ? (n_tile * BLOCK_N + i) % p.convt_cout : n_tile * BLOCK_N + i));
+                    named_bar_sync(3, 256);
+                } else {
+                    epilogue_consts<BLOCK_N, EPI>(p, n_tile, s_bias, s_outw, threadIdx.x - 128);
+                }
                 cur_nt = n_tile;
             }
             const int w = (m_tile % p.tiles_w) * p.tw + rw;
@@ -382,21 +394,26 @@ __global__ void __launch_bounds__(256, 1) conv_tc_kernel(const __grid_constant__
             const bool valid = n < p.N;
             uint32_t res0[32];   // first 64 residual channels of this pixel, requested before the accumulator is waited for
             if (EPI == EPI_STORE && p.res != nullptr && valid)
-                res_load64(p.res + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.res_c_stride + n_tile * BLOCK_N, res0);
+                res_load64(p.res + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.res_c_stride + n_tile * BLOCK_N + g * kGroupCols, res0);
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-            epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n - rn, h - rh, w - rw, n, h, w, valid, n_tile, s_bias, s_outw, s_out,
-                                        tiles_addr + S * Cfg::kStageBytes, store_count, threadIdx.x - 128, res0);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + g * kGroupCols;
+            if constexpr (EPG == 2)
+                epilogue_tile<BLOCK_N, EPI, kGroupCols>(p, taddr, row, n - rn, h - rh, w - rw, n, h, w, valid, n_tile, s_bias, s_outw,
+                                                        s_out + g * kOutBufBytes, tiles_addr + S * Cfg::kStageBytes + g * kOutBufBytes, store_count, etid,
+                                                        res0, g * kGroupCols, 1 + g);
+            else
+                epilogue_tile<BLOCK_N, EPI>(p, taddr, row, n - rn, h - rh, w - rw, n, h, w, valid, n_tile, s_bias, s_outw, s_out,
+                                            tiles_addr + S * Cfg::kStageBytes, store_count, etid, res0);
             tc_fence_before();
             if constexpr (PAIR) {
-                named_bar_sync(1, 128);   // all four warps have read their lanes of the accumulator
-                if (threadIdx.x == 128) mbar_arrive_cluster(tempty_sig + 8 * acc);
+                named_bar_sync(1 + g, 128);   // all four warps have read their lanes of the accumulator
+                if (etid == 0) mbar_arrive_cluster(tempty_sig + 8 * acc);
             } else {
                 mbar_arrive(bar_tempty + 8 * acc);
             }
         }
-        if (threadIdx.x == 128) bulk_wait_all();   // the staged tiles must have left shared memory before the CTA exits
+        if (etid == 0) bulk_wait_all();   // the staged tiles must have left shared memory before the CTA exits
     }
 
     tc_fence_before();
@@ -1705,6 +1722,14 @@ int conv_build(ConvLaunch& L, const __half* in, int Nmax, int Hin, int Win, int 
 // Generic kernel, BLOCK_N = 128 / 256, plain or transposed-conv store: run it as CTA pairs (each CTA then loads half of the
 // weight tile: the weight view gets a box of BLOCK_N / 2 rows).
 int conv_try_pair(ConvLaunch& L, const __half* w, int K, int rows) {
+    // generic kernel, N >= 128, at most four K steps (up3.up, the 1x1 downsamples): two epilogue groups, each with one of the
+    // two staging buffers.  Measured per 148 boards: up3.up 205 -> 190 us, layer2 downsample 52 -> 45 us; with 8 or 9 K steps
+    // (up2.up, layer2.0.conv1) it is 2-3 % slower, so the bound is 4.  CVB_EPG2=0 turns it off, CVB_EPG2_MAX_K sets the bound.
+    if (L.variant == 0 && (L.block_n == 128 || L.block_n == 256) && (L.epilogue == EPI_STORE || L.epilogue == EPI_CONVT)) {
+        const char* off = getenv("CVB_EPG2");
+        const char* mk = getenv("CVB_EPG2_MAX_K");
+        if (!(off && off[0] == '0') && L.p.taps * L.p.c_chunks <= (mk ? atoi(mk) : 4)) L.epg = 2;
+    }
     if (g_pair_clusters <= 0 || L.variant != 0 || (L.block_n != 128 && L.block_n != 256)) return 0;
     if (L.epilogue != EPI_STORE && L.epilogue != EPI_CONVT) return 0;
     // Measured (profiles/README.md, round 2): the pair form wins 7-14 % on N = 256 tiles with long K loops and loses on short
@@ -1772,7 +1797,7 @@ int conv_set_store(ConvLaunch& L, __half* out, int out_c_stride, int out_c_off, 
         p.out_bufs = 0;
         return 0;
     }
-    if (L.variant == 0) p.out_bufs = 2;
+    if (L.variant == 0) p.out_bufs = L.epg == 2 ? 1 : 2;   // two groups: one of the two staging buffers each
     int rc = 0;
     const int64_t C = out_c_stride;
     if (L.epilogue == EPI_CONVT) {
@@ -1821,6 +1846,11 @@ static cudaError_t configure_one() {
 // CTA-pair form of the generic kernel: clusters of two CTAs.  g_pair_clusters = how many such clusters the device runs at once
 // (74 on a B200: one per TPC); 0 turns the pair form off (CVB_NO_PAIR=1, or a device that cannot co-schedule them).
 template <int BN, int EPI>
+static cudaError_t configure_epg2() {
+    return cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN>::kSmemBytes);
+}
+
+template <int BN, int EPI>
 static cudaError_t configure_pair() {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BN, 1>::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -1853,6 +1883,10 @@ cudaError_t conv_configure() {
     if ((e = configure_one<128, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = configure_one<64, EPI_OUTC>()) != cudaSuccess) return e;
+    if ((e = configure_epg2<128, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_epg2<256, EPI_STORE>()) != cudaSuccess) return e;
+    if ((e = configure_epg2<128, EPI_CONVT>()) != cudaSuccess) return e;
+    if ((e = configure_epg2<256, EPI_CONVT>()) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_convt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedCfg::kSmemBytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_convt_pair_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedPairCfg<3, 16>::kSmemBytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(conv_convt_pair_kernel<4, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedPairCfg<4, 12>::kSmemBytes)) != cudaSuccess) return e;
@@ -1891,6 +1925,10 @@ cudaError_t conv_configure() {
 template <int BN, int EPI>
 static cudaError_t launch_one(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
     return launch_k(conv_tc_kernel<BN, EPI>, grid, 256, ConvCfg<BN>::kSmemBytes, s, pdl, p);
+}
+template <int BN, int EPI>
+static cudaError_t launch_one_epg2(const ConvParams& p, int grid, cudaStream_t s, bool pdl) {
+    return launch_k(conv_tc_kernel<BN, EPI, 0, 2>, grid, 384, ConvCfg<BN>::kSmemBytes, s, pdl, p);
 }
 template <int BN, int EPI>
 static cudaError_t launch_pair(const ConvParams& p, int clusters, cudaStream_t s, bool pdl) {
@@ -2054,6 +2092,15 @@ cudaError_t conv_launch(ConvLaunch& L, int n_images, int sm_count, cudaStream_t 
             case EPI_STORE * 1000 + 256: return launch_pair<256, EPI_STORE>(p, clusters, stream, pdl);
             case EPI_CONVT * 1000 + 128: return launch_pair<128, EPI_CONVT>(p, clusters, stream, pdl);
             case EPI_CONVT * 1000 + 256: return launch_pair<256, EPI_CONVT>(p, clusters, stream, pdl);
+            default: return cudaErrorInvalidValue;
+        }
+    }
+    if (L.epg == 2) {
+        switch (L.epilogue * 1000 + L.block_n) {
+            case EPI_STORE * 1000 + 128: return launch_one_epg2<128, EPI_STORE>(p, grid, stream, pdl);
+            case EPI_STORE * 1000 + 256: return launch_one_epg2<256, EPI_STORE>(p, grid, stream, pdl);
+            case EPI_CONVT * 1000 + 128: return launch_one_epg2<128, EPI_CONVT>(p, grid, stream, pdl);
+            case EPI_CONVT * 1000 + 256: return launch_one_epg2<256, EPI_CONVT>(p, grid, stream, pdl);
             default: return cudaErrorInvalidValue;
         }
     }

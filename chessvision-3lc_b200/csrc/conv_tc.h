@@ -65,7 +65,8 @@ struct ConvLaunch {
     int epilogue;  // ConvEpilogue
     int variant;   // 0 generic kernel, 1 vertical-reuse 3x3 kernel, 2 row-streaming 3x3 kernel (Cout = 64)
     int n_max;     // images the activation / output views were built for
-    int vr_epg;    // vertical-reuse kernel: epilogue groups (2 for N = 128 with a short K loop)
+    int vr_epg;    // vertical-reuse kernel: epilogue groups (A/B switch)
+    int epg;       // generic kernel: epilogue groups (2 for N >= 128 launches with a short K loop)
     int pair;      // generic kernel as CTA pairs (cta_group::2, M = 256 per MMA; each CTA loads half of the weight tile)
     int pdl;       // launch with programmatic stream serialization (resident weights are then requested before the previous
                    // kernel has finished: only for launches whose weights no kernel in the stream writes, i.e. inference)

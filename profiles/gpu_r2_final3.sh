@@ -1,0 +1,12 @@
+#!/usr/bin/env bash
+# Final code of the round: whole GPU suite, smoke(), the driver's bench command, ncu launch list + full-set capture + traffic.
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_final.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_final.log | cut -c1-300
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke_final.log 2>&1; echo "smoke exit $?"; tail -1 gpurun_out/smoke_final.log | cut -c1-200
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench exit $?"
+python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/bench_final.json").read().strip().splitlines()[-1])
+print(round(d["value"], 1), "boards/s e2e", round(d["e2e"]["value"], 1), "api", round(d["e2e_api"]["value"], 1), "frac", round(d["roofline"]["frac"], 3), d["clocks"], d["cpu_baseline"]["value"], d["stage_ms_per_step"])
+PY
+bash profiles/gpu_profile_r2b.sh 2>&1 | tail -3
