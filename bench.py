@@ -781,7 +781,7 @@ def run_pipeline(args):
     e2e_value = boards_total / (e2e_ms / 1000.0)
     api_value = B * api_steps * world / (api_ms / 1000.0)
 
-    # ---- roofline of the dominant kernel class: the tcgen05 implicit-GEMM convs of the UNet (21 launches per chunk)
+    # ---- roofline of the dominant kernel class: the tcgen05 implicit-GEMM convs of the UNet (20 launches per chunk)
     peak_tf, peak_hbm, peak_src = measured_peaks()
     unet_tc_ms = stages["unet_conv_tc"]
     tc_flops = (UNET_GFLOP - UNET_STEM_GFLOP) * 1e9 * B * args.steps
@@ -791,7 +791,7 @@ def run_pipeline(args):
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel / conv3x3_vr_kernel / conv3x3_rs_kernel (UNet layers, tcgen05 implicit GEMM)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "launches": 21 * chunks * args.steps, "avg_launch_ms": unet_tc_ms / max(1, 21 * chunks * args.steps),
+                "launches": 20 * chunks * args.steps, "avg_launch_ms": unet_tc_ms / max(1, 20 * chunks * args.steps),   # 20 conv launches per chunk (up3.conv3 + up4.up are one)
                 "algorithmic_gflop_per_board": UNET_GFLOP - UNET_STEM_GFLOP, "algorithmic_bytes_per_launch": 868.0e6 * chunk / 128}
     stage_share = {k: v / max(1e-9, sum(stages.values())) for k, v in stages.items()}
     cls_ms = stages["resnet_conv_tc"]
