@@ -631,6 +631,7 @@ struct cvb_jpeg_state {
     void* h_tables = nullptr;    void* d_tables = nullptr;
     int32_t* h_err = nullptr;    int32_t* d_err = nullptr;
     int cap_images = 0;
+    bool huff_configured = false;
 };
 
 void cvb_jpeg_free(cvb_jpeg_state* s) {
@@ -757,10 +758,9 @@ static int decode_jpeg_device(cvb_ctx* ctx, const uint8_t* const* data, const in
         CK(cudaMalloc(&J->d_qt, static_cast<size_t>(cap) * 192 * sizeof(uint16_t)));
         J->cap_images = cap;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!J->huff_configured) {   // per context: function attributes belong to the device the context runs on
         CK(cudaFuncSetAttribute(cvb::k_jpeg_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, cvb::kHuffWarps * cvb::kHuffSmemPerWarp));
-        attr_set = true;
+        J->huff_configured = true;
     }
     std::vector<cvb::JpegHeader> hdr(chunk);
     std::vector<size_t> off(chunk + 1);

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(128) k_cls_head_fwd(const float* __restrict__ 
             if (sl[j] > mx) { mx = sl[j]; am = j; }
         float den = 0.f;
         for (int j = 0; j < kClasses; ++j) den += expf(sl[j] - mx);
-        const int t = target ? target[n] : 0;
+        const int t = target ? min(max(target[n], 0), kClasses - 1) : 0;   // (an out-of-range label must not index past the logits)
         for (int j = 0; j < kClasses; ++j) {
             logits[n * kClasses + j] = sl[j];
             probs[n * kClasses + j] = expf(sl[j] - mx) / den;
@@ -353,7 +353,7 @@ __global__ void k_cls_head_bwd_logits(const float* __restrict__ probs, const int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * kClasses) return;
     const int n = i / kClasses, j = i % kClasses;
-    dlogits[i] = (probs[i] - (target[n] == j ? 1.f : 0.f)) / static_cast<float>(B);
+    dlogits[i] = (probs[i] - (min(max(target[n], 0), kClasses - 1) == j ? 1.f : 0.f)) / static_cast<float>(B);
 }
 __global__ void k_cls_head_bwd_fc(const float* __restrict__ dlogits, const float* __restrict__ pooled, int B, int C, float* __restrict__ dfw,
                                   float* __restrict__ dfb) {
