@@ -451,6 +451,81 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_train_classifier(args):
+    """--workload train-classifier: the piece-classifier training step of scripts/train/train_classifier.py
+    (resnet18 on 64x64 squares, CrossEntropyLoss, Adam) through chessvision.training.ClassifierTrainer, `--train-batch` squares
+    per GPU and step (default 256), data-parallel with an NCCL all-reduce of the flat gradient buffer.  fp32 CUDA-core kernels
+    (csrc/train_cls.cu); `cpu_baseline` is the same step in fp32 PyTorch on the host cores (the oracle of the parity tests)."""
+    import torch
+    import torch.distributed as dist
+    use_product_package()
+    from chessvision import utils
+    from chessvision.training import ClassifierTrainer
+
+    world, rank, local_rank, dev, barrier, max_over_ranks = _dist_env()
+    B = args.train_batch if args.train_batch != 8 else 256
+    sd = utils.load_state_dict(str(ROOT / "weights" / "best_classifier.pth"))[0]
+    tr = ClassifierTrainer(sd, batch_size=B, learning_rate=1e-3, device=local_rank)
+    g = torch.Generator().manual_seed(SEED + rank)
+    h_x = torch.rand(B, 1, 64, 64, generator=g).pin_memory()
+    h_t = torch.randint(0, 13, (B,), generator=g, dtype=torch.int32).pin_memory()
+    d_x, d_t = h_x.to(dev), h_t.to(dev)
+    stream = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        tr.step(d_x, d_t)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            loss, correct = tr.step(d_x, d_t)
+        e1.record(stream)
+        barrier()
+        dev_ms = max_over_ranks(e0.elapsed_time(e1))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):   # end to end: pinned host batch -> H2D -> step -> loss D2H
+            last = float(tr.step(h_x.to(dev, non_blocking=True), h_t.to(dev, non_blocking=True))[0].item())
+        barrier()
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+    clocks = clk.summary()
+    total = B * args.steps * world
+    value = total / (dev_ms / 1000.0)
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            sys.path.insert(0, str(ROOT))
+            from oracle import nets
+            torch.set_num_threads(os.cpu_count() or 1)
+            m = nets.PieceResNet18()
+            m.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
+            m.train()
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+            xb, tb = h_x[:64].clone(), h_t[:64].long()
+            n_steps, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < 10.0:
+                opt.zero_grad()
+                torch.nn.functional.cross_entropy(m(xb), tb).backward()
+                opt.step()
+                n_steps += 1
+            dt = time.perf_counter() - t0
+            cpu = {"value": 64 * n_steps / dt, "unit": "squares/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"{n_steps} steps of batch 64 of the same loop in fp32 PyTorch on the host ({dt:.1f} s)"}
+        emit(json.dumps({
+            "metric": "piece-classifier training squares/sec (fwd+bwd+Adam)", "value": value, "unit": "squares/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic squares, trained start weights",
+            "config": {"workload": "8(f) n3: resnet18(1 -> 13) training step on 64x64 squares, CrossEntropy + Adam", "batch_per_gpu": B,
+                       "parallelism": f"dp{world}, NCCL all-reduce of 11.2 M fp32 gradients per step"},
+            "e2e": {"value": total / (e2e_ms / 1000.0), "unit": "squares/s", "h2d_bytes_per_step": B * 4096 * 4 + B * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms / args.steps, "last_loss": last},
+            "algorithmic_gflop_per_square": 3 * CLS_GFLOP / 64, "tflops": 3 * CLS_GFLOP / 64 * value / 1000.0 / world,
+            "cpu_baseline": cpu, "clocks": clocks, "loss": float(loss.item())}))
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # =====================================================================================================================
 # JPEG front-end (8(f) n2)
 # =====================================================================================================================
@@ -838,7 +913,7 @@ def run_pipeline(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "unet-sweep", "classify", "train", "decode"],
+    ap.add_argument("--workload", default="pipeline", choices=["pipeline", "unet-sweep", "classify", "train", "train-classifier", "decode"],
                     help="pipeline = BASELINE.json's metric (configs[3]); unet-sweep = configs[1]; classify = configs[2]; train = configs[4]; "
                          "decode = JPEG front-end")
     ap.add_argument("--train-batch", type=int, default=8, help="--workload train: images per GPU per step")
@@ -858,12 +933,17 @@ def main():
     if args.impl == "reference":
         if args.workload == "train":
             return run_train_reference(args)
+        if args.workload == "train-classifier":
+            if int(os.environ.get("RANK", "0")) == 0:
+                emit(json.dumps({"impl": "reference", "unavailable": "the train-classifier workload reports the fp32 PyTorch loop as its cpu_baseline in the b200 arm"}))
+            return None
         if args.workload == "decode":
             if int(os.environ.get("RANK", "0")) == 0:
                 emit(json.dumps({"impl": "reference", "unavailable": "the decode workload reports cv2.imdecode as its cpu_baseline in the b200 arm"}))
             return None
         return run_reference(args)
-    return {"decode": run_decode, "train": run_train, "unet-sweep": run_unet_sweep, "classify": run_classify, "pipeline": run_pipeline}[args.workload](args)
+    return {"decode": run_decode, "train": run_train, "train-classifier": run_train_classifier, "unet-sweep": run_unet_sweep, "classify": run_classify,
+            "pipeline": run_pipeline}[args.workload](args)
 
 
 if __name__ == "__main__":

@@ -74,7 +74,10 @@ __device__ __forceinline__ float load_b(const GemmArgs& g, int k, int n) {
 }
 
 // C[M x N] = A[M x K] . B[K x N] with the operands gathered as above; 64 x 64 tile, 16-deep K steps, 4 x 4 outputs per thread.
-template <int MODE>
+// FAST (every layer but the 7x7 / Cin = 1 stem): channel counts are multiples of 16 and the output extent is a power of two,
+// so a K step lies inside one (r, q) tap -- the tap decode is uniform per K step, the pixel decode of a thread's four tile rows
+// is done once (forward / dgrad) or with shifts (wgrad), and an element costs an address computation instead of five divisions.
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(256) k_cls_gemm(const GemmArgs g) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -85,20 +88,91 @@ __global__ void __launch_bounds__(256) k_cls_gemm(const GemmArgs g) {
         k_lo = blockIdx.z * g.k_per_split;
         k_hi = min(g.K, k_lo + g.k_per_split);
     }
-    float acc[4][4] = {};
-    for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
+    // per-thread decode of the four A rows (forward: output pixel; dgrad: input pixel) it loads in every K step
+    int ph[4], pw[4];
+    const float* pbase[4];
+    bool pvalid[4];
+    if (FAST && MODE != MODE_WGRAD) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int idx = tid + 256 * e;
-            // A tile: consecutive threads along the dimension that is contiguous in memory for this mode
-            int am, ak;
-            if (MODE == MODE_WGRAD) { am = idx & (BM - 1); ak = idx >> 6; } else { ak = idx & (BK - 1); am = idx >> 4; }
-            const int gm = m0 + am, gk = k0 + ak;
-            As[ak][am] = (gm < g.M && gk < k_hi) ? load_a<MODE>(g, gm, gk) : 0.f;
-            int bk, bn;
-            if (MODE == MODE_FWD) { bk = idx & (BK - 1); bn = idx >> 4; } else { bn = idx & (BN - 1); bk = idx >> 6; }
-            const int hk = k0 + bk, hn = n0 + bn;
-            Bs[bk][bn] = (hk < k_hi && hn < g.N) ? load_b<MODE>(g, hk, hn) : 0.f;
+            const int gm = m0 + ((tid + 256 * e) >> 4);
+            pvalid[e] = gm < g.M;
+            const int Wm = MODE == MODE_FWD ? g.Wout : g.Win, Hm = MODE == MODE_FWD ? g.Hout : g.Hin;
+            const int w = gm % Wm, h = (gm / Wm) % Hm, n = gm / (Wm * Hm);
+            if (MODE == MODE_FWD) {
+                ph[e] = h * g.stride - g.pad;
+                pw[e] = w * g.stride - g.pad;
+                pbase[e] = g.a + static_cast<size_t>(n) * g.Hin * g.Win * g.Cin;
+            } else {
+                ph[e] = h + g.pad;
+                pw[e] = w + g.pad;
+                pbase[e] = g.a + static_cast<size_t>(n) * g.Hout * g.Wout * g.Cout;
+            }
+        }
+    }
+    float acc[4][4] = {};
+    for (int k0 = k_lo; k0 < k_hi; k0 += BK) {
+        if (FAST) {
+            if (MODE == MODE_FWD) {
+                const int rq = k0 / g.Cin, c0 = k0 - rq * g.Cin, r = rq / g.ks, q = rq - r * g.ks;
+                const int ak = tid & 15;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int am = (tid + 256 * e) >> 4;
+                    const int h = ph[e] + r, w = pw[e] + q;
+                    const bool ok = pvalid[e] && h >= 0 && h < g.Hin && w >= 0 && w < g.Win;
+                    As[ak][am] = ok ? pbase[e][(static_cast<size_t>(h) * g.Win + w) * g.Cin + c0 + ak] : 0.f;
+                    const int bn = am;   // the same split of the tile index for W[co][k]
+                    Bs[ak][bn] = n0 + bn < g.N ? g.b[static_cast<size_t>(n0 + bn) * g.K + k0 + ak] : 0.f;
+                }
+            } else if (MODE == MODE_DGRAD) {
+                const int rq = k0 / g.Cout, c0 = k0 - rq * g.Cout, r = rq / g.ks, q = rq - r * g.ks;
+                const int ak = tid & 15;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int am = (tid + 256 * e) >> 4;
+                    const int hs = ph[e] - r, ws = pw[e] - q;
+                    bool ok = pvalid[e] && hs >= 0 && ws >= 0;
+                    int ho = hs, wo = ws;
+                    if (g.stride == 2) {
+                        ok = ok && !((hs | ws) & 1);
+                        ho >>= 1;
+                        wo >>= 1;
+                    }
+                    ok = ok && ho < g.Hout && wo < g.Wout;
+                    As[ak][am] = ok ? pbase[e][(static_cast<size_t>(ho) * g.Wout + wo) * g.Cout + c0 + ak] : 0.f;
+                    const int bn = tid & 63, bk = (tid >> 6) + 4 * e;   // W[co0 + bk][rq][ci = n0 + bn]
+                    Bs[bk][bn] = n0 + bn < g.N ? g.b[(static_cast<size_t>(c0 + bk) * g.ks * g.ks + rq) * g.Cin + n0 + bn] : 0.f;
+                }
+            } else {   // wgrad: A(co, j) = dz[j][co]; B(j, (rq, ci)) = x[gather]; the 64 columns of this block lie in one tap
+                const int rq = n0 / g.Cin, c0 = n0 - rq * g.Cin, r = rq / g.ks, q = rq - r * g.ks;
+                const int lw = 31 - __clz(g.Wout), lh = 31 - __clz(g.Hout);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int am = tid & 63, ak = (tid >> 6) + 4 * e;
+                    const int j = k0 + ak;
+                    const bool in = j < k_hi;
+                    As[ak][am] = (in && m0 + am < g.M) ? g.a[static_cast<size_t>(j) * g.Cout + m0 + am] : 0.f;
+                    const int wo = j & (g.Wout - 1), ho = (j >> lw) & (g.Hout - 1), bi = j >> (lw + lh);
+                    const int h = ho * g.stride - g.pad + r, w = wo * g.stride - g.pad + q;
+                    const bool ok = in && h >= 0 && h < g.Hin && w >= 0 && w < g.Win && n0 + am < g.N;
+                    Bs[ak][am] = ok ? g.b[((static_cast<size_t>(bi) * g.Hin + h) * g.Win + w) * g.Cin + c0 + am] : 0.f;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int idx = tid + 256 * e;
+                // A tile: consecutive threads along the dimension that is contiguous in memory for this mode
+                int am, ak;
+                if (MODE == MODE_WGRAD) { am = idx & (BM - 1); ak = idx >> 6; } else { ak = idx & (BK - 1); am = idx >> 4; }
+                const int gm = m0 + am, gk = k0 + ak;
+                As[ak][am] = (gm < g.M && gk < k_hi) ? load_a<MODE>(g, gm, gk) : 0.f;
+                int bk, bn;
+                if (MODE == MODE_FWD) { bk = idx & (BK - 1); bn = idx >> 4; } else { bn = idx & (BN - 1); bk = idx >> 6; }
+                const int hk = k0 + bk, hn = n0 + bn;
+                Bs[bk][bn] = (hk < k_hi && hn < g.N) ? load_b<MODE>(g, hk, hn) : 0.f;
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -507,14 +581,18 @@ cudaError_t conv_gemm(int mode, const ClsConv& c, int B, const float* a, const f
     g.B = B; g.Hin = c.hin; g.Win = c.hin; g.Cin = c.cin; g.Hout = c.hout; g.Wout = c.hout; g.Cout = c.cout;
     g.ks = c.ks; g.stride = c.stride; g.pad = c.pad; g.accumulate = accumulate; g.k_per_split = 0;
     const int Kw = c.ks * c.ks * c.cin;
+    // every layer but the stem: channels in multiples of 64, power-of-two output extent, stride 1 or 2
+    const bool fast = c.cin % 64 == 0 && c.cout % 64 == 0 && (c.hout & (c.hout - 1)) == 0 && (c.stride == 1 || c.stride == 2);
     if (mode == MODE_FWD) {
         g.M = B * c.hout * c.hout; g.N = c.cout; g.K = Kw;
         dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-        k_cls_gemm<MODE_FWD><<<grid, 256, 0, s>>>(g);
+        if (fast) k_cls_gemm<MODE_FWD, true><<<grid, 256, 0, s>>>(g);
+        else k_cls_gemm<MODE_FWD, false><<<grid, 256, 0, s>>>(g);
     } else if (mode == MODE_DGRAD) {
         g.M = B * c.hin * c.hin; g.N = c.cin; g.K = c.ks * c.ks * c.cout;
         dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-        k_cls_gemm<MODE_DGRAD><<<grid, 256, 0, s>>>(g);
+        if (fast) k_cls_gemm<MODE_DGRAD, true><<<grid, 256, 0, s>>>(g);
+        else k_cls_gemm<MODE_DGRAD, false><<<grid, 256, 0, s>>>(g);
     } else {
         g.M = c.cout; g.N = Kw; g.K = B * c.hout * c.hout;
         // enough slices of the pixel dimension to fill the GPU, each a multiple of the K step
@@ -528,7 +606,8 @@ cudaError_t conv_gemm(int mode, const ClsConv& c, int B, const float* a, const f
         splits = (g.K + g.k_per_split - 1) / g.k_per_split;
         g.c = t->wpart;
         dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, splits);
-        k_cls_gemm<MODE_WGRAD><<<grid, 256, 0, s>>>(g);
+        if (fast) k_cls_gemm<MODE_WGRAD, true><<<grid, 256, 0, s>>>(g);
+        else k_cls_gemm<MODE_WGRAD, false><<<grid, 256, 0, s>>>(g);
         const size_t count = static_cast<size_t>(g.M) * g.N;
         k_cls_reduce_splits<<<blocks_for(count), 256, 0, s>>>(t->wpart, out, count, splits);
     }
