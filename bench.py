@@ -5,7 +5,7 @@
 
 Workloads (BASELINE.json `configs`):
   pipeline    configs[3]  one step = the whole pipeline (UNet -> mask -> quad -> warp/crop -> ResNet-18 -> FEN) over B distinct
-                          synthetic 512x512x3 boards per GPU; B is a multiple of the chunk (148 boards = one board per SM, so
+                          synthetic 512x512x3 boards per GPU; B is a multiple of the chunk (296 boards = two boards per SM, so
                           every conv launch is a whole number of waves) and the default B x 20 steps covers the 65,536 boards
                           of configs[3] on one GPU.  `value` = device-resident throughput (inputs in HBM, CUDA events, max over
                           ranks); `e2e` = the same through the host-buffer C-ABI entry point cvb_image_to_fen_host (pinned host
@@ -45,6 +45,8 @@ H2D_PER_BOARD = 512 * 512 * 3
 D2H_PER_BOARD = 4 * 2 * 4 + 1 + 4 + 64 * 13 * 4 + 64 + 64 + 2 * 72   # quad, found, status, probs, labels x2, fen
 D2H_FULL_PER_BOARD = D2H_PER_BOARD + 65536 * 4 + 65536 + 262144       # + logits, mask, board image
 CHUNK = 148                   # boards per network chunk = SM count of a B200: every persistent conv grid is whole waves
+PIPE_CHUNK = 296              # the pipeline workload's default: two boards per SM (per-launch prologue / drain amortised over twice the
+                              # boards: +1.0 % device-resident against 148 in a same-box A/B, profiles/README.md; 17.8 GB of workspace)
 CONFIG3_BOARDS = 65536
 
 _REAL_STDOUT = None
@@ -147,7 +149,7 @@ def measured_peaks():
     return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel_class: str):
+def ncu_traffic(kernel_class: str, boards_per_launch: int = 0):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel class, from the committed ncu `--set full` capture
     (profiles/<round>/traffic.json, written by profiles/traffic_from_ncu.py from the raw csv of the same command): a profiler
     counter cannot be read inside an un-profiled run, so the line cites the capture it comes from."""
@@ -157,7 +159,10 @@ def ncu_traffic(kernel_class: str):
             d = json.load(open(f))
             if kernel_class in d:
                 e = d[kernel_class]
-                return e["bytes_per_launch"], f"profiles/{rnd}/traffic.json ({e['launches']} launches, {e['boards']} boards per launch; {e['source']})"
+                scale = boards_per_launch / e["boards"] if boards_per_launch else 1.0   # the capture ran one 148-board chunk per launch
+                note = f", scaled to {boards_per_launch} boards per launch" if boards_per_launch and boards_per_launch != e["boards"] else ""
+                return e["bytes_per_launch"] * scale, (f"profiles/{rnd}/traffic.json ({e['launches']} launches, {e['boards']} boards per launch{note}; "
+                                                       f"{e['source']})")
     return None, "no ncu capture committed for this kernel class"
 
 
@@ -921,7 +926,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--boards", type=int, default=0, help="boards per GPU per step (0: whole chunks so that `steps` steps cover 65,536 boards)")
-    ap.add_argument("--chunk", type=int, default=CHUNK, help="boards per pipeline chunk (workspace size)")
+    ap.add_argument("--chunk", type=int, default=PIPE_CHUNK, help="boards per pipeline chunk (workspace size)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-boards", type=int, default=64, help="boards of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-boards-per-step", type=int, default=4, help="--impl reference: boards per step")
