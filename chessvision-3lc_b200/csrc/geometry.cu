@@ -1067,28 +1067,36 @@ __global__ void k_warp_generic(const uint8_t* __restrict__ src, int H, int W, in
 //
 // One CTA per 64x64 destination tile (= one chess square of the board image).  The source footprint of the tile is
 // staged once through shared memory (coalesced 48-byte groups -> one BGR0 word per pixel, zeros outside the image),
-// the gather then runs on shared memory with packed 16x8-bit dot products.  Coordinates: the division is replaced by a
-// Newton reciprocal (2^-50 relative error); whenever the result lies within 2^-13 of a rounding boundary, outside the
-// staged patch or out of range, that pixel is recomputed by `warp_px_exact` with the literal OpenCV arithmetic, so the
-// output stays bit-identical.
+// the gather then runs on shared memory with packed 16x8-bit dot products.
+//
+// Coordinates.  A thread owns one 16-pixel segment of one tile row.  It anchors U = 32*X/W at the segment centre in
+// float64 (once), and per pixel adds the float32 offset
+//     U(c + d) - U(c) = d * (32*M0 - U(c)*M6) / W(c + d),        d = -8 .. 7,
+// which is short (|offset| < 512 units of 1/32 px, checked per thread), so float32 carries it to 2^-13 of a unit: one
+// FFMA for W, one MUFU reciprocal, one FMUL, and one FFMA per axis whose addend is the magic number 1.5 * 2^23 -- the
+// integer lands in the mantissa and one IADD puts it on the anchor.  The error of that value is below 2.5 * 2^-13
+// (profiles/probes/warp_fast_model.py: 0.5 anchor rounding + 0.5 FMA rounding + 5.3 * 2^-24 relative on the offset; measured
+// maximum 2.0 with the reciprocal off by a whole ulp); a pixel whose value lies within 4 * 2^-13 of a rounding boundary
+// (0.2 % of them) is marked and recomputed after the segment with the literal OpenCV arithmetic, so the output stays
+// bit-identical; so are all pixels of threads whose offsets leave the magic range and of tiles whose footprint does not fit
+// the staged patch.  The main loop has no branch.
+//
+// Footprint.  The offset is monotonic over the segment, so anchor + offsets at d = -8 and d = 7 bound the segment's source
+// columns and rows; the CTA's footprint is the min / max of those over its 256 segments (redux.sync per warp, one
+// shared-memory exchange).  No thread computes anything the others wait for.
 // =====================================================================================================================
 constexpr int kWpRows = 88;          // staged patch capacity (source rows)
 constexpr int kWpCols16 = 7;         // ... and 16-pixel column groups
 constexpr int kWpStride = 116;       // words per staged row (multiple of 4 for 128-bit stores)
-constexpr int kWpSmem = kWpRows * kWpStride * 4 + 64 * 3 * 8;
+constexpr int kWpSmem = kWpRows * kWpStride * 4;
+constexpr int kWpFrac = 13;          // bits carried below 1/32 px
+constexpr int kWpBand = 8;           // guard band in 2^-13 units (covers an error below 4)
+constexpr int kWpMagicBits = 0x4B400000;   // 1.5 * 2^23 as float bits
+constexpr int kWpFar = 1 << 20;      // footprint bound of a segment outside the float32 path: the tile does not fit
 
-// The literal arithmetic for one destination pixel (also used for the tile corners); returns the gray value.
-__device__ __noinline__ uint32_t warp_px_exact(const uint8_t* __restrict__ src, int H, int W, double X0, double Y0, double W0,
-                                              double m0, double m3, double m6, int x1, int* sx_out, int* sy_out, int* wsign) {
-    const double xx = static_cast<double>(x1);
-    double w = W0 + m6 * xx;
-    if (wsign) *wsign = w > 0.0 ? 1 : (w < 0.0 ? -1 : 0);
-    w = w != 0.0 ? 32.0 / w : 0.0;
-    const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + m0 * xx) * w));
-    const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + m3 * xx) * w));
-    const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
+// The literal arithmetic for one destination pixel from global memory; returns the gray value.
+__device__ __noinline__ uint32_t warp_px_exact(const uint8_t* __restrict__ src, int H, int W, int Xi, int Yi) {
     const int sx = max(-32768, min(32767, Xi >> 5)), sy = max(-32768, min(32767, Yi >> 5));
-    if (sx_out) { *sx_out = sx; *sy_out = sy; }
     const int ax = Xi & 31, ay = Yi & 31;
     const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
     int acc[3] = {16384, 16384, 16384};
@@ -1104,56 +1112,102 @@ __device__ __noinline__ uint32_t warp_px_exact(const uint8_t* __restrict__ src, 
     return static_cast<uint32_t>((3735 * bl + 19235 * gr + 9798 * rd + 16384) >> 15);
 }
 
+// Four taps of the staged patch -> gray.  Xl, Yl: patch coordinates in 1/32 px (tap column Xl >> 5, fraction Xl & 31).
+__device__ __forceinline__ uint32_t warp_gather(uint32_t patch_addr, int Xl, int Yl) {
+    uint32_t p00, p01, p10, p11;
+    const uint32_t addr = patch_addr + static_cast<uint32_t>(Yl >> 5) * (kWpStride * 4) + (static_cast<uint32_t>(Xl >> 5) << 2);
+    asm("ld.shared.u32 %0, [%4];\n\tld.shared.u32 %1, [%4+4];\n\tld.shared.u32 %2, [%4+%5];\n\tld.shared.u32 %3, [%4+%6];"
+        : "=r"(p00), "=r"(p01), "=r"(p10), "=r"(p11)
+        : "r"(addr), "n"(kWpStride * 4), "n"(kWpStride * 4 + 4));
+    const uint32_t ax = Xl & 31, ay = Yl & 31;
+    const uint32_t u = ax * 0xffffu + 32u;             // (32-ax) | ax << 16
+    const uint32_t wr1 = u * ay, wr0 = (u << 5) - wr1; // row weights, 16 bits each, sum 1024
+    const uint32_t bg0 = __byte_perm(p00, p01, 0x5140), r0 = __byte_perm(p00, p01, 0x6262);
+    const uint32_t bg1 = __byte_perm(p10, p11, 0x5140), r1 = __byte_perm(p10, p11, 0x6262);
+    const uint32_t bl = __dp2a_lo(wr1, bg1, __dp2a_lo(wr0, bg0, 512u)) >> 10;
+    const uint32_t gn = __dp2a_hi(wr1, bg1, __dp2a_hi(wr0, bg0, 512u)) >> 10;
+    const uint32_t rd = __dp2a_lo(wr1, r1, __dp2a_lo(wr0, r0, 512u)) >> 10;
+    return (3735u * bl + 19235u * gn + 9798u * rd + 16384u) >> 15;
+}
+
 __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
                                                     const uint8_t* __restrict__ found, uint8_t* __restrict__ board,
                                                     uint8_t* __restrict__ squares, int H, int W) {
     extern __shared__ __align__(16) uint8_t wsm[];
     uint32_t* patch = reinterpret_cast<uint32_t*>(wsm);
-    double* rowtab = reinterpret_cast<double*>(wsm + kWpRows * kWpStride * 4);   // [64][3]: X0, Y0, W0/32 per tile row
-    __shared__ int s_corner[4][3];
+    __shared__ int4 s_ext[8];
     const int b = blockIdx.y, t = threadIdx.x;
     const int bx = (blockIdx.x & 7) * 64, by = (blockIdx.x >> 3) * 64;
-    uint8_t* dst_tile = board + (static_cast<size_t>(b) * 512 + by) * 512 + (448 - bx);   // destination x -> 511 - x
+    const int row = t >> 2, seg = t & 3;                       // this thread's 16 destination pixels: tile row, segment
+    // destination x -> 511 - x: the segment's 16 bytes, mirrored, are one aligned 16-byte store
+    uint8_t* dst = board + (static_cast<size_t>(b) * 512 + by + row) * 512 + (448 - bx) + (48 - 16 * seg);
     // optional second copy in the layout extract_squares returns (core.py:420-439): u8 [64 squares][64][64], square = 8*row + col
-    uint8_t* sq_tile = squares ? squares + (static_cast<size_t>(b) * 64 + (blockIdx.x >> 3) * 8 + (7 - (blockIdx.x & 7))) * 4096 : nullptr;
+    uint8_t* sq = squares ? squares + (static_cast<size_t>(b) * 64 + (blockIdx.x >> 3) * 8 + (7 - (blockIdx.x & 7))) * 4096 + row * 64 + (48 - 16 * seg)
+                          : nullptr;
     if (!found[b]) {
-        *reinterpret_cast<uint4*>(dst_tile + (t >> 2) * 512 + (t & 3) * 16) = make_uint4(0, 0, 0, 0);
-        if (sq_tile) *reinterpret_cast<uint4*>(sq_tile + t * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+        if (sq) *reinterpret_cast<uint4*>(sq) = make_uint4(0, 0, 0, 0);
         return;
     }
     const double* m = minv + static_cast<size_t>(b) * 9;
-    const double m0 = m[0], m3 = m[3], m6 = m[6];
     const uint8_t* src = img + static_cast<size_t>(b) * H * W * 3;
-    if (t < 64) {
-        const int y = by + t;
-        rowtab[t * 3 + 0] = m0 * bx + m[1] * y + m[2];
-        rowtab[t * 3 + 1] = m3 * bx + m[4] * y + m[5];
-        rowtab[t * 3 + 2] = (m6 * bx + m[7] * y + m[8]) * 0.03125;   // exact scaling
+    // The segment's anchor in float64.  Only its accuracy matters (2^-40 is ample), not OpenCV's order of roundings: fused
+    // multiply-adds, and the quotient by two Newton steps on the hardware seed.
+    const double m6 = m[6];
+    const double xg = static_cast<double>(bx + 16 * seg + 8), yg = static_cast<double>(by + row);
+    const double Xc = fma(m[0], xg, fma(m[1], yg, m[2])), Yc = fma(m[3], xg, fma(m[4], yg, m[5])), Wc = fma(m6, xg, fma(m[7], yg, m[8]));
+    double q;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(Wc));
+    q = fma(q, fma(-Wc, q, 1.0), q);
+    q = fma(q, fma(-Wc, q, 1.0), q);
+    const double Uc = Xc * q * 262144.0, Vc = Yc * q * 262144.0;                     // image coordinates, 2^-13 units of 1/32 px
+    // offset slope 32 * (M0 - U_c * M6) in the same units
+    const float Bx = static_cast<float>(fma(-Uc, m6, m[0] * 262144.0)), By = static_cast<float>(fma(-Vc, m6, m[3] * 262144.0));
+    const float Wcf = static_cast<float>(Wc), m6f = static_cast<float>(m6);
+    // The float32 path is valid for this thread when the offsets at both ends of the segment (the offset is monotonic in d)
+    // stay inside the magic range; everything is written so that a NaN fails.
+    float ra, rb;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(fmaf(m6f, -8.0f, Wcf)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(fmaf(m6f, 7.0f, Wcf)));
+    const float oxa = Bx * (-8.0f * ra), oxb = Bx * (7.0f * rb), oya = By * (-8.0f * ra), oyb = By * (7.0f * rb);
+    const float Uf = static_cast<float>(Uc), Vf = static_cast<float>(Vc);
+    constexpr float kRange = 4000000.0f;   // < 2^22 = 4194304
+    bool fast = fabsf(oxa) < kRange && fabsf(oxb) < kRange && fabsf(oya) < kRange && fabsf(oyb) < kRange;
+    fast = fast && fabsf(Wcf) > 1e-30f && fabsf(Wcf) < 1e30f && fabsf(m6f * 8.0f) <= 0.25f * fabsf(Wcf);   // W within 25 % over the segment
+    fast = fast && fabsf(Uf) < 5e8f && fabsf(Vf) < 5e8f;                                                    // |coordinate| < 2^29: integer arithmetic below is safe
+    // source columns / rows the segment touches (floor of the extreme coordinates in pixels; the margins are added below)
+    int4 ext = make_int4(-kWpFar, kWpFar, -kWpFar, kWpFar);   // outside the float32 path: a footprint no patch holds
+    if (fast) {
+        constexpr float kPx = 1.0f / 262144.0f;
+        ext.x = __float2int_rd((Uf + fminf(fminf(oxa, oxb), 0.0f)) * kPx);
+        ext.y = __float2int_rd((Uf + fmaxf(fmaxf(oxa, oxb), 0.0f)) * kPx);
+        ext.z = __float2int_rd((Vf + fminf(fminf(oya, oyb), 0.0f)) * kPx);
+        ext.w = __float2int_rd((Vf + fmaxf(fmaxf(oya, oyb), 0.0f)) * kPx);
     }
+    ext.x = __reduce_min_sync(0xffffffffu, ext.x);
+    ext.y = __reduce_max_sync(0xffffffffu, ext.y);
+    ext.z = __reduce_min_sync(0xffffffffu, ext.z);
+    ext.w = __reduce_max_sync(0xffffffffu, ext.w);
+    if ((t & 31) == 0) s_ext[t >> 5] = ext;
     __syncthreads();
-    if (t < 4) {   // source taps of the four tile corners bound the footprint (projective image of a convex tile)
-        const int ry = (t >> 1) * 63;
-        int sx, sy, sg;
-        warp_px_exact(src, H, W, rowtab[ry * 3], rowtab[ry * 3 + 1], rowtab[ry * 3 + 2] * 32.0, m0, m3, m6, (t & 1) * 63, &sx, &sy, &sg);
-        s_corner[t][0] = sx;
-        s_corner[t][1] = sy;
-        s_corner[t][2] = sg;
-    }
-    __syncthreads();
-    int x_min = s_corner[0][0], x_max = x_min, y_min = s_corner[0][1], y_max = y_min;
-    bool fits = s_corner[0][2] != 0 && (W & 15) == 0;
-#pragma unroll
-    for (int c = 1; c < 4; ++c) {
-        x_min = min(x_min, s_corner[c][0]);
-        x_max = max(x_max, s_corner[c][0]);
-        y_min = min(y_min, s_corner[c][1]);
-        y_max = max(y_max, s_corner[c][1]);
-        fits = fits && s_corner[c][2] == s_corner[0][2];
-    }
+    ext = s_ext[t & 7];
+    const int x_min = __reduce_min_sync(0xffffffffu, ext.x), x_max = __reduce_max_sync(0xffffffffu, ext.y);
+    const int y_min = __reduce_min_sync(0xffffffffu, ext.z), y_max = __reduce_max_sync(0xffffffffu, ext.w);
+    // rint can move a coordinate up by half a unit and the taps reach one further: columns x_min - 1 .. x_max + 2
     const int x_lo = (x_min - 1) & ~15, y_lo = y_min - 1;
     const int ncol16 = (x_max + 3 - x_lo + 15) >> 4;     // columns x_lo .. x_max + 2
     const int nrows = y_max + 3 - y_lo;                  // rows    y_lo .. y_max + 2
-    fits = fits && ncol16 <= kWpCols16 && nrows <= kWpRows && x_max - x_min < 4096 && y_max - y_min < 4096;
+    const bool fits = (W & 15) == 0 && static_cast<unsigned>(ncol16 - 1) < kWpCols16 && static_cast<unsigned>(nrows - 1) < kWpRows;
+    fast = fast && fits;
+    // anchor in patch coordinates + rounding offset + band offset, minus the magic bits: ix = bits(fma) + Cx is
+    // rint(U * 2^13) + 2^12 + band / 2.  A thread outside the float32 path gathers its 16 pixels at patch (0, 0) (discarded)
+    // and recomputes all of them below.
+    constexpr int kRound = (1 << (kWpFrac - 1)) + kWpBand / 2 - kWpMagicBits;
+    const int Cx = (fast ? __double2int_rn(Uc - static_cast<double>(x_lo * 262144)) : 0) + kRound;
+    const int Cy = (fast ? __double2int_rn(Vc - static_cast<double>(y_lo * 262144)) : 0) + kRound;
+    const float fBx = fast ? Bx : 0.0f, fBy = fast ? By : 0.0f, fW = fast ? Wcf : 1.0f, fm6 = fast ? m6f : 0.0f;
+    uint32_t redo = fast ? 0u : 0xffffu;   // pixels of the segment that need the literal arithmetic
+    const uint32_t patch_addr = static_cast<uint32_t>(__cvta_generic_to_shared(patch));
     if (fits) {
         // 48-byte groups of the footprint: a thread's (up to three) groups are requested together, so that one round of
         // DRAM latency covers the whole patch instead of one round per group
@@ -1191,61 +1245,54 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
         }
     }
     __syncthreads();
-    const int xq = t & 15, yq = t >> 4;
-    // Fast path of the coordinates (only has to land within the 2^-13 guard band of the exact value, which is 2^-27 relative):
-    // numerators and denominator advance by one destination pixel with one addition each, the quotient is one MUFU reciprocal
-    // (2^-22) refined by a single Newton step in float64 (2^-43), and the product is formed by the FMA that also adds the
-    // rounding constant.
-    const double xs = static_cast<double>(4 * xq);
-    const double m6s = m6 * 0.03125;   // exact scaling
-    const unsigned lim_x = static_cast<unsigned>(ncol16 * 16 - 1), lim_y = static_cast<unsigned>(nrows - 1);
-    constexpr double kMagic = 103079215104.0;   // 1.5 * 2^36: the low word of (v + kMagic) is rint(v * 2^16)
-    constexpr int kMagicHi = 0x42380000;        // high word of kMagic
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const int ry = yq + 16 * j;
-        const double X0 = rowtab[ry * 3], Y0 = rowtab[ry * 3 + 1], W0s = rowtab[ry * 3 + 2];
-        double Xn = fma(m0, xs, X0), Yn = fma(m3, xs, Y0), ws = fma(m6s, xs, W0s);
+    constexpr float kMagic = 12582912.0f;
+    uint32_t out[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
         uint32_t packed = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float rf;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(__double2float_rn(ws)));
-            double r = static_cast<double>(rf);
-            r = fma(r, fma(-ws, r, 1.0), r);
-            const double tx = fma(Xn, r, kMagic), ty = fma(Yn, r, kMagic);
-            Xn += m0;
-            Yn += m3;
-            ws += m6s;
-            const int vx = __double2loint(tx), vy = __double2loint(ty);
-            // in range (|v| < 2^15): the high word is kMagicHi, minus one when the low word borrowed
-            bool ok = fits && (__double2hiint(tx) - (vx >> 31)) == kMagicHi && (__double2hiint(ty) - (vy >> 31)) == kMagicHi;
-            const int ax16 = static_cast<int>(static_cast<unsigned>(vx) + 0x8000u), ay16 = static_cast<int>(static_cast<unsigned>(vy) + 0x8000u);
-            ok = ok && ((static_cast<unsigned>(ax16) + 8u) & 0xffffu) >= 16u && ((static_cast<unsigned>(ay16) + 8u) & 0xffffu) >= 16u;   // not within 2^-13 of a tie
-            const int Xi = ax16 >> 16, Yi = ay16 >> 16;
-            const int lx = (Xi >> 5) - x_lo, ly = (Yi >> 5) - y_lo;
-            ok = ok && static_cast<unsigned>(lx) < lim_x && static_cast<unsigned>(ly) < lim_y;
-            uint32_t gray;
-            if (ok) {
-                const uint32_t* p = patch + ly * kWpStride + lx;
-                const uint32_t p00 = p[0], p01 = p[1], p10 = p[kWpStride], p11 = p[kWpStride + 1];
-                const uint32_t ax = Xi & 31, ay = Yi & 31;
-                const uint32_t u = ax * 0xffffu + 32u;             // (32-ax) | ax << 16
-                const uint32_t wr0 = u * (32u - ay), wr1 = u * ay; // row weights, 16 bits each, sum 1024
-                const uint32_t bg0 = __byte_perm(p00, p01, 0x5140), r0 = __byte_perm(p00, p01, 0x6262);
-                const uint32_t bg1 = __byte_perm(p10, p11, 0x5140), r1 = __byte_perm(p10, p11, 0x6262);
-                const uint32_t bl = __dp2a_lo(wr1, bg1, __dp2a_lo(wr0, bg0, 512u)) >> 10;
-                const uint32_t gr = __dp2a_hi(wr1, bg1, __dp2a_hi(wr0, bg0, 512u)) >> 10;
-                const uint32_t rd = __dp2a_lo(wr1, r1, __dp2a_lo(wr0, r0, 512u)) >> 10;
-                gray = (3735u * bl + 19235u * gr + 9798u * rd + 16384u) >> 15;
-            } else {
-                gray = warp_px_exact(src, H, W, X0, Y0, W0s * 32.0, m0, m3, m6, 4 * xq + i, nullptr, nullptr, nullptr);
-            }
-            packed |= gray << (8 * (3 - i));
+            const float d = static_cast<float>(4 * g + i - 8);
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(fm6, d, fW)));
+            const float s = d * r;
+            const int ix = __float_as_int(fmaf(fBx, s, kMagic)) + Cx, iy = __float_as_int(fmaf(fBy, s, kMagic)) + Cy;
+            if ((ix & ((1 << kWpFrac) - 1)) < kWpBand || (iy & ((1 << kWpFrac) - 1)) < kWpBand) redo |= 1u << (4 * g + i);
+            packed |= warp_gather(patch_addr, ix >> kWpFrac, iy >> kWpFrac) << (8 * (3 - i));
         }
-        *reinterpret_cast<uint32_t*>(dst_tile + ry * 512 + (60 - 4 * xq)) = packed;
-        if (sq_tile) *reinterpret_cast<uint32_t*>(sq_tile + ry * 64 + (60 - 4 * xq)) = packed;
+        out[3 - g] = packed;
     }
+    if (redo) {   // guard-band pixels (0.2 %), threads outside the float32 range, tiles that were not staged
+        double X0, Y0, W0;   // row origin of the 64-wide block as cv::WarpPerspectiveInvoker forms it (separate roundings)
+        {
+            const int y = by + row;
+            X0 = m[0] * bx + m[1] * y + m[2];
+            Y0 = m[3] * bx + m[4] * y + m[5];
+            W0 = m6 * bx + m[7] * y + m[8];
+        }
+        const unsigned lim_x = fits ? static_cast<unsigned>(ncol16 * 16 - 1) : 0u, lim_y = fits ? static_cast<unsigned>(nrows - 1) : 0u;
+        do {
+            const int k = __ffs(redo) - 1;
+            redo &= redo - 1;
+            const double xx = static_cast<double>(16 * seg + k);
+            double w = W0 + m6 * xx;
+            w = w != 0.0 ? 32.0 / w : 0.0;
+            const double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + m[0] * xx) * w));
+            const double fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + m[3] * xx) * w));
+            const int Xi = __double2int_rn(fX), Yi = __double2int_rn(fY);
+            const int lx = max(-32768, min(32767, Xi >> 5)) - x_lo, ly = max(-32768, min(32767, Yi >> 5)) - y_lo;
+            // taps lx, lx + 1 and ly, ly + 1 inside the staged patch: the shared-memory gather; else global memory
+            const uint32_t gray = static_cast<unsigned>(lx) < lim_x && static_cast<unsigned>(ly) < lim_y
+                                      ? warp_gather(patch_addr, (lx << 5) | (Xi & 31), (ly << 5) | (Yi & 31))
+                                      : warp_px_exact(src, H, W, Xi, Yi);
+            const int sh = 8 * (3 - (k & 3));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j == 3 - (k >> 2)) out[j] = (out[j] & ~(0xffu << sh)) | (gray << sh);
+        } while (redo);
+    }
+    *reinterpret_cast<uint4*>(dst) = make_uint4(out[0], out[1], out[2], out[3]);
+    if (sq) *reinterpret_cast<uint4*>(sq) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 }  // namespace

@@ -191,6 +191,65 @@ def test_warp_squares_with_corners_outside_the_image(engine):
         assert np.array_equal(board[i], want), f"board {i}: {(board[i] != want).sum()} bytes differ"
 
 
+def _fuzz_quads(rng, n):
+    """Board quads in the 256-px mask frame: ordinary boards, strong perspective, tiny and over-sized boards, corners outside
+    the image, near-degenerate slivers -- every regime of k_warp_board (float32 offsets, per-thread and per-tile exact paths)."""
+    out = []
+    for i in range(n):
+        kind = i % 8
+        if kind <= 2:                                            # ordinary: a rotated, mildly sheared board
+            c, r = rng.uniform(90, 166, 2), rng.uniform(50, 125)
+            a = rng.uniform(0, 2 * np.pi) + np.array([0, 0.5, 1.0, 1.5]) * np.pi + rng.uniform(-0.2, 0.2, 4)
+            q = c + (r * rng.uniform(0.8, 1.2, 4))[:, None] * np.stack([np.cos(a), np.sin(a)], 1)
+        elif kind == 3:                                          # strong perspective: one edge a quarter of the opposite one
+            w0, w1 = rng.uniform(20, 60), rng.uniform(160, 250)
+            y0, y1 = rng.uniform(10, 80), rng.uniform(170, 250)
+            q = np.array([[128 + w0 / 2, y0], [128 - w0 / 2, y0], [128 - w1 / 2, y1], [128 + w1 / 2, y1]]) + rng.uniform(-4, 4, (4, 2))
+        elif kind == 4:                                          # tiny board: many destination pixels per source pixel
+            c, r = rng.uniform(60, 200, 2), rng.uniform(6, 25)
+            a = rng.uniform(0, 2 * np.pi) + np.array([0, 0.5, 1.0, 1.5]) * np.pi
+            q = c + r * np.stack([np.cos(a), np.sin(a)], 1)
+        elif kind == 5:                                          # larger than the frame: taps outside, footprints beyond the staged patch
+            c, r = rng.uniform(100, 156, 2), rng.uniform(200, 700)
+            a = rng.uniform(0, 2 * np.pi) + np.array([0, 0.5, 1.0, 1.5]) * np.pi + rng.uniform(-0.3, 0.3, 4)
+            q = c + r * np.stack([np.cos(a), np.sin(a)], 1)
+        elif kind == 6:                                          # any four points (self-intersecting, W changing sign)
+            q = rng.uniform(-40, 296, (4, 2))
+        else:                                                    # sliver
+            t = np.sort(rng.uniform(0, 255, 4))
+            q = np.stack([t, t + rng.uniform(-3, 3, 4)], 1)
+        out.append(np.round(q).astype(np.int32))
+    return np.stack(out)
+
+
+def test_warp_squares_fuzz_noise_images_against_cv2(engine):
+    """256 quads x white-noise images (every 1/32-px coordinate difference changes bytes): warp + gray + mirror must equal
+    cv2.getPerspectiveTransform + cv2.warpPerspective + cvtColor + flip byte for byte (utils.py:115-132, core.py:298-300)."""
+    import cv2
+    rng = np.random.default_rng(20261018)
+    quads = _fuzz_quads(rng, 256)
+    dest = np.array(((0, 0), (512, 0), (512, 512), (0, 512)), np.float32)
+    imgs = rng.integers(0, 256, (8, 512, 512, 3), dtype=np.uint8)
+    dimgs = torch.from_numpy(imgs).cuda()
+    found = torch.ones(8, dtype=torch.uint8).cuda()
+    n_checked = 0
+    for lo in range(0, 256, 8):
+        q = quads[lo:lo + 8]
+        board = engine.warp_squares(dimgs, torch.from_numpy(q).cuda(), found).cpu().numpy()
+        for i in range(8):
+            src = og.scale_quadrangle(q[i].reshape(4, 1, 2), (512, 512)).reshape(4, 2)
+            try:
+                M = cv2.getPerspectiveTransform(src, dest)
+            except cv2.error:
+                continue
+            if not np.isfinite(M).all() or abs(np.linalg.det(M)) < 1e-12:
+                continue                                        # singular system: cv2 returns garbage of its own LU; not a board
+            want = cv2.flip(cv2.cvtColor(cv2.warpPerspective(imgs[i], M, (512, 512)), cv2.COLOR_BGR2GRAY), 1)
+            assert np.array_equal(board[i], want), f"quad {lo + i} {q[i].tolist()}: {(board[i] != want).sum()} bytes differ"
+            n_checked += 1
+    assert n_checked >= 200, n_checked
+
+
 @pytest.mark.parametrize("shape,out_size", [((300, 400, 3), (512, 512)), ((300, 400, 3), (300, 200)), ((480, 640, 3), (640, 480)),
                                             ((97, 131, 3), (50, 30)), ((256, 256), (64, 64)), ((200, 100), (1000, 8)),
                                             ((64, 64, 1), (33, 77)), ((512, 512, 3), (5, 5))])
