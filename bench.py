@@ -867,7 +867,7 @@ def run_pipeline(args):
     tc_flops = (UNET_GFLOP - UNET_STEM_GFLOP) * 1e9 * B * args.steps
     achieved = tc_flops / (unet_tc_ms / 1000.0) / 1e12 if unet_tc_ms > 0 else 0.0
     chunks = (B + chunk - 1) // chunk
-    traffic, traffic_src = ncu_traffic("unet_conv_tc")
+    traffic, traffic_src = ncu_traffic("unet_conv_tc", chunk)
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel / conv3x3_vr_kernel / conv3x3_rs_kernel (UNet layers, tcgen05 implicit GEMM)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -878,8 +878,8 @@ def run_pipeline(args):
     # second named metric of BASELINE.json: warp + 64-square crop against the measured HBM copy bandwidth
     warp_ms = stages["warp"]
     warp_gbs = WARP_BYTES_PER_BOARD * B * args.steps / (warp_ms / 1000.0) / 1e9 if warp_ms > 0 else 0.0
-    wtraffic, wtraffic_src = ncu_traffic("warp_board")
     groups = (B + 8 * chunk - 1) // (8 * chunk)
+    wtraffic, wtraffic_src = ncu_traffic("warp_board", (B + groups - 1) // groups)   # one warp launch per group of 8 chunks
     roofline_warp = {"bound": "hbm", "kernel": "k_warp_board (+ k_homography)", "achieved": warp_gbs, "peak": peak_hbm, "unit": "GB/s",
                      "frac": warp_gbs / peak_hbm if peak_hbm else None, "traffic": wtraffic, "traffic_source": wtraffic_src,
                      "launches": 2 * groups * args.steps, "avg_launch_ms": warp_ms / max(1, groups * args.steps),

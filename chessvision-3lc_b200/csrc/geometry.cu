@@ -1092,6 +1092,7 @@ constexpr int kWpSmem = kWpRows * kWpStride * 4;
 constexpr int kWpFrac = 13;          // bits carried below 1/32 px
 constexpr int kWpBand = 8;           // guard band in 2^-13 units (covers an error below 4)
 constexpr int kWpMagicBits = 0x4B400000;   // 1.5 * 2^23 as float bits
+__constant__ uint32_t kWpInv[8] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363};   // ceil(2^16 / n)
 constexpr int kWpFar = 1 << 20;      // footprint bound of a segment outside the float32 path: the tile does not fit
 
 // The literal arithmetic for one destination pixel from global memory; returns the gray value.
@@ -1209,40 +1210,47 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
     uint32_t redo = fast ? 0u : 0xffffu;   // pixels of the segment that need the literal arithmetic
     const uint32_t patch_addr = static_cast<uint32_t>(__cvta_generic_to_shared(patch));
     if (fits) {
-        // 48-byte groups of the footprint: a thread's (up to three) groups are requested together, so that one round of
-        // DRAM latency covers the whole patch instead of one round per group
+        // 48-byte groups of the footprint: a thread's groups are requested together, so that one round of DRAM latency covers
+        // the whole patch instead of one round per group.  Two groups per thread hold 512 (a footprint of up to ~1.2 source
+        // pixels per destination pixel); a third round follows for larger ones.
         const int n_groups = nrows * ncol16;   // <= 88 * 7 = 616 <= 3 * 256
-        uint4 ld[3][3];
-        int gr[3], gc[3];
+        const unsigned inv = kWpInv[ncol16];   // g / ncol16 == (g * inv) >> 16 for g < 9362
+        auto stage = [&](auto n_const, int g0) {
+            constexpr int kN = decltype(n_const)::value;
+            uint4 ld[kN][3];
+            int gr[kN], gc[kN];
 #pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            const int g = t + 256 * u;
-            gr[u] = g / ncol16;
-            gc[u] = g - gr[u] * ncol16;
-            const int gy = y_lo + gr[u], gx = x_lo + 16 * gc[u];
-            const bool in = g < n_groups && gy >= 0 && gy < H && gx >= 0 && gx < W;
-            const uint4* s4 = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(in ? gy : 0) * W + (in ? gx : 0)) * 3);
-            ld[u][0] = in ? __ldg(s4) : make_uint4(0, 0, 0, 0);
-            ld[u][1] = in ? __ldg(s4 + 1) : make_uint4(0, 0, 0, 0);
-            ld[u][2] = in ? __ldg(s4 + 2) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-            if (t + 256 * u >= n_groups) break;
-            const uint32_t w[12] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w,
-                                    ld[u][2].x, ld[u][2].y, ld[u][2].z, ld[u][2].w};
-            uint32_t o[16];   // pixel k = bytes 3k..3k+2 -> (B,G,R,x); the top byte is never read
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                o[4 * k + 0] = w[3 * k];
-                o[4 * k + 1] = __byte_perm(w[3 * k], w[3 * k + 1], 0x6543);
-                o[4 * k + 2] = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
-                o[4 * k + 3] = w[3 * k + 2] >> 8;
+            for (int u = 0; u < kN; ++u) {
+                const int g = g0 + 256 * u;
+                gr[u] = static_cast<int>((static_cast<unsigned>(g) * inv) >> 16);
+                gc[u] = g - gr[u] * ncol16;
+                const int gy = y_lo + gr[u], gx = x_lo + 16 * gc[u];
+                const bool in = g < n_groups && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                const uint4* s4 = reinterpret_cast<const uint4*>(src + (static_cast<size_t>(in ? gy : 0) * W + (in ? gx : 0)) * 3);
+                ld[u][0] = in ? __ldg(s4) : make_uint4(0, 0, 0, 0);
+                ld[u][1] = in ? __ldg(s4 + 1) : make_uint4(0, 0, 0, 0);
+                ld[u][2] = in ? __ldg(s4 + 2) : make_uint4(0, 0, 0, 0);
             }
-            uint4* d4 = reinterpret_cast<uint4*>(patch + gr[u] * kWpStride + 16 * gc[u]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) d4[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
-        }
+            for (int u = 0; u < kN; ++u) {
+                if (g0 + 256 * u >= n_groups) break;
+                const uint32_t w[12] = {ld[u][0].x, ld[u][0].y, ld[u][0].z, ld[u][0].w, ld[u][1].x, ld[u][1].y, ld[u][1].z, ld[u][1].w,
+                                        ld[u][2].x, ld[u][2].y, ld[u][2].z, ld[u][2].w};
+                uint32_t o[16];   // pixel k = bytes 3k..3k+2 -> (B,G,R,x); the top byte is never read
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    o[4 * k + 0] = w[3 * k];
+                    o[4 * k + 1] = __byte_perm(w[3 * k], w[3 * k + 1], 0x6543);
+                    o[4 * k + 2] = __byte_perm(w[3 * k + 1], w[3 * k + 2], 0x5432);
+                    o[4 * k + 3] = w[3 * k + 2] >> 8;
+                }
+                uint4* d4 = reinterpret_cast<uint4*>(patch + gr[u] * kWpStride + 16 * gc[u]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d4[k] = make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+            }
+        };
+        stage(std::integral_constant<int, 2>{}, t);
+        if (n_groups > 512) stage(std::integral_constant<int, 1>{}, t + 512);
     }
     __syncthreads();
     constexpr float kMagic = 12582912.0f;
@@ -1258,7 +1266,8 @@ __global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict
             const float s = d * r;
             const int ix = __float_as_int(fmaf(fBx, s, kMagic)) + Cx, iy = __float_as_int(fmaf(fBy, s, kMagic)) + Cy;
             if ((ix & ((1 << kWpFrac) - 1)) < kWpBand || (iy & ((1 << kWpFrac) - 1)) < kWpBand) redo |= 1u << (4 * g + i);
-            packed |= warp_gather(patch_addr, ix >> kWpFrac, iy >> kWpFrac) << (8 * (3 - i));
+            // gray (< 256) into byte 3 - i
+            packed = __byte_perm(packed, warp_gather(patch_addr, ix >> kWpFrac, iy >> kWpFrac), i == 0 ? 0x4210 : i == 1 ? 0x3410 : i == 2 ? 0x3240 : 0x3214);
         }
         out[3 - g] = packed;
     }
