@@ -1116,7 +1116,8 @@ __device__ __noinline__ uint32_t warp_px_exact(const uint8_t* __restrict__ src, 
 // Four taps of the staged patch -> gray.  Xl, Yl: patch coordinates in 1/32 px (tap column Xl >> 5, fraction Xl & 31).
 __device__ __forceinline__ uint32_t warp_gather(uint32_t patch_addr, int Xl, int Yl) {
     uint32_t p00, p01, p10, p11;
-    const uint32_t addr = patch_addr + static_cast<uint32_t>(Yl >> 5) * (kWpStride * 4) + (static_cast<uint32_t>(Xl >> 5) << 2);
+    uint32_t addr;   // row base + 4 * column as one multiply-add (the compiler's own form masks and adds separately)
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"(Xl >> 5), "r"(patch_addr + static_cast<uint32_t>(Yl >> 5) * (kWpStride * 4)));
     asm("ld.shared.u32 %0, [%4];\n\tld.shared.u32 %1, [%4+4];\n\tld.shared.u32 %2, [%4+%5];\n\tld.shared.u32 %3, [%4+%6];"
         : "=r"(p00), "=r"(p01), "=r"(p10), "=r"(p11)
         : "r"(addr), "n"(kWpStride * 4), "n"(kWpStride * 4 + 4));
@@ -1131,7 +1132,7 @@ __device__ __forceinline__ uint32_t warp_gather(uint32_t patch_addr, int Xl, int
     return (3735u * bl + 19235u * gn + 9798u * rd + 16384u) >> 15;
 }
 
-__global__ void __launch_bounds__(256, 4) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
+__global__ void __launch_bounds__(256, 5) k_warp_board(const uint8_t* __restrict__ img, const double* __restrict__ minv,
                                                     const uint8_t* __restrict__ found, uint8_t* __restrict__ board,
                                                     uint8_t* __restrict__ squares, int H, int W) {
     extern __shared__ __align__(16) uint8_t wsm[];
