@@ -146,6 +146,37 @@ def test_host_path_with_small_groups(golden, monkeypatch):
         eng.close()
 
 
+def test_results_do_not_depend_on_batch_size_or_position(trained_engine, golden):
+    """Size-independent property at the bench's chunk size (configs[3] shards 65,536 boards into chunks of 296): 1,184 boards
+    drawn with repetition from data/test, in random order, through a context with 296-board chunks -- every board's outputs
+    must equal what the 16-board context returns for that image alone-ish (integers and FEN bytes exactly, probabilities and
+    logits to fp16 noise at most; measured: identical)."""
+    from chessvision import _native
+    _, _, imgs = golden
+    base = trained_engine.image_to_fen(torch.from_numpy(imgs).cuda(), trained_engine.alloc_outputs(len(imgs), full=True))
+    base = {k: v.cpu().numpy() for k, v in base.items()}
+    rng = np.random.default_rng(20261018)
+    idx = rng.integers(0, len(imgs), 1184)
+    eng = _native.Engine(0, max_batch=296)
+    try:
+        eng.load_unet(load_checkpoint(WEIGHTS / "best_extractor.pth"))
+        eng.load_resnet18(load_checkpoint(WEIGHTS / "best_classifier.pth"))
+        big_in = torch.from_numpy(imgs[idx]).cuda()
+        out = eng.image_to_fen(big_in, eng.alloc_outputs(len(idx), full=True))
+        torch.cuda.synchronize()
+        again = eng.image_to_fen(big_in, eng.alloc_outputs(len(idx), full=True))     # idempotence of the context (workspaces reused)
+        torch.cuda.synchronize()
+        for k, v in out.items():
+            got, want = v.cpu().numpy(), base[k][idx]
+            assert np.array_equal(got, again[k].cpu().numpy()), f"output '{k}' differs between two passes over the same batch"
+            if got.dtype.kind == "f":
+                assert np.allclose(got, want, atol=2e-3, rtol=0), f"output '{k}': max abs difference {np.abs(got - want).max()}"
+            else:
+                assert np.array_equal(got, want), f"output '{k}' depends on the batch: {(got != want).reshape(len(idx), -1).any(axis=1).sum()} boards differ"
+    finally:
+        eng.close()
+
+
 def test_python_api_process_image(golden):
     """The drop-in class, as the reference's tests use it (tests/test_chessvision.py:45-116): structural checks plus
     agreement with the golden FEN for the reference's own fixture image."""
