@@ -1,5 +1,6 @@
 // Integer / geometric half of the image->FEN path on the device (compiled with -fmad=false: every float64 result
-// below must equal what OpenCV computes on the CPU, so no contraction is allowed).
+// below must equal what OpenCV computes on the CPU, so no contraction is allowed; explicit fma() calls appear only
+// where accuracy rather than OpenCV's order of roundings matters -- the float64 segment anchors of k_warp_board).
 //
 //   k_mask_to_quad   ChessVision._find_quadrangle (core.py:358-379): cv2.findContours(RETR_CCOMP, TC89_KCOS) +
 //                    _filter_contours (core.py:382-404) + arcLength/approxPolyDP (core.py:372-377) +
