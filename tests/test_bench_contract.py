@@ -31,3 +31,19 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     p = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_roofline_traffic_cites_the_committed_capture_and_scales_with_the_launch_size():
+    """`roofline.traffic` is read from profiles/<round>/traffic.json (written from the ncu --set full csv of one 148-board
+    pass) and scaled to the boards one launch of the bench covers; both kernel classes the pipeline line cites must be there."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_under_test", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for cls in ("unet_conv_tc", "warp_board"):
+        per148, src = bench.ncu_traffic(cls)
+        assert per148 and per148 > 0 and "traffic.json" in src and "148 boards per launch" in src, (cls, src)
+        scaled, src2 = bench.ncu_traffic(cls, 296)
+        assert abs(scaled - 2 * per148) < 1e-6 * per148 and "scaled to 296 boards per launch" in src2
+    # algorithmic bytes of the warp stage (DESIGN.md section 4): 512x512x3 read + 512x512 written per board
+    assert bench.WARP_BYTES_PER_BOARD == 512 * 512 * 3 + 512 * 512
